@@ -1,0 +1,178 @@
+/* admm_b200.h -- C-ABI of the B200-native ADMM-elastic step.
+ *
+ * One opaque solver handle owns all device memory of ONE GPU.  Every entry point takes plain
+ * pointers and sizes (host memory, borrowed for the duration of the call), returns 0 on success
+ * and non-zero on failure with a message available from admm_b200_last_error().
+ *
+ * The library is a drop-in for the hot path of the reference (mattoverby/admm-elastic @ c6c09a3):
+ * the body of admm::Solver::step() (src/Solver.cpp:35-110) -- per-element EnergyTerm::update
+ * (src/EnergyTerm.hpp:130-140), the right-hand side assembly (src/Solver.cpp:98) and the global
+ * solve LinearSolver::solve (src/LinearSolver.hpp:48, src/NodalMultiColorGS.hpp:60-146,
+ * src/LinearSolver.hpp:87-90, src/UzawaCG.hpp:57-125).  The host keeps the reference's plugin
+ * surface (admm::Solver / EnergyTerm / LinearSolver); what it harvests from that surface is
+ * handed over through the calls below.  INTEGRATION.md shows the reference-side binding.
+ *
+ * There is NO CPU fallback: every compute entry point fails if no CUDA device is usable.
+ */
+#ifndef ADMM_B200_H
+#define ADMM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct admm_b200_solver admm_b200_solver;
+
+/* Constitutive model of a batch of tets.  Replaces the dynamic type of the reference's terms:
+ * TetEnergyTerm (src/TetEnergyTerm.hpp:57), NeoHookeanTet (:117), StVKTet (:146), SplineTet (:179)
+ * with the three built-in xu::Spline materials (src/XuSpline.hpp:48-94). */
+enum admm_b200_tet_model {
+	ADMM_B200_TET_LINEAR = 0,
+	ADMM_B200_TET_NEOHOOKEAN = 1,
+	ADMM_B200_TET_STVK = 2,
+	ADMM_B200_TET_SPLINE_NH = 3,
+	ADMM_B200_TET_SPLINE_STVK = 4,
+	ADMM_B200_TET_SPLINE_COROT = 5
+};
+
+/* Settings::linsolver (src/Solver.hpp:46): 0=LDLT, 1=NodalMultiColorGS, 2=UzawaCG */
+enum admm_b200_linsolver {
+	ADMM_B200_LDLT = 0,
+	ADMM_B200_MCGS = 1,
+	ADMM_B200_UZAWA = 2
+};
+
+/* Storage/arithmetic type of per-element data (z, u, Dm^-1, corner forces).  Node data
+ * (x, v, b) and the global solve are always fp64 on the device. */
+enum admm_b200_precision {
+	ADMM_B200_FP32 = 0,
+	ADMM_B200_FP64 = 1
+};
+
+/* Passive obstacles handled inside the Gauss-Seidel sweep (src/PassiveObject.hpp:32-64). */
+enum admm_b200_obstacle {
+	ADMM_B200_FLOOR = 0,   /* params: y                      (Floor,  src/PassiveObject.hpp:32-45) */
+	ADMM_B200_SPHERE = 1   /* params: cx, cy, cz, radius     (Sphere, src/PassiveObject.hpp:48-64) */
+};
+
+/* RuntimeData of the last step (src/Solver.hpp:54-61), times from CUDA events. */
+typedef struct admm_b200_runtime {
+	double global_ms;
+	double local_ms;
+	double collision_ms;
+	int inner_iters;
+} admm_b200_runtime;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Creates a solver on CUDA device `device`.  Fails (non-zero) when no CUDA device is present. */
+int admm_b200_create( int device, admm_b200_solver **out );
+void admm_b200_destroy( admm_b200_solver *s );
+/* Message of the last failure on this handle (or of the last failed create when s == NULL). */
+const char *admm_b200_last_error( const admm_b200_solver *s );
+/* All work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the solver's own stream). */
+int admm_b200_set_stream( admm_b200_solver *s, void *cuda_stream );
+int admm_b200_synchronize( admm_b200_solver *s );
+
+/* ---- scene hand-over (before finalize) ----------------------------------------------------- */
+
+/* Node state, replaces Solver::add_nodes / public m_x, m_v, m_masses (src/Solver.hpp:66-68,
+ * 127-141).  x, m: 3*n_nodes doubles (xyz interleaved; masses "scaled x3" as in the reference).
+ * v may be NULL (zeros; initialize() zeroes it, src/Solver.cpp:187). */
+int admm_b200_set_nodes( admm_b200_solver *s, int n_nodes, const double *x, const double *v, const double *m );
+
+/* A batch of n tets sharing one material.  Replaces what TetEnergyTerm's constructor and
+ * get_reduction compute (src/TetEnergyTerm.cpp:31-71):
+ *   idx[4e+c]          vertex c of tet e
+ *   dminv[9e+3c+r]     edges_inv(c,r), the inverse rest edge matrix, so F = Ds * edges_inv
+ *   weight[e]          get_weight() = sqrt(K*vol)
+ *   row_offset[e]      g_index, the first of the tet's 9 rows of D (src/EnergyTerm.hpp:117);
+ *                      only used to lay out debug_get("z"/"u") like the reference; may be NULL
+ *   mu, lambda         Lame parameters; kappa: compression term of the spline models. */
+int admm_b200_add_tets( admm_b200_solver *s, int n, const int *idx, const double *dminv, const double *weight,
+	int model, double mu, double lambda, double kappa, const int *row_offset );
+
+/* A batch of n triangles (TriEnergyTerm, src/TriEnergyTerm.cpp:29-101):
+ *   idx[3e+c]; restpose[4e+2c+r] = rest_pose(c,r) (2x2, F = [x1-x0, x2-x0] * rest_pose);
+ *   weight[e] = sqrt(K*area); limit_min/limit_max = Lame::limit_min/max (src/EnergyTerm.hpp:46). */
+int admm_b200_add_tris( admm_b200_solver *s, int n, const int *idx, const double *restpose, const double *weight,
+	double limit_min, double limit_max, const int *row_offset );
+
+/* Energy-based hard pins, SpringPin (src/SpringEnergyTerm.hpp:31-73), used with LDLT / Uzawa
+ * (src/Solver.cpp:190-196): idx[i], pos[3i..], weight[i] = sqrt(2*K_rubber).  Each pin reserves
+ * 6 rows of D of which 3 are live. */
+int admm_b200_add_pins( admm_b200_solver *s, int n, const int *idx, const double *pos, const double *weight, const int *row_offset );
+/* Per-frame update of the same pins: SpringPin::set_pin / set_active via Solver::set_pins
+ * (src/Solver.cpp:135-156).  pin i of this call addresses the i-th pin added. */
+int admm_b200_update_pins( admm_b200_solver *s, int n, const double *pos, const unsigned char *active );
+
+/* Hard pins of the Gauss-Seidel solver: ConstraintSet::pins consulted inside the sweep
+ * (src/NodalMultiColorGS.hpp:111-117).  May be called every frame with a different set. */
+int admm_b200_set_gs_pins( admm_b200_solver *s, int n, const int *idx, const double *pos );
+
+/* Passive obstacles tested per node inside the sweep, Collider::detect_passive
+ * (src/Collider.hpp:137-150); order of calls = order of passive_objs. */
+int admm_b200_add_obstacle( admm_b200_solver *s, int kind, const double *params );
+
+/* The constant global matrix A = M + dt^2 D^T W^2 D (src/Solver.cpp:226).  Every get_reduction of
+ * the reference couples x-x, y-y, z-z only, so A = L (x) I3 plus a diagonal: the host passes the
+ * n x n scalar matrix L in CSR (both triangles, WITHOUT the mass term) and the library adds the
+ * per-component masses to the diagonal. */
+int admm_b200_set_system( admm_b200_solver *s, int n, const int *rowptr, const int *cols, const double *vals );
+
+/* Colour -> node lists computed once on the host, graphcolor::color_matrix(A, colors, 3)
+ * (deps/mclscene/include/MCL/GraphColor.hpp:66-72) or any valid colouring. */
+int admm_b200_set_colors( admm_b200_solver *s, int n_colors, const int *offsets, const int *nodes );
+
+/* Prefactored L D L^T of P (L_scalar + M) P^T, replaces Cholesky::compute in
+ * LDLTSolver::update_system (src/LinearSolver.hpp:79-84): perm[new] = old, unit lower L in CSC
+ * without the diagonal (Lp, Li, Lx), D = diagonal.  Requires equal x/y/z masses per node. */
+int admm_b200_set_ldlt( admm_b200_solver *s, int n, const int *perm, const int *Lp, const int *Li, const double *Lx, const double *D );
+
+/* Ends the hand-over: Solver::initialize (src/Solver.cpp:167-261).  dt = Settings::timestep_s;
+ * gs_iters, gs_omega, gs_tol = NodalMultiColorGS::max_iters, m_omega, m_tol
+ * (src/NodalMultiColorGS.hpp:41-46; gs_tol <= 0 disables the residual test). */
+int admm_b200_finalize( admm_b200_solver *s, double dt, int linsolver, int gs_iters, double gs_omega, double gs_tol, int precision );
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* One Solver::step() (src/Solver.cpp:35-110) on device-resident state. runtime may be NULL. */
+int admm_b200_step( admm_b200_solver *s, int admm_iters, double gravity, admm_b200_runtime *runtime );
+/* The same with host state: uploads x, v (3n doubles each), steps, downloads them again -- what a
+ * caller that reads m_x after every step() sees (samples/utils/Application.hpp:274-299). */
+int admm_b200_step_host( admm_b200_solver *s, int admm_iters, double gravity, double *x, double *v, admm_b200_runtime *runtime );
+int admm_b200_upload_state( admm_b200_solver *s, const double *x, const double *v );
+int admm_b200_download_state( admm_b200_solver *s, double *x, double *v );
+
+/* ---- pieces of the path, for parity tests and micro-benchmarks ----------------------------- */
+
+/* prox() alone on n deformation gradients, column-major 9 doubles each, in the chosen precision:
+ * TetEnergyTerm::prox / HyperElasticTet::prox (src/TetEnergyTerm.cpp:73-92, 114-136). */
+int admm_b200_prox_tets( admm_b200_solver *s, int model, double mu, double lambda, double kappa,
+	int precision, int n, const double *z_in, double *z_out );
+/* TriEnergyTerm::prox (src/TriEnergyTerm.cpp:73-101), 6 doubles each. */
+int admm_b200_prox_tris( admm_b200_solver *s, double limit_min, double limit_max,
+	int precision, int n, const double *z_in, double *z_out );
+/* LinearSolver::solve alone: x (3n, in: warm start, out: solution), b (3n). Returns the solver's
+ * iteration count in *iters (NodalMultiColorGS returns the sweep count, LDLT 1). */
+int admm_b200_linsolve( admm_b200_solver *s, double *x, const double *b, int *iters );
+/* Copies an internal array to the host: "z", "u" (reference row layout, needs row_offset),
+ * "b", "x" (current iterate), "v".  n_out = capacity in doubles. */
+int admm_b200_debug_get( admm_b200_solver *s, const char *name, double *out, long long n_out );
+/* Keep z on the device (debug_get "z"); off by default because the path never re-reads z. */
+int admm_b200_set_debug( admm_b200_solver *s, int store_z );
+
+/* Device timing of the last `admm_b200_time_kernels` call: runs each kernel of one ADMM iteration
+ * `reps` times back to back and reports the average milliseconds of local (tet prox), assemble and
+ * global (solve) in out_ms[3].  Used by bench.py for the roofline numbers. */
+int admm_b200_time_kernels( admm_b200_solver *s, int reps, double *out_ms );
+
+/* Counts of kernels launched by this handle since creation (bench.py's gpu_launches). */
+long long admm_b200_launch_count( const admm_b200_solver *s );
+
+int admm_b200_version( void );
+
+#ifdef __cplusplus
+}
+#endif
+#endif
