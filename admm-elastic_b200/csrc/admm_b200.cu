@@ -1,0 +1,1066 @@
+// admm_b200.cu -- C-ABI (include/admm_b200.h) and host orchestration of the CUDA path.
+// One handle = one GPU.  No CPU fallback: every entry point that computes needs the device.
+#include "../../include/admm_b200.h"
+#include "kernels.cuh"
+#include "sptrsv.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace admmb200;
+
+namespace {
+
+std::string g_create_error;
+
+#define CK(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess) {                                                                   \
+			throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+		}                                                                                          \
+	} while (0)
+
+template <typename T> struct DevBuf {
+	T *p = nullptr;
+	size_t n = 0;
+	void alloc(size_t count) {
+		release();
+		n = count;
+		if (count) { CK(cudaMalloc((void **)&p, count * sizeof(T))); }
+	}
+	void zero(cudaStream_t s) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+	void upload(const T *h, size_t count, cudaStream_t s) {
+		if (count > n) alloc(count);
+		if (count) CK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+	}
+	void upload(const std::vector<T> &h, cudaStream_t s) { alloc(h.size()); upload(h.data(), h.size(), s); }
+	void release() { if (p) { cudaFree(p); p = nullptr; } n = 0; }
+	~DevBuf() { release(); }
+	DevBuf() {}
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+};
+
+inline int pad32(int n) { return (n + 31) & ~31; }
+
+struct TetBatchH {
+	int n = 0, n_pad = 0, model = 0;
+	double mu = 0, lambda = 0, kappa = 0;
+	std::vector<int> idx;      // 4n
+	std::vector<double> dminv; // 9n
+	std::vector<double> w;     // n
+	std::vector<int> row_off;  // n or empty
+	size_t slot_base = 0;
+	DevBuf<int4> d_idx;
+	DevBuf<char> d_dminv, d_wdt2, d_u, d_z; // element precision, raw bytes
+};
+struct TriBatchH {
+	int n = 0, n_pad = 0;
+	double limit_min = -100, limit_max = 100;
+	std::vector<int> idx;      // 3n
+	std::vector<double> rest;  // 4n
+	std::vector<double> w;
+	std::vector<int> row_off;
+	size_t slot_base = 0;
+	DevBuf<int4> d_idx;
+	DevBuf<char> d_rest, d_wdt2, d_u, d_z;
+};
+struct PinsH {
+	int n = 0;
+	std::vector<int> idx;
+	std::vector<double> pos, w;
+	std::vector<unsigned char> active;
+	std::vector<int> row_off;
+	DevBuf<int> d_idx;
+	DevBuf<double> d_pos, d_wdt2, d_u, d_z;
+	DevBuf<unsigned char> d_active;
+	DevBuf<double4> d_f;
+};
+
+} // namespace
+
+struct admm_b200_solver {
+	int device = 0;
+	int n_sms = 0;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	std::string err;
+	long long launches = 0;
+
+	// nodes
+	int n_nodes = 0;
+	std::vector<double> h_m; // 3n
+	DevBuf<double4> x, v, cx, mxbar, b, m;
+	DevBuf<double> stage3, stage3b; // 3n staging for AoS host copies
+
+	// elements
+	std::vector<TetBatchH *> tets;
+	std::vector<TriBatchH *> tris;
+	PinsH pins;
+	size_t n_slots = 0;
+	DevBuf<char> f; // Vec4<E> per slot
+	DevBuf<int> inc_off, inc_slot;
+
+	// system
+	int sys_n = 0;
+	std::vector<int> L_rowptr, L_cols;
+	std::vector<double> L_vals;
+	std::vector<int> color_off, color_nodes;
+	int n_colors = 0;
+	// gs pins / obstacles
+	std::vector<int> gs_pin_idx;
+	std::vector<double> gs_pin_pos;
+	DevBuf<int> d_pin_slot;
+	DevBuf<double> d_pin_pos;
+	std::vector<Obstacle> obstacles;
+
+	// mcgs device
+	int gs_lanes = 4;
+	DevBuf<int> gs_color_first, gs_slice_ptr, gs_slice_node, gs_ell_col;
+	DevBuf<double> gs_ell_val, gs_diag, gs_resid;
+	DevBuf<unsigned int> barrier;
+	DevBuf<int> gs_iters_done, iter_log;
+	int gs_grid = 0;
+	size_t gs_nnz = 0, gs_ell_entries = 0;
+
+	// ldlt
+	bool have_ldlt = false;
+	int ld_n = 0;
+	std::vector<int> ld_perm, ld_Lp, ld_Li;
+	std::vector<double> ld_Lx, ld_D;
+	DevBuf<int> d_ld_perm, d_fwd_level_ptr, d_fwd_rows, d_fwd_rowptr, d_fwd_cols, d_bwd_level_ptr, d_bwd_rows, d_bwd_rowptr, d_bwd_cols;
+	DevBuf<double> d_fwd_vals, d_bwd_vals, d_ld_D;
+	DevBuf<double4> d_ld_y;
+	int ld_levels_fwd = 0, ld_levels_bwd = 0, ld_grid = 0, ld_lanes = 4;
+
+	// settings
+	bool finalized = false;
+	double dt = 1.0 / 24.0;
+	int linsolver = 0, gs_iters = 30, precision = 0;
+	double gs_omega = 1.9, gs_tol = 1e-10;
+	bool store_z = false;
+
+	// events
+	std::vector<cudaEvent_t> events;
+
+	~admm_b200_solver() {
+		for (auto t : tets) delete t;
+		for (auto t : tris) delete t;
+		for (auto e : events) cudaEventDestroy(e);
+		if (own_stream) cudaStreamDestroy(own_stream);
+	}
+};
+
+namespace {
+
+typedef admm_b200_solver S;
+
+template <typename F> int guard(S *s, F fn)
+{
+	try {
+		if (s) CK(cudaSetDevice(s->device));
+		fn();
+		return 0;
+	} catch (std::exception &e) {
+		if (s) s->err = e.what(); else g_create_error = e.what();
+		return 1;
+	}
+}
+
+inline void require(bool c, const char *msg) { if (!c) throw std::runtime_error(msg); }
+
+template <typename E> void upload_soa(DevBuf<char> &dst, const std::vector<double> &src, int n, int n_pad, int k, cudaStream_t st, double scale_unused = 1.0)
+{
+	// src is AoS [n][k] doubles -> dst SoA [k][n_pad] of E
+	std::vector<E> tmp((size_t)k * n_pad, E(0));
+	for (int e = 0; e < n; ++e)
+		for (int j = 0; j < k; ++j) tmp[(size_t)j * n_pad + e] = E(src[(size_t)e * k + j]);
+	dst.alloc(tmp.size() * sizeof(E));
+	CK(cudaMemcpyAsync(dst.p, tmp.data(), tmp.size() * sizeof(E), cudaMemcpyHostToDevice, st));
+	CK(cudaStreamSynchronize(st)); // tmp dies at scope exit
+}
+
+// ------------------------------------------------------------------------------------------
+// local-step launches
+// ------------------------------------------------------------------------------------------
+template <typename E, int MODEL> void launch_tet_model(S *s, TetBatchH *t)
+{
+	TetBatch<E> tb;
+	tb.n = t->n; tb.n_pad = t->n_pad;
+	tb.idx = t->d_idx.p;
+	tb.dminv = (const E *)t->d_dminv.p;
+	tb.wdt2 = (const E *)t->d_wdt2.p;
+	tb.u = (E *)t->d_u.p;
+	tb.z = (E *)t->d_z.p;
+	tb.f = (typename Vec4<E>::type *)s->f.p + t->slot_base;
+	double K = t->lambda + (2.0 / 3.0) * t->mu; // Lame::bulk_modulus (src/EnergyTerm.hpp:41)
+	tb.mat.a = E(t->mu / K); tb.mat.l = E(t->lambda / K); tb.mat.kap = E(t->kappa / K);
+	const int threads = 128;
+	int blocks = (t->n + threads - 1) / threads;
+	if (s->store_z && t->d_z.p) tet_local_kernel<E, MODEL, true><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	else tet_local_kernel<E, MODEL, false><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	CK(cudaGetLastError());
+	s->launches++;
+}
+
+template <typename E> void launch_tet(S *s, TetBatchH *t)
+{
+	switch (t->model) {
+	case TET_LINEAR: launch_tet_model<E, TET_LINEAR>(s, t); break;
+	case TET_NEOHOOKEAN: launch_tet_model<E, TET_NEOHOOKEAN>(s, t); break;
+	case TET_STVK: launch_tet_model<E, TET_STVK>(s, t); break;
+	case TET_SPLINE_NH: launch_tet_model<E, TET_SPLINE_NH>(s, t); break;
+	case TET_SPLINE_STVK: launch_tet_model<E, TET_SPLINE_STVK>(s, t); break;
+	case TET_SPLINE_COROT: launch_tet_model<E, TET_SPLINE_COROT>(s, t); break;
+	default: throw std::runtime_error("unknown tet model");
+	}
+}
+
+template <typename E> void launch_tri(S *s, TriBatchH *t)
+{
+	TriBatch<E> tb;
+	tb.n = t->n; tb.n_pad = t->n_pad;
+	tb.idx = t->d_idx.p;
+	tb.rest = (const E *)t->d_rest.p;
+	tb.wdt2 = (const E *)t->d_wdt2.p;
+	tb.u = (E *)t->d_u.p;
+	tb.z = (E *)t->d_z.p;
+	tb.f = (typename Vec4<E>::type *)s->f.p + t->slot_base;
+	tb.limit_min = E(t->limit_min); tb.limit_max = E(t->limit_max);
+	const int threads = 128;
+	int blocks = (t->n + threads - 1) / threads;
+	if (s->store_z && t->d_z.p) tri_local_kernel<E, true><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	else tri_local_kernel<E, false><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	CK(cudaGetLastError());
+	s->launches++;
+}
+
+void launch_pins(S *s)
+{
+	if (!s->pins.n) return;
+	PinBatch pb;
+	pb.n = s->pins.n; pb.idx = s->pins.d_idx.p; pb.pos = s->pins.d_pos.p; pb.active = s->pins.d_active.p;
+	pb.wdt2 = s->pins.d_wdt2.p; pb.u = s->pins.d_u.p; pb.z = s->pins.d_z.p; pb.f = s->pins.d_f.p;
+	pin_local_kernel<<<(pb.n + 127) / 128, 128, 0, s->stream>>>(pb, s->cx.p);
+	CK(cudaGetLastError());
+	s->launches++;
+}
+
+void launch_local(S *s)
+{
+	for (auto t : s->tets) { if (s->precision == ADMM_B200_FP64) launch_tet<double>(s, t); else launch_tet<float>(s, t); }
+	for (auto t : s->tris) { if (s->precision == ADMM_B200_FP64) launch_tri<double>(s, t); else launch_tri<float>(s, t); }
+	launch_pins(s);
+}
+
+void launch_assemble(S *s)
+{
+	int n = s->n_nodes;
+	if (s->precision == ADMM_B200_FP64)
+		assemble_kernel<double><<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->inc_off.p, s->inc_slot.p, (const double4 *)s->f.p, s->pins.d_f.p, s->mxbar.p, s->b.p);
+	else
+		assemble_kernel<float><<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->inc_off.p, s->inc_slot.p, (const float4 *)s->f.p, s->pins.d_f.p, s->mxbar.p, s->b.p);
+	CK(cudaGetLastError());
+	s->launches++;
+}
+
+// ------------------------------------------------------------------------------------------
+// global solve launches
+// ------------------------------------------------------------------------------------------
+template <int T> void mcgs_launch_T(S *s, McgsParams &P)
+{
+	void *args[] = {&P};
+	CK(cudaLaunchCooperativeKernel((void *)mcgs_kernel<T>, dim3(s->gs_grid), dim3(512), args, 0, s->stream));
+}
+template <int T> int mcgs_occupancy()
+{
+	int nb = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mcgs_kernel<T>, 512, 0));
+	return nb;
+}
+
+void launch_mcgs(S *s)
+{
+	McgsParams P;
+	P.n_nodes = s->n_nodes; P.n_colors = s->n_colors; P.iters = s->gs_iters; P.omega = s->gs_omega;
+	P.tol2 = s->gs_tol > 0 ? s->gs_tol * s->gs_tol : 0.0;
+	P.color_first_slice = s->gs_color_first.p; P.slice_ptr = s->gs_slice_ptr.p; P.slice_node = s->gs_slice_node.p;
+	P.ell_col = s->gs_ell_col.p; P.ell_val = s->gs_ell_val.p; P.diag = s->gs_diag.p;
+	P.pin_slot = s->d_pin_slot.p; P.pin_pos = s->d_pin_pos.p; P.has_pins = s->gs_pin_idx.empty() ? 0 : 1;
+	P.n_obstacles = (int)s->obstacles.size();
+	for (int i = 0; i < P.n_obstacles; ++i) P.obs[i] = s->obstacles[i];
+	P.x = s->cx.p; P.b = s->b.p; P.barrier = s->barrier.p; P.resid = s->gs_resid.p; P.iters_done = s->gs_iters_done.p;
+	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
+	if (P.tol2 > 0) CK(cudaMemsetAsync(s->gs_resid.p, 0, s->gs_resid.n * sizeof(double), s->stream));
+	switch (s->gs_lanes) {
+	case 1: mcgs_launch_T<1>(s, P); break;
+	case 2: mcgs_launch_T<2>(s, P); break;
+	case 8: mcgs_launch_T<8>(s, P); break;
+	default: mcgs_launch_T<4>(s, P); break;
+	}
+	s->launches++;
+}
+
+template <int T> void ldlt_launch_T(S *s, LdltParams &P)
+{
+	void *args[] = {&P};
+	CK(cudaLaunchCooperativeKernel((void *)ldlt_solve_kernel<T>, dim3(s->ld_grid), dim3(512), args, 0, s->stream));
+}
+
+void launch_ldlt(S *s)
+{
+	LdltParams P;
+	P.n = s->ld_n; P.n_levels_fwd = s->ld_levels_fwd; P.n_levels_bwd = s->ld_levels_bwd;
+	P.perm = s->d_ld_perm.p;
+	P.fwd_level_ptr = s->d_fwd_level_ptr.p; P.fwd_rows = s->d_fwd_rows.p; P.fwd_rowptr = s->d_fwd_rowptr.p; P.fwd_cols = s->d_fwd_cols.p; P.fwd_vals = s->d_fwd_vals.p;
+	P.bwd_level_ptr = s->d_bwd_level_ptr.p; P.bwd_rows = s->d_bwd_rows.p; P.bwd_rowptr = s->d_bwd_rowptr.p; P.bwd_cols = s->d_bwd_cols.p; P.bwd_vals = s->d_bwd_vals.p;
+	P.dinv_unused = nullptr; P.D = s->d_ld_D.p; P.y = s->d_ld_y.p; P.b = s->b.p; P.x = s->cx.p; P.barrier = s->barrier.p;
+	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
+	switch (s->ld_lanes) {
+	case 1: ldlt_launch_T<1>(s, P); break;
+	case 2: ldlt_launch_T<2>(s, P); break;
+	case 8: ldlt_launch_T<8>(s, P); break;
+	default: ldlt_launch_T<4>(s, P); break;
+	}
+	s->launches++;
+}
+
+void launch_global(S *s)
+{
+	if (s->linsolver == ADMM_B200_MCGS) launch_mcgs(s);
+	else launch_ldlt(s); // LDLT, and UzawaCG with an empty constraint matrix (src/UzawaCG.hpp:78-81)
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize helpers
+// ------------------------------------------------------------------------------------------
+void build_incidence(S *s)
+{
+	int n = s->n_nodes;
+	std::vector<int> off(n + 1, 0);
+	size_t slots = 0;
+	for (auto t : s->tets) { t->slot_base = slots; slots += (size_t)4 * t->n; for (int i = 0; i < 4 * t->n; ++i) off[t->idx[i] + 1]++; }
+	for (auto t : s->tris) { t->slot_base = slots; slots += (size_t)3 * t->n; for (int i = 0; i < 3 * t->n; ++i) off[t->idx[i] + 1]++; }
+	for (int i = 0; i < s->pins.n; ++i) off[s->pins.idx[i] + 1]++;
+	require(slots < (size_t)0x7fffffff, "too many element corners for int32 slots");
+	s->n_slots = slots;
+	for (int i = 0; i < n; ++i) off[i + 1] += off[i];
+	std::vector<int> fill(off.begin(), off.end() - 1), slot(off[n]);
+	for (auto t : s->tets)
+		for (int e = 0; e < t->n; ++e)
+			for (int c = 0; c < 4; ++c) slot[fill[t->idx[4 * e + c]]++] = (int)(t->slot_base + 4 * (size_t)e + c);
+	for (auto t : s->tris)
+		for (int e = 0; e < t->n; ++e)
+			for (int c = 0; c < 3; ++c) slot[fill[t->idx[3 * e + c]]++] = (int)(t->slot_base + 3 * (size_t)e + c);
+	for (int i = 0; i < s->pins.n; ++i) slot[fill[s->pins.idx[i]]++] = (int)(0x80000000u | (unsigned)i);
+	s->inc_off.upload(off, s->stream);
+	s->inc_slot.upload(slot, s->stream);
+	CK(cudaStreamSynchronize(s->stream));
+}
+
+template <typename E> void upload_elements(S *s)
+{
+	const double dt2 = s->dt * s->dt;
+	for (auto t : s->tets) {
+		t->n_pad = pad32(t->n);
+		std::vector<int4> id(t->n);
+		for (int e = 0; e < t->n; ++e) id[e] = make_int4(t->idx[4 * e], t->idx[4 * e + 1], t->idx[4 * e + 2], t->idx[4 * e + 3]);
+		t->d_idx.upload(id, s->stream);
+		CK(cudaStreamSynchronize(s->stream));
+		upload_soa<E>(t->d_dminv, t->dminv, t->n, t->n_pad, 9, s->stream);
+		std::vector<double> w2(t->n);
+		for (int e = 0; e < t->n; ++e) w2[e] = dt2 * t->w[e] * t->w[e];
+		upload_soa<E>(t->d_wdt2, w2, t->n, t->n_pad, 1, s->stream);
+		t->d_u.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_u.zero(s->stream);
+		if (s->store_z) { t->d_z.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_z.zero(s->stream); }
+	}
+	for (auto t : s->tris) {
+		t->n_pad = pad32(t->n);
+		std::vector<int4> id(t->n);
+		for (int e = 0; e < t->n; ++e) id[e] = make_int4(t->idx[3 * e], t->idx[3 * e + 1], t->idx[3 * e + 2], 0);
+		t->d_idx.upload(id, s->stream);
+		CK(cudaStreamSynchronize(s->stream));
+		upload_soa<E>(t->d_rest, t->rest, t->n, t->n_pad, 4, s->stream);
+		std::vector<double> w2(t->n);
+		for (int e = 0; e < t->n; ++e) w2[e] = dt2 * t->w[e] * t->w[e];
+		upload_soa<E>(t->d_wdt2, w2, t->n, t->n_pad, 1, s->stream);
+		t->d_u.alloc((size_t)6 * t->n_pad * sizeof(E)); t->d_u.zero(s->stream);
+		if (s->store_z) { t->d_z.alloc((size_t)6 * t->n_pad * sizeof(E)); t->d_z.zero(s->stream); }
+	}
+	s->f.alloc(std::max<size_t>(s->n_slots, 1) * sizeof(typename Vec4<E>::type));
+	s->f.zero(s->stream);
+}
+
+void upload_pins(S *s)
+{
+	PinsH &p = s->pins;
+	if (!p.n) return;
+	const double dt2 = s->dt * s->dt;
+	p.d_idx.upload(p.idx, s->stream);
+	p.d_pos.upload(p.pos, s->stream);
+	p.d_active.upload(p.active, s->stream);
+	std::vector<double> w2(p.n);
+	for (int i = 0; i < p.n; ++i) w2[i] = dt2 * p.w[i] * p.w[i];
+	p.d_wdt2.upload(w2, s->stream);
+	p.d_u.alloc((size_t)3 * p.n); p.d_u.zero(s->stream);
+	p.d_z.alloc((size_t)3 * p.n); p.d_z.zero(s->stream);
+	p.d_f.alloc(p.n); p.d_f.zero(s->stream);
+	CK(cudaStreamSynchronize(s->stream));
+}
+
+void upload_gs_pins(S *s)
+{
+	std::vector<int> slot(std::max(s->n_nodes, 1), -1);
+	for (size_t i = 0; i < s->gs_pin_idx.size(); ++i) {
+		require(s->gs_pin_idx[i] >= 0 && s->gs_pin_idx[i] < s->n_nodes, "gs pin index out of range");
+		slot[s->gs_pin_idx[i]] = (int)i;
+	}
+	s->d_pin_slot.upload(slot, s->stream);
+	std::vector<double> pos = s->gs_pin_pos;
+	if (pos.empty()) pos.resize(3, 0.0);
+	s->d_pin_pos.upload(pos, s->stream);
+	CK(cudaStreamSynchronize(s->stream));
+}
+
+void build_mcgs(S *s)
+{
+	const int n = s->n_nodes;
+	require(s->sys_n == n, "set_system: matrix size does not match the node count");
+	require(s->n_colors > 0, "NodalMultiColorGS needs colours (admm_b200_set_colors)");
+	const char *env = getenv("ADMM_B200_GS_LANES");
+	int T = env ? atoi(env) : 4;
+	if (T != 1 && T != 2 && T != 4 && T != 8) T = 4;
+	s->gs_lanes = T;
+	const int G = 32 / T;
+	std::vector<double> diag((size_t)3 * n, 0.0);
+	std::vector<char> seen(n, 0);
+	std::vector<int> color_first(s->n_colors + 1, 0), slice_ptr(1, 0), slice_node, ell_col;
+	std::vector<double> ell_val;
+	size_t nnz = 0;
+	for (int c = 0; c < s->n_colors; ++c) {
+		int k0 = s->color_off[c], k1 = s->color_off[c + 1];
+		for (int k = k0; k < k1; k += G) {
+			int width = 0;
+			int nodes[32];
+			for (int g = 0; g < G; ++g) {
+				int node = (k + g < k1) ? s->color_nodes[k + g] : -1;
+				nodes[g] = node;
+				if (node < 0) continue;
+				require(node < n, "colour list: node out of range");
+				require(!seen[node], "colour list: node appears twice");
+				seen[node] = 1;
+				int len = 0;
+				for (int q = s->L_rowptr[node]; q < s->L_rowptr[node + 1]; ++q)
+					if (s->L_cols[q] != node && s->L_vals[q] != 0.0) len++;
+				width = std::max(width, (len + T - 1) / T);
+			}
+			size_t base = ell_col.size();
+			ell_col.resize(base + (size_t)width * 32, 0);
+			ell_val.resize(base + (size_t)width * 32, 0.0);
+			for (int g = 0; g < G; ++g) {
+				int node = nodes[g];
+				slice_node.push_back(node);
+				if (node < 0) continue;
+				int j = 0;
+				for (int q = s->L_rowptr[node]; q < s->L_rowptr[node + 1]; ++q) {
+					int col = s->L_cols[q];
+					double val = s->L_vals[q];
+					if (col == node) { for (int d = 0; d < 3; ++d) diag[3 * (size_t)node + d] += val; continue; }
+					if (val == 0.0) continue;
+					require(col >= 0 && col < n, "set_system: column out of range");
+					int r = j / T, t = j % T;
+					ell_col[base + (size_t)r * 32 + g * T + t] = col;
+					ell_val[base + (size_t)r * 32 + g * T + t] = val;
+					++j; ++nnz;
+				}
+				// padding entries read the node itself with a zero coefficient
+				for (; j < width * T; ++j) { int r = j / T, t = j % T; ell_col[base + (size_t)r * 32 + g * T + t] = node; }
+			}
+			for (int g = 0; g < G; ++g) if (nodes[g] < 0) for (int r = 0; r < width; ++r) for (int t = 0; t < T; ++t) ell_col[base + (size_t)r * 32 + g * T + t] = nodes[0];
+			slice_ptr.push_back((int)(ell_col.size() / 32));
+		}
+		color_first[c + 1] = (int)slice_ptr.size() - 1;
+	}
+	for (int i = 0; i < n; ++i) require(seen[i], "colour list: a node has no colour");
+	for (int i = 0; i < n; ++i) for (int d = 0; d < 3; ++d) {
+		diag[3 * (size_t)i + d] += s->h_m[3 * (size_t)i + d];
+		// LinearSolver::is_zero (src/LinearSolver.hpp:51), "Zero on diagonal" (src/NodalMultiColorGS.hpp:203-206)
+		require(std::abs(diag[3 * (size_t)i + d]) >= 2.2250738585072014e-308, "**NodalMultiColorGS Error: Zero on diagonal");
+	}
+	s->gs_nnz = nnz; s->gs_ell_entries = ell_col.size();
+	s->gs_color_first.upload(color_first, s->stream);
+	s->gs_slice_ptr.upload(slice_ptr, s->stream);
+	s->gs_slice_node.upload(slice_node, s->stream);
+	s->gs_ell_col.upload(ell_col, s->stream);
+	s->gs_ell_val.upload(ell_val, s->stream);
+	s->gs_diag.upload(diag, s->stream);
+	s->gs_resid.alloc(s->gs_iters + 2);
+	s->gs_iters_done.alloc(1);
+	CK(cudaStreamSynchronize(s->stream));
+	int occ = 1;
+	switch (T) { case 1: occ = mcgs_occupancy<1>(); break; case 2: occ = mcgs_occupancy<2>(); break; case 8: occ = mcgs_occupancy<8>(); break; default: occ = mcgs_occupancy<4>(); }
+	require(occ >= 1, "mcgs kernel does not fit on an SM");
+	const char *envb = getenv("ADMM_B200_GS_BLOCKS_PER_SM");
+	int bps = envb ? std::max(1, std::min(occ, atoi(envb))) : 1;
+	s->gs_grid = s->n_sms * bps;
+	upload_gs_pins(s);
+}
+
+void build_ldlt(S *s)
+{
+	require(s->have_ldlt, "LDLT / UzawaCG need a factor (admm_b200_set_ldlt)");
+	const int n = s->ld_n;
+	require(n == s->n_nodes, "set_ldlt: factor size does not match the node count");
+	for (int i = 0; i < n; ++i) require(s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 1] && s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 2], "LDLT path needs equal x/y/z masses per node");
+	const std::vector<int> &Lp = s->ld_Lp, &Li = s->ld_Li;
+	const std::vector<double> &Lx = s->ld_Lx;
+	// CSR of strictly lower L (row gather for the forward solve)
+	std::vector<int> rp(n + 1, 0);
+	for (int j = 0; j < n; ++j) for (int q = Lp[j]; q < Lp[j + 1]; ++q) { require(Li[q] > j && Li[q] < n, "set_ldlt: L must be strictly lower, CSC"); rp[Li[q] + 1]++; }
+	for (int i = 0; i < n; ++i) rp[i + 1] += rp[i];
+	std::vector<int> fill(rp.begin(), rp.end() - 1), rc(Lp[n]);
+	std::vector<double> rv(Lp[n]);
+	for (int j = 0; j < n; ++j) for (int q = Lp[j]; q < Lp[j + 1]; ++q) { int i = Li[q]; rc[fill[i]] = j; rv[fill[i]] = Lx[q]; fill[i]++; }
+	// levels
+	std::vector<int> lf(n, 0), lb(n, 0);
+	int nlf = 0, nlb = 0;
+	for (int i = 0; i < n; ++i) { int l = 0; for (int q = rp[i]; q < rp[i + 1]; ++q) l = std::max(l, lf[rc[q]] + 1); lf[i] = l; nlf = std::max(nlf, l + 1); }
+	for (int j = n - 1; j >= 0; --j) { int l = 0; for (int q = Lp[j]; q < Lp[j + 1]; ++q) l = std::max(l, lb[Li[q]] + 1); lb[j] = l; nlb = std::max(nlb, l + 1); }
+	auto bucket = [&](const std::vector<int> &lev, int nl, std::vector<int> &ptr, std::vector<int> &rows) {
+		ptr.assign(nl + 1, 0);
+		for (int i = 0; i < n; ++i) ptr[lev[i] + 1]++;
+		for (int l = 0; l < nl; ++l) ptr[l + 1] += ptr[l];
+		std::vector<int> f2(ptr.begin(), ptr.end() - 1);
+		rows.resize(n);
+		for (int i = 0; i < n; ++i) rows[f2[lev[i]]++] = i;
+	};
+	std::vector<int> fptr, frows, bptr, brows;
+	bucket(lf, nlf, fptr, frows);
+	bucket(lb, nlb, bptr, brows);
+	s->ld_levels_fwd = nlf; s->ld_levels_bwd = nlb;
+	s->d_ld_perm.upload(s->ld_perm, s->stream);
+	s->d_fwd_level_ptr.upload(fptr, s->stream); s->d_fwd_rows.upload(frows, s->stream);
+	s->d_fwd_rowptr.upload(rp, s->stream); s->d_fwd_cols.upload(rc, s->stream); s->d_fwd_vals.upload(rv, s->stream);
+	s->d_bwd_level_ptr.upload(bptr, s->stream); s->d_bwd_rows.upload(brows, s->stream);
+	s->d_bwd_rowptr.upload(s->ld_Lp, s->stream); s->d_bwd_cols.upload(s->ld_Li, s->stream); s->d_bwd_vals.upload(s->ld_Lx, s->stream);
+	s->d_ld_D.upload(s->ld_D, s->stream);
+	s->d_ld_y.alloc(n);
+	CK(cudaStreamSynchronize(s->stream));
+	const char *env = getenv("ADMM_B200_LDLT_LANES");
+	int T = env ? atoi(env) : 4;
+	if (T != 1 && T != 2 && T != 4 && T != 8) T = 4;
+	s->ld_lanes = T;
+	s->ld_grid = s->n_sms;
+}
+
+cudaEvent_t get_event(S *s, size_t i)
+{
+	while (s->events.size() <= i) { cudaEvent_t e; CK(cudaEventCreate(&e)); s->events.push_back(e); }
+	return s->events[i];
+}
+
+void zero_duals(S *s)
+{
+	for (auto t : s->tets) t->d_u.zero(s->stream);
+	for (auto t : s->tris) t->d_u.zero(s->stream);
+	s->pins.d_u.zero(s->stream);
+}
+
+void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
+{
+	require(s->finalized, "step before finalize");
+	require(admm_iters >= 0 && (!rt || admm_iters <= (int)s->iter_log.n), "admm_iters out of range");
+	const int n = s->n_nodes;
+	const int nb = (n + 255) / 256;
+	step_begin_kernel<<<nb, 256, 0, s->stream>>>(n, s->dt, gravity, s->x.p, s->v.p, s->m.p, s->mxbar.p, s->cx.p);
+	CK(cudaGetLastError());
+	s->launches++;
+	zero_duals(s); // curr_u = 0 every step (src/Solver.cpp:71)
+	size_t ev = 0;
+	for (int it = 0; it < admm_iters; ++it) {
+		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
+		launch_local(s);
+		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
+		launch_assemble(s);
+		launch_global(s);
+		if (rt) {
+			CK(cudaEventRecord(get_event(s, ev++), s->stream));
+			if (s->linsolver == ADMM_B200_MCGS) {
+				// inner_iters += solve() (src/Solver.cpp:99): read back after the step
+				CK(cudaMemcpyAsync(s->iter_log.p + it, s->gs_iters_done.p, sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+			}
+		}
+	}
+	step_end_kernel<<<nb, 256, 0, s->stream>>>(n, s->dt, s->x.p, s->v.p, s->cx.p);
+	CK(cudaGetLastError());
+	s->launches++;
+	if (rt) {
+		CK(cudaStreamSynchronize(s->stream));
+		rt->global_ms = rt->local_ms = rt->collision_ms = 0; rt->inner_iters = 0;
+		for (int it = 0; it < admm_iters; ++it) {
+			float a = 0, b = 0;
+			CK(cudaEventElapsedTime(&a, s->events[3 * it], s->events[3 * it + 1]));
+			CK(cudaEventElapsedTime(&b, s->events[3 * it + 1], s->events[3 * it + 2]));
+			rt->local_ms += a; rt->global_ms += b;
+		}
+		if (s->linsolver == ADMM_B200_MCGS) {
+			std::vector<int> its(admm_iters);
+			CK(cudaMemcpy(its.data(), s->iter_log.p, sizeof(int) * admm_iters, cudaMemcpyDeviceToHost));
+			for (int i : its) rt->inner_iters += i;
+		} else rt->inner_iters = admm_iters; // LDLT / empty-C Uzawa return 1 per solve
+	}
+}
+
+void upload_state(S *s, const double *x, const double *v)
+{
+	const int n = s->n_nodes;
+	if (x) {
+		CK(cudaMemcpyAsync(s->stage3.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream));
+		pack3_to4_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->stage3.p, s->x.p);
+		s->launches++;
+	}
+	if (v) {
+		CK(cudaMemcpyAsync(s->stage3b.p, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream));
+		pack3_to4_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->stage3b.p, s->v.p);
+		s->launches++;
+	}
+	CK(cudaGetLastError());
+}
+
+void download_state(S *s, double *x, double *v)
+{
+	const int n = s->n_nodes;
+	if (x) {
+		unpack4_to3_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->x.p, s->stage3.p);
+		CK(cudaMemcpyAsync(x, s->stage3.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
+		s->launches++;
+	}
+	if (v) {
+		unpack4_to3_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->v.p, s->stage3b.p);
+		CK(cudaMemcpyAsync(v, s->stage3b.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
+		s->launches++;
+	}
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(s->stream));
+}
+
+template <typename E> void prox_tets_impl(S *s, int model, double mu, double lambda, double kappa, int n, const double *z_in, double *z_out)
+{
+	int n_pad = pad32(n);
+	std::vector<E> tmp((size_t)9 * n_pad, E(0));
+	for (int e = 0; e < n; ++e) for (int k = 0; k < 9; ++k) tmp[(size_t)k * n_pad + e] = E(z_in[(size_t)9 * e + k]);
+	DevBuf<E> d; d.upload(tmp, s->stream);
+	double K = lambda + (2.0 / 3.0) * mu;
+	Material<E> mat; mat.a = E(mu / K); mat.l = E(lambda / K); mat.kap = E(kappa / K);
+	int threads = 128, blocks = (n + threads - 1) / threads;
+	switch (model) {
+	case TET_LINEAR: tet_prox_only_kernel<E, TET_LINEAR><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
+	case TET_NEOHOOKEAN: tet_prox_only_kernel<E, TET_NEOHOOKEAN><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
+	case TET_STVK: tet_prox_only_kernel<E, TET_STVK><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
+	case TET_SPLINE_NH: tet_prox_only_kernel<E, TET_SPLINE_NH><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
+	case TET_SPLINE_STVK: tet_prox_only_kernel<E, TET_SPLINE_STVK><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
+	case TET_SPLINE_COROT: tet_prox_only_kernel<E, TET_SPLINE_COROT><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
+	default: throw std::runtime_error("unknown tet model");
+	}
+	CK(cudaGetLastError());
+	s->launches++;
+	CK(cudaMemcpyAsync(tmp.data(), d.p, tmp.size() * sizeof(E), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	for (int e = 0; e < n; ++e) for (int k = 0; k < 9; ++k) z_out[(size_t)9 * e + k] = double(tmp[(size_t)k * n_pad + e]);
+}
+
+template <typename E> void prox_tris_impl(S *s, double lmin, double lmax, int n, const double *z_in, double *z_out)
+{
+	int n_pad = pad32(n);
+	std::vector<E> tmp((size_t)6 * n_pad, E(0));
+	for (int e = 0; e < n; ++e) for (int k = 0; k < 6; ++k) tmp[(size_t)k * n_pad + e] = E(z_in[(size_t)6 * e + k]);
+	DevBuf<E> d; d.upload(tmp, s->stream);
+	int threads = 128, blocks = (n + threads - 1) / threads;
+	tri_prox_only_kernel<E><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, E(lmin), E(lmax));
+	CK(cudaGetLastError());
+	s->launches++;
+	CK(cudaMemcpyAsync(tmp.data(), d.p, tmp.size() * sizeof(E), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	for (int e = 0; e < n; ++e) for (int k = 0; k < 6; ++k) z_out[(size_t)6 * e + k] = double(tmp[(size_t)k * n_pad + e]);
+}
+
+// copies element-precision SoA rows back into the reference's row layout
+template <typename E> void gather_rows(S *s, bool want_z, double *out, long long n_out)
+{
+	auto fetch = [&](DevBuf<char> &buf, int k, int n, int n_pad, const std::vector<int> &row_off, const char *what) {
+		require(!row_off.empty(), "debug_get z/u needs row_offset for every batch");
+		require(buf.p != nullptr, what);
+		std::vector<E> tmp((size_t)k * n_pad);
+		CK(cudaMemcpy(tmp.data(), buf.p, tmp.size() * sizeof(E), cudaMemcpyDeviceToHost));
+		for (int e = 0; e < n; ++e) for (int j = 0; j < k; ++j) {
+			long long r = (long long)row_off[e] + j;
+			require(r < n_out, "debug_get: output too small");
+			out[r] = double(tmp[(size_t)j * n_pad + e]);
+		}
+	};
+	for (auto t : s->tets) fetch(want_z ? t->d_z : t->d_u, 9, t->n, t->n_pad, t->row_off, "z not stored: call admm_b200_set_debug(1) before finalize");
+	for (auto t : s->tris) fetch(want_z ? t->d_z : t->d_u, 6, t->n, t->n_pad, t->row_off, "z not stored: call admm_b200_set_debug(1) before finalize");
+	if (s->pins.n) {
+		require(!s->pins.row_off.empty(), "debug_get z/u needs row_offset for pins");
+		std::vector<double> tmp((size_t)3 * s->pins.n);
+		CK(cudaMemcpy(tmp.data(), want_z ? s->pins.d_z.p : s->pins.d_u.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+		for (int i = 0; i < s->pins.n; ++i) for (int j = 0; j < 3; ++j) {
+			long long r = (long long)s->pins.row_off[i] + j;
+			require(r < n_out, "debug_get: output too small");
+			out[r] = tmp[(size_t)3 * i + j];
+		}
+	}
+}
+
+} // namespace
+
+// ==========================================================================================
+// C-ABI
+// ==========================================================================================
+extern "C" {
+
+int admm_b200_version(void) { return 1; }
+
+int admm_b200_create(int device, admm_b200_solver **out)
+{
+	if (!out) { g_create_error = "null out pointer"; return 1; }
+	*out = nullptr;
+	S *s = nullptr;
+	int rc = guard(nullptr, [&]() {
+		int count = 0;
+		cudaError_t e = cudaGetDeviceCount(&count);
+		if (e != cudaSuccess || count == 0) throw std::runtime_error(std::string("no CUDA device available (") + cudaGetErrorString(e) + "): the B200 path has no CPU fallback");
+		if (device < 0 || device >= count) throw std::runtime_error("device index out of range");
+		CK(cudaSetDevice(device));
+		s = new S();
+		s->device = device;
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, device));
+		s->n_sms = prop.multiProcessorCount;
+		if (!prop.cooperativeLaunch) throw std::runtime_error("device lacks cooperative launch");
+		CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+		s->stream = s->own_stream;
+		s->barrier.alloc(4);
+		s->iter_log.alloc(4096);
+	});
+	if (rc) { delete s; return rc; }
+	*out = s;
+	return 0;
+}
+
+void admm_b200_destroy(admm_b200_solver *s)
+{
+	if (!s) return;
+	cudaSetDevice(s->device);
+	cudaDeviceSynchronize();
+	delete s;
+}
+
+const char *admm_b200_last_error(const admm_b200_solver *s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+int admm_b200_set_stream(admm_b200_solver *s, void *cuda_stream)
+{
+	return guard(s, [&]() {
+		CK(cudaStreamSynchronize(s->stream));
+		s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+	});
+}
+
+int admm_b200_synchronize(admm_b200_solver *s) { return guard(s, [&]() { CK(cudaStreamSynchronize(s->stream)); }); }
+
+int admm_b200_set_nodes(admm_b200_solver *s, int n_nodes, const double *x, const double *v, const double *m)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_nodes after finalize");
+		require(n_nodes >= 1 && x && m, "**Solver Error: Problem with node data!");
+		s->n_nodes = n_nodes;
+		s->h_m.assign(m, m + (size_t)3 * n_nodes);
+		s->x.alloc(n_nodes); s->v.alloc(n_nodes); s->cx.alloc(n_nodes); s->mxbar.alloc(n_nodes); s->b.alloc(n_nodes); s->m.alloc(n_nodes);
+		s->stage3.alloc((size_t)3 * n_nodes); s->stage3b.alloc(std::max<size_t>((size_t)3 * n_nodes, 4096));
+		s->v.zero(s->stream); s->b.zero(s->stream); s->mxbar.zero(s->stream);
+		upload_state(s, x, v);
+		CK(cudaStreamSynchronize(s->stream));
+		CK(cudaMemcpyAsync(s->stage3.p, m, sizeof(double) * 3 * n_nodes, cudaMemcpyHostToDevice, s->stream));
+		pack3_to4_kernel<<<(n_nodes + 255) / 256, 256, 0, s->stream>>>(n_nodes, s->stage3.p, s->m.p);
+		CK(cudaMemcpyAsync(s->cx.p, s->x.p, sizeof(double4) * n_nodes, cudaMemcpyDeviceToDevice, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+	});
+}
+
+int admm_b200_add_tets(admm_b200_solver *s, int n, const int *idx, const double *dminv, const double *weight,
+	int model, double mu, double lambda, double kappa, const int *row_offset)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "add_tets after finalize");
+		require(n >= 0 && (n == 0 || (idx && dminv && weight)), "add_tets: null input");
+		require(model >= 0 && model <= TET_SPLINE_COROT, "add_tets: unknown model");
+		if (n == 0) return;
+		for (int i = 0; i < 4 * n; ++i) require(idx[i] >= 0 && idx[i] < s->n_nodes, "add_tets: vertex index out of range (call set_nodes first)");
+		for (int e = 0; e < n; ++e) require(weight[e] > 0.0, "**EnergyTerm::get_reduction Error: Some weight leq 0");
+		TetBatchH *t = new TetBatchH();
+		t->n = n; t->model = model; t->mu = mu; t->lambda = lambda; t->kappa = kappa;
+		t->idx.assign(idx, idx + (size_t)4 * n);
+		t->dminv.assign(dminv, dminv + (size_t)9 * n);
+		t->w.assign(weight, weight + n);
+		if (row_offset) t->row_off.assign(row_offset, row_offset + n);
+		s->tets.push_back(t);
+	});
+}
+
+int admm_b200_add_tris(admm_b200_solver *s, int n, const int *idx, const double *restpose, const double *weight,
+	double limit_min, double limit_max, const int *row_offset)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "add_tris after finalize");
+		require(n >= 0 && (n == 0 || (idx && restpose && weight)), "add_tris: null input");
+		require(!(limit_min > 1.0), "**TriEnergyTerm Error: Strain limit min should be -inf to 1");
+		require(!(limit_max < 1.0), "**TriEnergyTerm Error: Strain limit max should be 1 to inf");
+		if (n == 0) return;
+		for (int i = 0; i < 3 * n; ++i) require(idx[i] >= 0 && idx[i] < s->n_nodes, "add_tris: vertex index out of range (call set_nodes first)");
+		for (int e = 0; e < n; ++e) require(weight[e] > 0.0, "**EnergyTerm::get_reduction Error: Some weight leq 0");
+		TriBatchH *t = new TriBatchH();
+		t->n = n; t->limit_min = limit_min; t->limit_max = limit_max;
+		t->idx.assign(idx, idx + (size_t)3 * n);
+		t->rest.assign(restpose, restpose + (size_t)4 * n);
+		t->w.assign(weight, weight + n);
+		if (row_offset) t->row_off.assign(row_offset, row_offset + n);
+		s->tris.push_back(t);
+	});
+}
+
+int admm_b200_add_pins(admm_b200_solver *s, int n, const int *idx, const double *pos, const double *weight, const int *row_offset)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "add_pins after finalize");
+		require(n >= 0 && (n == 0 || (idx && pos && weight)), "add_pins: null input");
+		for (int i = 0; i < n; ++i) require(idx[i] >= 0 && idx[i] < s->n_nodes, "add_pins: vertex index out of range");
+		PinsH &p = s->pins;
+		p.idx.insert(p.idx.end(), idx, idx + n);
+		p.pos.insert(p.pos.end(), pos, pos + (size_t)3 * n);
+		p.w.insert(p.w.end(), weight, weight + n);
+		p.active.insert(p.active.end(), n, (unsigned char)1);
+		if (row_offset) p.row_off.insert(p.row_off.end(), row_offset, row_offset + n);
+		p.n += n;
+	});
+}
+
+int admm_b200_update_pins(admm_b200_solver *s, int n, const double *pos, const unsigned char *active)
+{
+	return guard(s, [&]() {
+		PinsH &p = s->pins;
+		require(n == p.n, "update_pins: pin count differs from add_pins");
+		if (pos) p.pos.assign(pos, pos + (size_t)3 * n);
+		if (active) p.active.assign(active, active + n);
+		if (s->finalized && n) {
+			// synchronous so the borrowed host arrays can be released on return
+			CK(cudaMemcpyAsync(p.d_pos.p, p.pos.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream));
+			CK(cudaMemcpyAsync(p.d_active.p, p.active.data(), n, cudaMemcpyHostToDevice, s->stream));
+			CK(cudaStreamSynchronize(s->stream));
+		}
+	});
+}
+
+int admm_b200_set_gs_pins(admm_b200_solver *s, int n, const int *idx, const double *pos)
+{
+	return guard(s, [&]() {
+		require(n >= 0 && (n == 0 || (idx && pos)), "set_gs_pins: null input");
+		s->gs_pin_idx.assign(idx, idx + n);
+		s->gs_pin_pos.assign(pos, pos + (size_t)3 * n);
+		if (s->finalized && s->linsolver == ADMM_B200_MCGS) upload_gs_pins(s);
+	});
+}
+
+int admm_b200_add_obstacle(admm_b200_solver *s, int kind, const double *params)
+{
+	return guard(s, [&]() {
+		require(kind == ADMM_B200_FLOOR || kind == ADMM_B200_SPHERE, "add_obstacle: unknown kind");
+		require((int)s->obstacles.size() < ADMMB200_MAX_OBSTACLES, "add_obstacle: too many obstacles");
+		Obstacle o; o.kind = kind;
+		for (int i = 0; i < 4; ++i) o.p[i] = (kind == ADMM_B200_FLOOR && i > 0) ? 0.0 : params[i];
+		s->obstacles.push_back(o);
+	});
+}
+
+int admm_b200_set_system(admm_b200_solver *s, int n, const int *rowptr, const int *cols, const double *vals)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_system after finalize");
+		require(n > 0 && rowptr && cols && vals, "**NodalMultiColorGS Error: Bad dimensions in A");
+		s->sys_n = n;
+		s->L_rowptr.assign(rowptr, rowptr + n + 1);
+		s->L_cols.assign(cols, cols + rowptr[n]);
+		s->L_vals.assign(vals, vals + rowptr[n]);
+	});
+}
+
+int admm_b200_set_colors(admm_b200_solver *s, int n_colors, const int *offsets, const int *nodes)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_colors after finalize");
+		require(n_colors > 0 && offsets && nodes, "set_colors: null input");
+		s->n_colors = n_colors;
+		s->color_off.assign(offsets, offsets + n_colors + 1);
+		s->color_nodes.assign(nodes, nodes + offsets[n_colors]);
+	});
+}
+
+int admm_b200_set_ldlt(admm_b200_solver *s, int n, const int *perm, const int *Lp, const int *Li, const double *Lx, const double *D)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_ldlt after finalize");
+		require(n > 0 && perm && Lp && D, "**LDLTSolver Error: Bad dimensions in A");
+		s->ld_n = n;
+		s->ld_perm.assign(perm, perm + n);
+		s->ld_Lp.assign(Lp, Lp + n + 1);
+		s->ld_Li.assign(Li, Li + Lp[n]);
+		s->ld_Lx.assign(Lx, Lx + Lp[n]);
+		s->ld_D.assign(D, D + n);
+		for (int i = 0; i < n; ++i) require(D[i] != 0.0, "set_ldlt: zero pivot");
+		s->have_ldlt = true;
+	});
+}
+
+int admm_b200_set_debug(admm_b200_solver *s, int store_z)
+{
+	return guard(s, [&]() { require(!s->finalized, "set_debug after finalize"); s->store_z = store_z != 0; });
+}
+
+int admm_b200_finalize(admm_b200_solver *s, double dt, int linsolver, int gs_iters, double gs_omega, double gs_tol, int precision)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "finalize called twice");
+		require(s->n_nodes > 0, "**Solver Error: Problem with node data!");
+		require(linsolver >= 0 && linsolver <= 2, "unknown linsolver");
+		require(precision == ADMM_B200_FP32 || precision == ADMM_B200_FP64, "unknown precision");
+		if (dt <= 0.0) dt = 1.0 / 24.0; // src/Solver.cpp:175-179
+		s->dt = dt; s->linsolver = linsolver; s->gs_iters = gs_iters; s->gs_omega = gs_omega; s->gs_tol = gs_tol; s->precision = precision;
+		// No collisions with the LDLT solver (src/Solver.cpp:249-254)
+		if (linsolver == ADMM_B200_LDLT) require(s->obstacles.empty(), "**Solver::add_obstacle Error: No collisions with LDLT solver");
+		if (linsolver == ADMM_B200_UZAWA) require(s->obstacles.empty(), "UzawaCG with passive collisions is not on the B200 path yet (SURVEY.md 8f rank 1)");
+		build_incidence(s);
+		if (precision == ADMM_B200_FP64) upload_elements<double>(s); else upload_elements<float>(s);
+		upload_pins(s);
+		if (linsolver == ADMM_B200_MCGS) build_mcgs(s); else build_ldlt(s);
+		CK(cudaStreamSynchronize(s->stream));
+		s->finalized = true;
+	});
+}
+
+int admm_b200_step(admm_b200_solver *s, int admm_iters, double gravity, admm_b200_runtime *runtime)
+{
+	return guard(s, [&]() { do_step(s, admm_iters, gravity, runtime); });
+}
+
+int admm_b200_upload_state(admm_b200_solver *s, const double *x, const double *v)
+{
+	return guard(s, [&]() { require(s->n_nodes > 0, "no nodes"); upload_state(s, x, v); CK(cudaStreamSynchronize(s->stream)); });
+}
+
+int admm_b200_download_state(admm_b200_solver *s, double *x, double *v)
+{
+	return guard(s, [&]() { require(s->n_nodes > 0, "no nodes"); download_state(s, x, v); });
+}
+
+int admm_b200_step_host(admm_b200_solver *s, int admm_iters, double gravity, double *x, double *v, admm_b200_runtime *runtime)
+{
+	return guard(s, [&]() {
+		require(x && v, "step_host: null state");
+		upload_state(s, x, v);
+		do_step(s, admm_iters, gravity, runtime);
+		download_state(s, x, v);
+	});
+}
+
+int admm_b200_prox_tets(admm_b200_solver *s, int model, double mu, double lambda, double kappa, int precision, int n, const double *z_in, double *z_out)
+{
+	return guard(s, [&]() {
+		require(n >= 0 && (n == 0 || (z_in && z_out)), "prox_tets: null input");
+		if (n == 0) return;
+		if (precision == ADMM_B200_FP64) prox_tets_impl<double>(s, model, mu, lambda, kappa, n, z_in, z_out);
+		else prox_tets_impl<float>(s, model, mu, lambda, kappa, n, z_in, z_out);
+	});
+}
+
+int admm_b200_prox_tris(admm_b200_solver *s, double limit_min, double limit_max, int precision, int n, const double *z_in, double *z_out)
+{
+	return guard(s, [&]() {
+		require(n >= 0 && (n == 0 || (z_in && z_out)), "prox_tris: null input");
+		if (n == 0) return;
+		if (precision == ADMM_B200_FP64) prox_tris_impl<double>(s, limit_min, limit_max, n, z_in, z_out);
+		else prox_tris_impl<float>(s, limit_min, limit_max, n, z_in, z_out);
+	});
+}
+
+int admm_b200_linsolve(admm_b200_solver *s, double *x, const double *b, int *iters)
+{
+	return guard(s, [&]() {
+		require(s->finalized, "linsolve before finalize");
+		const int n = s->n_nodes;
+		CK(cudaMemcpyAsync(s->stage3.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream));
+		pack3_to4_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->stage3.p, s->cx.p);
+		CK(cudaMemcpyAsync(s->stage3b.p, b, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream));
+		pack3_to4_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->stage3b.p, s->b.p);
+		launch_global(s);
+		unpack4_to3_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->cx.p, s->stage3.p);
+		CK(cudaMemcpyAsync(x, s->stage3.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
+		int it = 1;
+		if (s->linsolver == ADMM_B200_MCGS) CK(cudaMemcpyAsync(&it, s->gs_iters_done.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		if (iters) *iters = it;
+	});
+}
+
+int admm_b200_debug_get(admm_b200_solver *s, const char *name, double *out, long long n_out)
+{
+	return guard(s, [&]() {
+		require(name && out, "debug_get: null input");
+		CK(cudaStreamSynchronize(s->stream));
+		std::string nm(name);
+		const int n = s->n_nodes;
+		if (nm == "z" || nm == "u") {
+			require(s->finalized, "debug_get before finalize");
+			if (s->precision == ADMM_B200_FP64) gather_rows<double>(s, nm == "z", out, n_out); else gather_rows<float>(s, nm == "z", out, n_out);
+			return;
+		}
+		const double4 *src = nullptr;
+		if (nm == "b") src = s->b.p; else if (nm == "x") src = s->cx.p; else if (nm == "v") src = s->v.p; else if (nm == "x0") src = s->x.p;
+		else throw std::runtime_error("debug_get: unknown array name");
+		require(n_out >= 3LL * n, "debug_get: output too small");
+		std::vector<double4> tmp(n);
+		CK(cudaMemcpy(tmp.data(), src, sizeof(double4) * n, cudaMemcpyDeviceToHost));
+		for (int i = 0; i < n; ++i) { out[3 * i] = tmp[i].x; out[3 * i + 1] = tmp[i].y; out[3 * i + 2] = tmp[i].z; }
+	});
+}
+
+int admm_b200_time_kernels(admm_b200_solver *s, int reps, double *out_ms)
+{
+	return guard(s, [&]() {
+		require(s->finalized && reps > 0 && out_ms, "time_kernels: bad arguments");
+		cudaEvent_t e0 = get_event(s, 0), e1 = get_event(s, 1);
+		float ms;
+		CK(cudaStreamSynchronize(s->stream));
+		CK(cudaEventRecord(e0, s->stream));
+		for (int r = 0; r < reps; ++r) launch_local(s);
+		CK(cudaEventRecord(e1, s->stream));
+		CK(cudaEventSynchronize(e1));
+		CK(cudaEventElapsedTime(&ms, e0, e1)); out_ms[0] = ms / reps;
+		CK(cudaEventRecord(e0, s->stream));
+		for (int r = 0; r < reps; ++r) launch_assemble(s);
+		CK(cudaEventRecord(e1, s->stream));
+		CK(cudaEventSynchronize(e1));
+		CK(cudaEventElapsedTime(&ms, e0, e1)); out_ms[1] = ms / reps;
+		CK(cudaEventRecord(e0, s->stream));
+		for (int r = 0; r < reps; ++r) launch_global(s);
+		CK(cudaEventRecord(e1, s->stream));
+		CK(cudaEventSynchronize(e1));
+		CK(cudaEventElapsedTime(&ms, e0, e1)); out_ms[2] = ms / reps;
+	});
+}
+
+long long admm_b200_launch_count(const admm_b200_solver *s) { return s ? s->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,504 @@
+// kernels.cuh -- the CUDA kernels of one ADMM-elastic time step on sm_100a.
+//
+// Path (reference: admm::Solver::step, src/Solver.cpp:35-110):
+//   step_begin_kernel      x_bar = x + dt v, M x_bar, curr_x = x_bar                 (:57-67)
+//   tet_local_kernel       EnergyTerm::update for every tet: F = D_i x, z = prox(F+u),
+//                          u += F - z  (src/EnergyTerm.hpp:130-140) fused with the element's
+//                          share of dt^2 D^T W^2 (z-u)  (src/Solver.cpp:98)
+//   tri_local_kernel       the same for TriEnergyTerm
+//   pin_local_kernel       the same for SpringPin
+//   assemble_kernel        b = M x_bar + sum of the per-corner shares (per-vertex segmented sum)
+//   mcgs_kernel            NodalMultiColorGS::solve (src/NodalMultiColorGS.hpp:60-146), persistent,
+//                          all sweeps x colours in one cooperative launch
+//   step_end_kernel        v = (curr_x - x)/dt, x = curr_x                             (:105-106)
+//
+// Data layout (all in HBM, allocated once):
+//   nodes      double4 per node (xyz + pad): x, v, curr_x, M x_bar, b, masses
+//   tets       int4 idx[e]; E dminv[9][n_pad] (SoA, entry 3c+r); E u[9][n_pad]; E wdt2[n_pad];
+//              E4 f[4e+c] = corner c's share of dt^2 D^T W^2 (z-u)   (E = float or double)
+//   assembly   CSR node -> slots into f
+//   MCGS       per colour sliced-ELL of the scalar matrix L (A = L (x) I3 + M), T lanes per node
+#pragma once
+#include "prox.cuh"
+#include <cooperative_groups.h>
+
+namespace admmb200 {
+
+template <typename E> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; static __device__ __forceinline__ float4 make(float a, float b, float c) { return make_float4(a, b, c, 0.f); } };
+template <> struct Vec4<double> { typedef double4 type; static __device__ __forceinline__ double4 make(double a, double b, double c) { return make_double4(a, b, c, 0.0); } };
+
+__device__ __forceinline__ double4 ld_node(const double4 *p) {
+	// 2 x 16-byte read-only loads
+	const double2 *q = reinterpret_cast<const double2 *>(p);
+	double2 a = __ldg(q), b = __ldg(q + 1);
+	return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double4 ld_node_cg(const double4 *p) {
+	// L2-coherent loads: other SMs write these values inside the same kernel
+	const double2 *q = reinterpret_cast<const double2 *>(p);
+	double2 a = __ldcg(q), b = __ldcg(q + 1);
+	return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_node(double4 *p, double x, double y, double z) {
+	double2 *q = reinterpret_cast<double2 *>(p);
+	q[0] = make_double2(x, y);
+	q[1] = make_double2(z, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// step begin / end
+// ---------------------------------------------------------------------------------------------
+__global__ void step_begin_kernel(int n, double dt, double gravity, const double4 *__restrict__ x, double4 *__restrict__ v,
+	const double4 *__restrict__ m, double4 *__restrict__ mxbar, double4 *__restrict__ cx)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double4 xi = x[i], vi = v[i], mi = m[i];
+	if (fabs(gravity) > 0) { vi.y += dt * gravity; v[i] = vi; }
+	double bx = xi.x + dt * vi.x, by = xi.y + dt * vi.y, bz = xi.z + dt * vi.z;
+	st_node(&cx[i], bx, by, bz);
+	st_node(&mxbar[i], mi.x * bx, mi.y * by, mi.z * bz);
+}
+
+__global__ void step_end_kernel(int n, double dt, double4 *__restrict__ x, double4 *__restrict__ v, const double4 *__restrict__ cx)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double4 xi = x[i], ci = cx[i];
+	double inv = 1.0 / dt;
+	st_node(&v[i], (ci.x - xi.x) * inv, (ci.y - xi.y) * inv, (ci.z - xi.z) * inv);
+	st_node(&x[i], ci.x, ci.y, ci.z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// local step: tets
+// ---------------------------------------------------------------------------------------------
+template <typename E>
+struct TetBatch {
+	int n, n_pad;             // elements, SoA pitch
+	const int4 *idx;          // [n]
+	const E *dminv;           // [9][n_pad], entry 3c+r = edges_inv(c,r)
+	const E *wdt2;            // [n_pad]   dt^2 w^2
+	E *u;                     // [9][n_pad]
+	E *z;                     // [9][n_pad] or NULL
+	typename Vec4<E>::type *f; // [4n]
+	Material<E> mat;
+};
+
+template <typename E, int MODEL, bool STORE_Z>
+__global__ void __launch_bounds__(128) tet_local_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= tb.n) return;
+	const int np = tb.n_pad;
+	int4 id = __ldg(&tb.idx[e]);
+	double4 p0 = ld_node(&cx[id.x]), p1 = ld_node(&cx[id.y]), p2 = ld_node(&cx[id.z]), p3 = ld_node(&cx[id.w]);
+	// Ds = [x1-x0, x2-x0, x3-x0], differences in fp64 (positions are ~metres, edges ~centimetres)
+	E ds[9] = {E(p1.x - p0.x), E(p1.y - p0.y), E(p1.z - p0.z), E(p2.x - p0.x), E(p2.y - p0.y), E(p2.z - p0.z), E(p3.x - p0.x), E(p3.y - p0.y), E(p3.z - p0.z)};
+	E bi[9], u[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) bi[k] = tb.dminv[(size_t)k * np + e];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) u[k] = tb.u[(size_t)k * np + e];
+	// F = Ds * Binv, column-major F[3r+j] = sum_c Ds(j,c) Binv(c,r)   (D_i x, src/TetEnergyTerm.cpp:50-71)
+	E F[9], z[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r)
+#pragma unroll
+		for (int j = 0; j < 3; ++j) {
+			F[3 * r + j] = ds[j] * bi[r] + ds[3 + j] * bi[3 + r] + ds[6 + j] * bi[6 + r];
+			z[3 * r + j] = F[3 * r + j] + u[3 * r + j];
+		}
+	prox_tet<E, MODEL>(tb.mat, z);
+	// u += Dx - z ; y = z - u_new
+	E y[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) {
+		E un = u[k] + (F[k] - z[k]);
+		tb.u[(size_t)k * np + e] = un;
+		if (STORE_Z) tb.z[(size_t)k * np + e] = z[k];
+		y[k] = z[k] - un;
+	}
+	// corner shares of dt^2 D^T W^2 y: corner c>=1: wdt2 * sum_r Binv(c-1,r) y[:,r]; corner 0: minus their sum
+	E w = tb.wdt2[e];
+	E f1[3], f2[3], f3[3];
+#pragma unroll
+	for (int j = 0; j < 3; ++j) {
+		f1[j] = w * (bi[0] * y[j] + bi[1] * y[3 + j] + bi[2] * y[6 + j]);
+		f2[j] = w * (bi[3] * y[j] + bi[4] * y[3 + j] + bi[5] * y[6 + j]);
+		f3[j] = w * (bi[6] * y[j] + bi[7] * y[3 + j] + bi[8] * y[6 + j]);
+	}
+	typename Vec4<E>::type *f = tb.f + (size_t)4 * e;
+	f[0] = Vec4<E>::make(-(f1[0] + f2[0] + f3[0]), -(f1[1] + f2[1] + f3[1]), -(f1[2] + f2[2] + f3[2]));
+	f[1] = Vec4<E>::make(f1[0], f1[1], f1[2]);
+	f[2] = Vec4<E>::make(f2[0], f2[1], f2[2]);
+	f[3] = Vec4<E>::make(f3[0], f3[1], f3[2]);
+}
+
+// prox alone on raw deformation gradients (parity tests / micro-benchmarks): zio is [9][n_pad] SoA
+template <typename E, int MODEL>
+__global__ void __launch_bounds__(128) tet_prox_only_kernel(int n, int n_pad, E *zio, Material<E> mat)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n) return;
+	E z[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) z[k] = zio[(size_t)k * n_pad + e];
+	prox_tet<E, MODEL>(mat, z);
+#pragma unroll
+	for (int k = 0; k < 9; ++k) zio[(size_t)k * n_pad + e] = z[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// local step: triangles
+// ---------------------------------------------------------------------------------------------
+template <typename E>
+struct TriBatch {
+	int n, n_pad;
+	const int4 *idx;   // [n] (w unused)
+	const E *rest;     // [4][n_pad], entry 2c+r = rest_pose(c,r)
+	const E *wdt2;     // [n_pad]
+	E *u;              // [6][n_pad]
+	E *z;              // [6][n_pad] or NULL
+	typename Vec4<E>::type *f; // [3n]
+	E limit_min, limit_max;
+};
+
+template <typename E, bool STORE_Z>
+__global__ void __launch_bounds__(128) tri_local_kernel(TriBatch<E> tb, const double4 *__restrict__ cx)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= tb.n) return;
+	const int np = tb.n_pad;
+	int4 id = __ldg(&tb.idx[e]);
+	double4 p0 = ld_node(&cx[id.x]), p1 = ld_node(&cx[id.y]), p2 = ld_node(&cx[id.z]);
+	E ds[6] = {E(p1.x - p0.x), E(p1.y - p0.y), E(p1.z - p0.z), E(p2.x - p0.x), E(p2.y - p0.y), E(p2.z - p0.z)};
+	E rp[4], u[6];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) rp[k] = tb.rest[(size_t)k * np + e];
+#pragma unroll
+	for (int k = 0; k < 6; ++k) u[k] = tb.u[(size_t)k * np + e];
+	// F (3x2) = [x1-x0, x2-x0] * rest_pose; rows of D: i for column 0, 3+i for column 1 (src/TriEnergyTerm.cpp:54-70)
+	E F[6], z[6];
+#pragma unroll
+	for (int r = 0; r < 2; ++r)
+#pragma unroll
+		for (int j = 0; j < 3; ++j) {
+			F[3 * r + j] = ds[j] * rp[r] + ds[3 + j] * rp[2 + r];
+			z[3 * r + j] = F[3 * r + j] + u[3 * r + j];
+		}
+	prox_tri<E>(tb.limit_min, tb.limit_max, z);
+	E y[6];
+#pragma unroll
+	for (int k = 0; k < 6; ++k) {
+		E un = u[k] + (F[k] - z[k]);
+		tb.u[(size_t)k * np + e] = un;
+		if (STORE_Z) tb.z[(size_t)k * np + e] = z[k];
+		y[k] = z[k] - un;
+	}
+	E w = tb.wdt2[e];
+	E f1[3], f2[3];
+#pragma unroll
+	for (int j = 0; j < 3; ++j) {
+		f1[j] = w * (rp[0] * y[j] + rp[1] * y[3 + j]);
+		f2[j] = w * (rp[2] * y[j] + rp[3] * y[3 + j]);
+	}
+	typename Vec4<E>::type *f = tb.f + (size_t)3 * e;
+	f[0] = Vec4<E>::make(-(f1[0] + f2[0]), -(f1[1] + f2[1]), -(f1[2] + f2[2]));
+	f[1] = Vec4<E>::make(f1[0], f1[1], f1[2]);
+	f[2] = Vec4<E>::make(f2[0], f2[1], f2[2]);
+}
+
+template <typename E>
+__global__ void __launch_bounds__(128) tri_prox_only_kernel(int n, int n_pad, E *zio, E limit_min, E limit_max)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n) return;
+	E z[6];
+#pragma unroll
+	for (int k = 0; k < 6; ++k) z[k] = zio[(size_t)k * n_pad + e];
+	prox_tri<E>(limit_min, limit_max, z);
+#pragma unroll
+	for (int k = 0; k < 6; ++k) zio[(size_t)k * n_pad + e] = z[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// local step: SpringPin (src/SpringEnergyTerm.hpp:31-73).  Always fp64: a handful of elements.
+// ---------------------------------------------------------------------------------------------
+struct PinBatch {
+	int n;
+	const int *idx;        // [n]
+	const double *pos;     // [3n]
+	const unsigned char *active; // [n]
+	const double *wdt2;    // [n]
+	double *u;             // [3n]
+	double *z;             // [3n]
+	double4 *f;            // [n]
+};
+
+__global__ void pin_local_kernel(PinBatch pb, const double4 *__restrict__ cx)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= pb.n) return;
+	double4 p = cx[pb.idx[i]];
+	double dix[3] = {p.x, p.y, p.z};
+	double out[3];
+#pragma unroll
+	for (int j = 0; j < 3; ++j) {
+		double u = pb.u[3 * i + j];
+		double z = dix[j] + u;
+		if (pb.active[i]) z = pb.pos[3 * i + j];
+		double un = u + (dix[j] - z);
+		pb.u[3 * i + j] = un;
+		pb.z[3 * i + j] = z;
+		out[j] = pb.wdt2[i] * (z - un);
+	}
+	pb.f[i] = make_double4(out[0], out[1], out[2], 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// global step 1: b = M x_bar + dt^2 D^T W^2 (z-u)   (src/Solver.cpp:98), per-vertex segmented sum
+// over the corner shares written by the local kernels.  inc_slot entries: bits 0..28 slot, bits
+// 29..30 which share array (0 = element precision tets/tris, 1 = fp64 pins).
+// ---------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256) assemble_kernel(int n, const int *__restrict__ inc_off, const int *__restrict__ inc_slot,
+	const typename Vec4<E>::type *__restrict__ f, const double4 *__restrict__ fpin, const double4 *__restrict__ mxbar, double4 *__restrict__ b)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double4 acc = mxbar[i];
+	double sx = 0, sy = 0, sz = 0;
+	int k0 = inc_off[i], k1 = inc_off[i + 1];
+	for (int k = k0; k < k1; ++k) {
+		int s = __ldg(&inc_slot[k]);
+		if (s >= 0) {
+			typename Vec4<E>::type v = f[s];
+			sx += double(v.x); sy += double(v.y); sz += double(v.z);
+		} else {
+			double4 v = fpin[s & 0x7fffffff];
+			sx += v.x; sy += v.y; sz += v.z;
+		}
+	}
+	st_node(&b[i], acc.x + sx, acc.y + sy, acc.z + sz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// global step 2: nodal multi-colour Gauss-Seidel, persistent cooperative kernel.
+// ---------------------------------------------------------------------------------------------
+struct Obstacle { int kind; double p[4]; };
+#define ADMMB200_MAX_OBSTACLES 8
+
+struct McgsParams {
+	int n_nodes;
+	int n_colors;
+	int iters;                  // max_iters
+	double omega;
+	double tol2;                // m_tol^2, <= 0: no residual test
+	const int *color_first_slice; // [n_colors+1]
+	const int *slice_ptr;       // [n_slices+1], offset (in 32-entry rows) into ell_col / ell_val
+	const int *slice_node;      // [n_slices * (32/T)] node of each group, -1 = padding
+	const int *ell_col;         // [rows*32]
+	const double *ell_val;      // [rows*32]
+	const double *diag;         // [3*n_nodes]  a_ii per component (L_ii + m)
+	const int *pin_slot;        // [n_nodes] -1 or index into pin_pos
+	const double *pin_pos;      // [3*n_pins]
+	int has_pins;
+	int n_obstacles;
+	Obstacle obs[ADMMB200_MAX_OBSTACLES];
+	double4 *x;                 // curr_x, in/out
+	const double4 *b;
+	unsigned int *barrier;      // zeroed before launch
+	double *resid;              // [iters+1], zeroed before launch: [0] = |b|^2, [1+it] = |b-Ax|^2 after sweep it
+	int *iters_done;            // return value of solve()
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &target, unsigned int n_blocks)
+{
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		target += n_blocks;
+		__threadfence();
+		atomicAdd(counter, 1u);
+		unsigned int seen;
+		do {
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+		} while (seen < target);
+	}
+	__syncthreads();
+}
+
+// Creates the ortho projection of NodalMultiColorGS::orthoG (src/NodalMultiColorGS.hpp:171-177)
+// and applies constrained_segment_update's plane solve (:249-259): G G^T (x_gs - p) + p.
+__device__ __forceinline__ void plane_project(const double *n, const double *p, const double *xgs, double *out)
+{
+	double nn0 = n[0] > 0.999 ? 0.0 : 1.0, nn1 = 0.0, nn2 = n[0] > 0.999 ? 1.0 : 0.0;
+	double u0 = nn1 * n[2] - nn2 * n[1], u1 = nn2 * n[0] - nn0 * n[2], u2 = nn0 * n[1] - nn1 * n[0];
+	double iu = 1.0 / sqrt(u0 * u0 + u1 * u1 + u2 * u2); u0 *= iu; u1 *= iu; u2 *= iu;
+	double v0 = n[1] * u2 - n[2] * u1, v1 = n[2] * u0 - n[0] * u2, v2 = n[0] * u1 - n[1] * u0;
+	double iv = 1.0 / sqrt(v0 * v0 + v1 * v1 + v2 * v2); v0 *= iv; v1 *= iv; v2 *= iv;
+	double d0 = xgs[0] - p[0], d1 = xgs[1] - p[1], d2 = xgs[2] - p[2];
+	double t0 = u0 * d0 + u1 * d1 + u2 * d2, t1 = v0 * d0 + v1 * d1 + v2 * d2;
+	out[0] = (u0 * t0 + v0 * t1) + p[0];
+	out[1] = (u1 * t0 + v1 * t1) + p[1];
+	out[2] = (u2 * t0 + v2 * t1) + p[2];
+}
+
+// Collider::detect_passive (src/Collider.hpp:137-150) for Floor / Sphere (src/PassiveObject.hpp:32-64)
+__device__ __forceinline__ bool detect_passive(const McgsParams &P, const double *x, double *n, double *p)
+{
+	double dx = 1.7976931348623157e308;
+	for (int j = 0; j < P.n_obstacles; ++j) {
+		const Obstacle &o = P.obs[j];
+		if (o.kind == 0) {
+			double d = x[1] - o.p[0];
+			if (!(d > dx)) { dx = d; p[0] = x[0]; p[1] = o.p[0]; p[2] = x[2]; n[0] = 0; n[1] = 1; n[2] = 0; }
+		} else {
+			double r0 = x[0] - o.p[0], r1 = x[1] - o.p[1], r2 = x[2] - o.p[2];
+			double len = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+			double d = len - o.p[3];
+			if (!(d > dx)) {
+				dx = d; r0 /= len; r1 /= len; r2 /= len;
+				p[0] = o.p[0] + r0 * o.p[3]; p[1] = o.p[1] + r1 * o.p[3]; p[2] = o.p[2] + r2 * o.p[3];
+				n[0] = r0; n[1] = r1; n[2] = r2;
+			}
+		}
+		if (dx < 0) return true;
+	}
+	return false;
+}
+
+template <int T>
+__global__ void __launch_bounds__(512, 1) mcgs_kernel(McgsParams P)
+{
+	constexpr int G = 32 / T; // nodes per slice
+	const int lane = threadIdx.x & 31;
+	const int sub = lane % T;
+	const int grp = lane / T;
+	const int warps_per_block = blockDim.x >> 5;
+	const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+	const int n_warps = gridDim.x * warps_per_block;
+	unsigned int bar_target = 0;
+	__shared__ double red[32];
+	const bool check = P.tol2 > 0.0;
+
+	if (check) {
+		// b_norm = |b|^2 (src/NodalMultiColorGS.hpp:92)
+		double acc = 0;
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_nodes; i += gridDim.x * blockDim.x) {
+			double4 bi = P.b[i];
+			acc += bi.x * bi.x + bi.y * bi.y + bi.z * bi.z;
+		}
+		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+		if (lane == 0) red[threadIdx.x >> 5] = acc;
+		__syncthreads();
+		if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < warps_per_block; ++w) s += red[w]; atomicAdd(&P.resid[0], s); }
+	}
+
+	int it = 0;
+	for (; it < P.iters; ++it) {
+		for (int color = 0; color < P.n_colors; ++color) {
+			const int s0 = P.color_first_slice[color], s1 = P.color_first_slice[color + 1];
+			for (int sl = s0 + warp_global; sl < s1; sl += n_warps) {
+				const int node = P.slice_node[sl * G + grp];
+				const int r0 = P.slice_ptr[sl], r1 = P.slice_ptr[sl + 1];
+				double sx = 0, sy = 0, sz = 0;
+				for (int r = r0; r < r1; ++r) {
+					int c = __ldg(&P.ell_col[(size_t)r * 32 + lane]);
+					double a = __ldg(&P.ell_val[(size_t)r * 32 + lane]);
+					double4 xc = ld_node_cg(&P.x[c]);
+					sx += a * xc.x; sy += a * xc.y; sz += a * xc.z;
+				}
+#pragma unroll
+				for (int o = 1; o < T; o <<= 1) {
+					sx += __shfl_xor_sync(0xffffffffu, sx, o);
+					sy += __shfl_xor_sync(0xffffffffu, sy, o);
+					sz += __shfl_xor_sync(0xffffffffu, sz, o);
+				}
+				if (sub == 0 && node >= 0) {
+					int ps = P.has_pins ? P.pin_slot[node] : -1;
+					if (ps >= 0) {
+						st_node(&P.x[node], P.pin_pos[3 * ps], P.pin_pos[3 * ps + 1], P.pin_pos[3 * ps + 2]);
+					} else {
+						double4 bi = P.b[node];
+						double4 xi = ld_node_cg(&P.x[node]);
+						double a0 = P.diag[3 * node], a1 = P.diag[3 * node + 1], a2 = P.diag[3 * node + 2];
+						// segment_update (src/NodalMultiColorGS.hpp:180-215)
+						double gs[3] = {(bi.x - sx) / a0, (bi.y - sy) / a1, (bi.z - sz) / a2};
+						double nx[3] = {(1.0 - P.omega) * xi.x + P.omega * gs[0], (1.0 - P.omega) * xi.y + P.omega * gs[1], (1.0 - P.omega) * xi.z + P.omega * gs[2]};
+						if (P.n_obstacles > 0) {
+							double nrm[3], pt[3];
+							if (detect_passive(P, nx, nrm, pt)) {
+								// constrained_segment_update (:218-262): no over-relaxation
+								double out[3];
+								plane_project(nrm, pt, gs, out);
+								nx[0] = out[0]; nx[1] = out[1]; nx[2] = out[2];
+							}
+						}
+						st_node(&P.x[node], nx[0], nx[1], nx[2]);
+					}
+				}
+			}
+			grid_barrier(P.barrier, bar_target, gridDim.x);
+		}
+		if (check) {
+			// residual = b - A x (src/NodalMultiColorGS.hpp:136-139), every row including pinned ones
+			double acc = 0;
+			const int n_slices = P.color_first_slice[P.n_colors];
+			for (int sl = warp_global; sl < n_slices; sl += n_warps) {
+				const int node = P.slice_node[sl * G + grp];
+				const int r0 = P.slice_ptr[sl], r1 = P.slice_ptr[sl + 1];
+				double sx = 0, sy = 0, sz = 0;
+				for (int r = r0; r < r1; ++r) {
+					int c = __ldg(&P.ell_col[(size_t)r * 32 + lane]);
+					double a = __ldg(&P.ell_val[(size_t)r * 32 + lane]);
+					double4 xc = ld_node_cg(&P.x[c]);
+					sx += a * xc.x; sy += a * xc.y; sz += a * xc.z;
+				}
+#pragma unroll
+				for (int o = 1; o < T; o <<= 1) {
+					sx += __shfl_xor_sync(0xffffffffu, sx, o);
+					sy += __shfl_xor_sync(0xffffffffu, sy, o);
+					sz += __shfl_xor_sync(0xffffffffu, sz, o);
+				}
+				if (sub == 0 && node >= 0) {
+					double4 bi = P.b[node];
+					double4 xi = ld_node_cg(&P.x[node]);
+					double rx = bi.x - (sx + P.diag[3 * node] * xi.x);
+					double ry = bi.y - (sy + P.diag[3 * node + 1] * xi.y);
+					double rz = bi.z - (sz + P.diag[3 * node + 2] * xi.z);
+					acc += rx * rx + ry * ry + rz * rz;
+				}
+			}
+			for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+			__syncthreads();
+			if (lane == 0) red[threadIdx.x >> 5] = acc;
+			__syncthreads();
+			if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < warps_per_block; ++w) s += red[w]; atomicAdd(&P.resid[1 + it], s); }
+			grid_barrier(P.barrier, bar_target, gridDim.x);
+			double r2 = __ldcg(&P.resid[1 + it]), b2 = __ldcg(&P.resid[0]);
+			if (r2 / b2 < P.tol2) break;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) *P.iters_done = it;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers: AoS <-> padded / SoA conversions done on the device so host copies stay contiguous
+// ---------------------------------------------------------------------------------------------
+__global__ void pack3_to4_kernel(int n, const double *__restrict__ in3, double4 *__restrict__ out4)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	st_node(&out4[i], in3[3 * i], in3[3 * i + 1], in3[3 * i + 2]);
+}
+__global__ void unpack4_to3_kernel(int n, const double4 *__restrict__ in4, double *__restrict__ out3)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double4 v = in4[i];
+	out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z;
+}
+
+} // namespace admmb200

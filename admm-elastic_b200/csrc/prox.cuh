@@ -1,0 +1,414 @@
+// prox.cuh -- per-element proximal operators of the ADMM local step, in registers.
+//
+// One thread owns one element.  Everything is templated on the element scalar T
+// (float = production path, double = validation path).
+//
+// What is computed (parity targets in the reference, mattoverby/admm-elastic @ c6c09a3):
+//   svd3_signed       signed_svd            src/FastSVD.hpp:43-68  (a stub around Eigen::JacobiSVD;
+//                                           parity target is U*diag(f(S))*V^T, not U and V themselves)
+//   prox_tet_linear   TetEnergyTerm::prox   src/TetEnergyTerm.cpp:73-92
+//   prox_tet_hyper    HyperElasticTet::prox src/TetEnergyTerm.cpp:114-136 with the energies of
+//                     NHProx :173-204, StVKProx :210-237, SplineProx :243-265 + src/XuSpline.hpp:48-94
+//   prox_tri          TriEnergyTerm::prox   src/TriEnergyTerm.cpp:73-101
+//
+// The reference minimises the 3-variable prox objective with L-BFGS + cubic backtracking
+// (deps/mcloptlib LBFGS.hpp:52-152) to |grad|<1e-6 or |dx|<1e-6; here it is a safeguarded Newton
+// iteration with the closed-form 3x3 Hessian, which converges to the same minimiser in 3-6
+// iterations (SURVEY.md 0.2, 7 "hard parts" 1-2).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace admmb200 {
+
+enum TetModel { TET_LINEAR = 0, TET_NEOHOOKEAN = 1, TET_STVK = 2, TET_SPLINE_NH = 3, TET_SPLINE_STVK = 4, TET_SPLINE_COROT = 5 };
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+	static __device__ __forceinline__ float eps() { return 1.1920929e-7f; }
+	static __device__ __forceinline__ float tiny() { return 1e-30f; }
+	static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
+	static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
+	static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+	static constexpr int jacobi_sweeps = 5;
+	static constexpr int newton_iters = 24;
+};
+template <> struct Num<double> {
+	static __device__ __forceinline__ double eps() { return 2.220446049250313e-16; }
+	static __device__ __forceinline__ double tiny() { return 1e-290; }
+	static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+	static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+	static __device__ __forceinline__ double log(double x) { return ::log(x); }
+	static constexpr int jacobi_sweeps = 8;
+	static constexpr int newton_iters = 48;
+};
+
+// One Jacobi rotation in the (p,q) plane of a symmetric 3x3 matrix; r is the third index.
+// A' = P^T A P, V' = V P with P a proper rotation, so det V stays +1.
+template <typename T>
+__device__ __forceinline__ void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &arq,
+	T &v0p, T &v0q, T &v1p, T &v1q, T &v2p, T &v2q)
+{
+	if (fabs(apq) <= Num<T>::eps() * T(0.125) * (fabs(app) + fabs(aqq)) || fabs(apq) < Num<T>::tiny()) { apq = (fabs(apq) < Num<T>::tiny()) ? T(0) : apq; return; }
+	T theta = (aqq - app) / (T(2) * apq);
+	T t = copysign(T(1), theta) / (fabs(theta) + Num<T>::sqrt(theta * theta + T(1)));
+	T c = Num<T>::rsqrt(t * t + T(1));
+	T s = t * c;
+	app -= t * apq;
+	aqq += t * apq;
+	apq = T(0);
+	T nrp = c * arp - s * arq, nrq = s * arp + c * arq; arp = nrp; arq = nrq;
+	T a, b;
+	a = c * v0p - s * v0q; b = s * v0p + c * v0q; v0p = a; v0q = b;
+	a = c * v1p - s * v1q; b = s * v1p + c * v1q; v1p = a; v1q = b;
+	a = c * v2p - s * v2q; b = s * v2p + c * v2q; v2p = a; v2q = b;
+}
+
+// F (column-major, F[3c+r] = F(r,c)) = U diag(S) V^T with U, V in SO(3), S[0] >= S[1] >= |S[2]|,
+// sign(S[2]) = sign(det F): the convention signed_svd (src/FastSVD.hpp:43-68) produces.
+// U, V are column-major too.
+template <typename T>
+__device__ __forceinline__ void svd3_signed(const T *F, T *S, T *U, T *V)
+{
+	// C = F^T F
+	T c00 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+	T c01 = F[0] * F[3] + F[1] * F[4] + F[2] * F[5];
+	T c02 = F[0] * F[6] + F[1] * F[7] + F[2] * F[8];
+	T c11 = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
+	T c12 = F[3] * F[6] + F[4] * F[7] + F[5] * F[8];
+	T c22 = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+	// V(r,c): v{r}{c}
+	T v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#pragma unroll 1
+	for (int sweep = 0; sweep < Num<T>::jacobi_sweeps; ++sweep) {
+		jacobi_rot(c00, c11, c01, c02, c12, v00, v01, v10, v11, v20, v21); // (0,1), r=2
+		jacobi_rot(c00, c22, c02, c01, c12, v00, v02, v10, v12, v20, v22); // (0,2), r=1
+		jacobi_rot(c11, c22, c12, c01, c02, v01, v02, v11, v12, v21, v22); // (1,2), r=0
+	}
+	// sort eigenvalues descending; a swap of two columns with one negation keeps det V = +1
+#define ADMMB200_SWAPCOL(la, lb, a0, a1, a2, b0, b1, b2)                \
+	if (la < lb) {                                                        \
+		T t_ = la; la = lb; lb = t_;                                      \
+		t_ = a0; a0 = b0; b0 = -t_;                                       \
+		t_ = a1; a1 = b1; b1 = -t_;                                       \
+		t_ = a2; a2 = b2; b2 = -t_;                                       \
+	}
+	ADMMB200_SWAPCOL(c00, c11, v00, v10, v20, v01, v11, v21)
+	ADMMB200_SWAPCOL(c00, c22, v00, v10, v20, v02, v12, v22)
+	ADMMB200_SWAPCOL(c11, c22, v01, v11, v21, v02, v12, v22)
+#undef ADMMB200_SWAPCOL
+	// B = F V
+	T b00 = F[0] * v00 + F[3] * v10 + F[6] * v20, b10 = F[1] * v00 + F[4] * v10 + F[7] * v20, b20 = F[2] * v00 + F[5] * v10 + F[8] * v20;
+	T b01 = F[0] * v01 + F[3] * v11 + F[6] * v21, b11 = F[1] * v01 + F[4] * v11 + F[7] * v21, b21 = F[2] * v01 + F[5] * v11 + F[8] * v21;
+	T b02 = F[0] * v02 + F[3] * v12 + F[6] * v22, b12 = F[1] * v02 + F[4] * v12 + F[7] * v22, b22 = F[2] * v02 + F[5] * v12 + F[8] * v22;
+	// U by Gram-Schmidt on the (already nearly orthogonal) columns of B, third column = cross product
+	T s0 = Num<T>::sqrt(b00 * b00 + b10 * b10 + b20 * b20);
+	T u00, u10, u20;
+	if (s0 > Num<T>::tiny()) { T i = T(1) / s0; u00 = b00 * i; u10 = b10 * i; u20 = b20 * i; }
+	else { u00 = 1; u10 = 0; u20 = 0; }
+	T d = u00 * b01 + u10 * b11 + u20 * b21;
+	T w0 = b01 - d * u00, w1 = b11 - d * u10, w2 = b21 - d * u20;
+	T s1 = Num<T>::sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+	T u01, u11, u21;
+	if (s1 > T(4) * Num<T>::eps() * s0 && s1 > Num<T>::tiny()) { T i = T(1) / s1; u01 = w0 * i; u11 = w1 * i; u21 = w2 * i; }
+	else {
+		// rank <= 1: any unit vector orthogonal to u0
+		T ax = fabs(u00), ay = fabs(u10), az = fabs(u20);
+		T e0 = 0, e1 = 0, e2 = 0;
+		if (ax <= ay && ax <= az) e0 = 1; else if (ay <= az) e1 = 1; else e2 = 1;
+		w0 = u10 * e2 - u20 * e1; w1 = u20 * e0 - u00 * e2; w2 = u00 * e1 - u10 * e0;
+		T i = Num<T>::rsqrt(w0 * w0 + w1 * w1 + w2 * w2);
+		u01 = w0 * i; u11 = w1 * i; u21 = w2 * i;
+		s1 = u01 * b01 + u11 * b11 + u21 * b21;
+	}
+	T u02 = u10 * u21 - u20 * u11, u12 = u20 * u01 - u00 * u21, u22 = u00 * u11 - u10 * u01;
+	T s2 = u02 * b02 + u12 * b12 + u22 * b22;
+	S[0] = s0; S[1] = s1; S[2] = s2;
+	U[0] = u00; U[1] = u10; U[2] = u20; U[3] = u01; U[4] = u11; U[5] = u21; U[6] = u02; U[7] = u12; U[8] = u22;
+	V[0] = v00; V[1] = v10; V[2] = v20; V[3] = v01; V[4] = v11; V[5] = v21; V[6] = v02; V[7] = v12; V[8] = v22;
+}
+
+// Z = U diag(s) V^T, column-major.
+template <typename T>
+__device__ __forceinline__ void usvt(const T *U, const T *s, const T *V, T *Z)
+{
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			Z[3 * c + r] = U[r] * s[0] * V[c] + U[3 + r] * s[1] * V[3 + c] + U[6 + r] * s[2] * V[6 + c];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prox objectives in principal stretches, all divided by K = bulk modulus:
+//     phi(x) = Psi(x)/K + 1/2 |x - x0|^2
+// (HyperElasticTet::Prox::value = energy_density + k/2 |x-x0|^2; src/TetEnergyTerm.cpp:183-191).
+// Each model returns value, gradient g[3] and Hessian h = {h00,h11,h22,h01,h02,h12}.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Material { T a, l, kap; }; // mu/K, lambda/K, kappa/K
+
+template <typename T, int MODEL> struct Energy;
+
+// NHProx (src/TetEnergyTerm.cpp:173-204): Psi = mu/2 (I1 - log I3 - 3) + lambda/8 log^2 I3
+template <typename T> struct Energy<T, TET_NEOHOOKEAN> {
+	static __device__ __forceinline__ T value(const Material<T> &m, const T *x) {
+		T lj = Num<T>::log(x[0] * x[1] * x[2]);
+		return T(0.5) * m.a * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] - T(2) * lj - T(3)) + T(0.5) * m.l * lj * lj;
+	}
+	static __device__ __forceinline__ void derivs(const Material<T> &m, const T *x, T *g, T *h) {
+		T lj = Num<T>::log(x[0] * x[1] * x[2]);
+		T i0 = T(1) / x[0], i1 = T(1) / x[1], i2 = T(1) / x[2];
+		T q = m.l * lj - m.a; // (lambda log J - mu)
+		g[0] = m.a * x[0] + q * i0; g[1] = m.a * x[1] + q * i1; g[2] = m.a * x[2] + q * i2;
+		T p = m.a + m.l - m.l * lj; // mu + lambda (1 - log J)
+		h[0] = m.a + p * i0 * i0; h[1] = m.a + p * i1 * i1; h[2] = m.a + p * i2 * i2;
+		h[3] = m.l * i0 * i1; h[4] = m.l * i0 * i2; h[5] = m.l * i1 * i2;
+	}
+};
+
+// StVKProx (src/TetEnergyTerm.cpp:210-237): E = (x^2-1)/2, Psi = mu |E|^2 + lambda/2 tr(E)^2
+template <typename T> struct Energy<T, TET_STVK> {
+	static __device__ __forceinline__ T value(const Material<T> &m, const T *x) {
+		T e0 = T(0.5) * (x[0] * x[0] - T(1)), e1 = T(0.5) * (x[1] * x[1] - T(1)), e2 = T(0.5) * (x[2] * x[2] - T(1));
+		T tr = e0 + e1 + e2;
+		return m.a * (e0 * e0 + e1 * e1 + e2 * e2) + T(0.5) * m.l * tr * tr;
+	}
+	static __device__ __forceinline__ void derivs(const Material<T> &m, const T *x, T *g, T *h) {
+		T n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+		T q = T(0.5) * m.l * (n2 - T(3));
+#pragma unroll
+		for (int i = 0; i < 3; ++i) {
+			g[i] = m.a * x[i] * (x[i] * x[i] - T(1)) + q * x[i];
+			h[i] = m.a * (T(3) * x[i] * x[i] - T(1)) + q + m.l * x[i] * x[i];
+		}
+		h[3] = m.l * x[0] * x[1]; h[4] = m.l * x[0] * x[2]; h[5] = m.l * x[1] * x[2];
+	}
+};
+
+// xu::Spline materials (src/XuSpline.hpp:34-94): Psi = sum f(x_i) + sum g(x_i x_j) + h(x0 x1 x2)
+// (SplineProx::energy_density, src/TetEnergyTerm.cpp:243-247).  fgh[k] = {value, d, dd}.
+template <typename T, int MODEL> struct Spline;
+template <typename T> __device__ __forceinline__ void compress_term(T kap, T x, T *o) {
+	T s = (T(1) - x) / T(6);
+	o[0] += (kap / T(12)) * s * s * s; o[1] += (-kap / T(24)) * s * s; o[2] += (kap / T(72)) * s;
+}
+template <typename T> struct Spline<T, TET_SPLINE_NH> {
+	static __device__ __forceinline__ void f(const Material<T> &m, T x, T *o) { o[0] = T(0.5) * m.a * (x * x - T(1)); o[1] = m.a * x; o[2] = m.a; }
+	static __device__ __forceinline__ void g(const Material<T> &, T, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; }
+	static __device__ __forceinline__ void h(const Material<T> &m, T x, T *o) {
+		T lx = Num<T>::log(x), ix = T(1) / x;
+		o[0] = -m.a * lx + T(0.5) * m.l * lx * lx; o[1] = (m.l * lx - m.a) * ix; o[2] = (m.a + m.l - m.l * lx) * ix * ix;
+		compress_term(m.kap, x, o);
+	}
+};
+template <typename T> struct Spline<T, TET_SPLINE_STVK> {
+	static __device__ __forceinline__ void f(const Material<T> &m, T x, T *o) {
+		T x2 = x * x;
+		o[0] = T(0.125) * m.l * (x2 * x2 - T(6) * x2 + T(5)) + T(0.25) * m.a * (x2 - T(1)) * (x2 - T(1));
+		o[1] = T(0.125) * m.l * (T(4) * x2 * x - T(12) * x) + m.a * x * (x2 - T(1));
+		o[2] = T(0.125) * m.l * (T(12) * x2 - T(12)) + m.a * (T(3) * x2 - T(1));
+	}
+	static __device__ __forceinline__ void g(const Material<T> &m, T x, T *o) { o[0] = T(0.25) * m.l * (x * x - T(1)); o[1] = T(0.5) * m.l * x; o[2] = T(0.5) * m.l; }
+	static __device__ __forceinline__ void h(const Material<T> &m, T x, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; compress_term(m.kap, x, o); }
+};
+template <typename T> struct Spline<T, TET_SPLINE_COROT> {
+	static __device__ __forceinline__ void f(const Material<T> &m, T x, T *o) {
+		o[0] = T(0.5) * m.l * (x * x - T(6) * x + T(5)) + m.a * (x - T(1)) * (x - T(1));
+		o[1] = T(0.5) * m.l * (T(2) * x - T(6)) + T(2) * m.a * (x - T(1));
+		o[2] = m.l + T(2) * m.a;
+	}
+	static __device__ __forceinline__ void g(const Material<T> &m, T x, T *o) { o[0] = m.l * (x - T(1)); o[1] = m.l; o[2] = 0; }
+	static __device__ __forceinline__ void h(const Material<T> &m, T x, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; compress_term(m.kap, x, o); }
+};
+
+template <typename T, int MODEL> struct SplineEnergy {
+	typedef Spline<T, MODEL> Sp;
+	static __device__ __forceinline__ T value(const Material<T> &m, const T *x) {
+		T o[3], v = 0;
+		Sp::f(m, x[0], o); v += o[0]; Sp::f(m, x[1], o); v += o[0]; Sp::f(m, x[2], o); v += o[0];
+		Sp::g(m, x[0] * x[1], o); v += o[0]; Sp::g(m, x[1] * x[2], o); v += o[0]; Sp::g(m, x[2] * x[0], o); v += o[0];
+		Sp::h(m, x[0] * x[1] * x[2], o); v += o[0];
+		return v;
+	}
+	static __device__ __forceinline__ void derivs(const Material<T> &m, const T *x, T *g, T *h) {
+		T f0[3], f1[3], f2[3], g01[3], g12[3], g20[3], hh[3];
+		Sp::f(m, x[0], f0); Sp::f(m, x[1], f1); Sp::f(m, x[2], f2);
+		Sp::g(m, x[0] * x[1], g01); Sp::g(m, x[1] * x[2], g12); Sp::g(m, x[2] * x[0], g20);
+		Sp::h(m, x[0] * x[1] * x[2], hh);
+		T y0 = x[1] * x[2], y1 = x[2] * x[0], y2 = x[0] * x[1]; // dJ/dx_i
+		g[0] = f0[1] + g01[1] * x[1] + g20[1] * x[2] + hh[1] * y0;
+		g[1] = f1[1] + g12[1] * x[2] + g01[1] * x[0] + hh[1] * y1;
+		g[2] = f2[1] + g20[1] * x[0] + g12[1] * x[1] + hh[1] * y2;
+		h[0] = f0[2] + g01[2] * x[1] * x[1] + g20[2] * x[2] * x[2] + hh[2] * y0 * y0;
+		h[1] = f1[2] + g12[2] * x[2] * x[2] + g01[2] * x[0] * x[0] + hh[2] * y1 * y1;
+		h[2] = f2[2] + g20[2] * x[0] * x[0] + g12[2] * x[1] * x[1] + hh[2] * y2 * y2;
+		h[3] = g01[2] * y2 + g01[1] + hh[2] * y0 * y1 + hh[1] * x[2];
+		h[4] = g20[2] * y1 + g20[1] + hh[2] * y0 * y2 + hh[1] * x[1];
+		h[5] = g12[2] * y0 + g12[1] + hh[2] * y1 * y2 + hh[1] * x[0];
+	}
+};
+template <typename T> struct Energy<T, TET_SPLINE_NH> : SplineEnergy<T, TET_SPLINE_NH> {};
+template <typename T> struct Energy<T, TET_SPLINE_STVK> : SplineEnergy<T, TET_SPLINE_STVK> {};
+template <typename T> struct Energy<T, TET_SPLINE_COROT> : SplineEnergy<T, TET_SPLINE_COROT> {};
+
+// does the model need x > 0 strictly (log barrier)?
+template <int MODEL> struct NeedsPositive { static constexpr bool value = (MODEL == TET_NEOHOOKEAN || MODEL == TET_SPLINE_NH); };
+
+// argmin_x>=0 phi(x), started at x (already made feasible), quadratic centre x0.
+template <typename T, int MODEL>
+__device__ __forceinline__ void prox_newton(const Material<T> &m, const T *x0, T *x)
+{
+	typedef Energy<T, MODEL> En;
+	const T floor_x = NeedsPositive<MODEL>::value ? T(1e-12) : T(0);
+#pragma unroll 1
+	for (int it = 0; it < Num<T>::newton_iters; ++it) {
+		T g[3], h[6];
+		En::derivs(m, x, g, h);
+		g[0] += x[0] - x0[0]; g[1] += x[1] - x0[1]; g[2] += x[2] - x0[2];
+		h[0] += T(1); h[1] += T(1); h[2] += T(1);
+		// Newton direction by LDL^T; if H is not positive definite fall back to a scaled gradient step
+		T d[3];
+		bool pd = true;
+		T d0 = h[0];
+		pd = pd && (d0 > T(0));
+		T l10 = h[3] / d0, l20 = h[4] / d0;
+		T d1 = h[1] - l10 * h[3];
+		pd = pd && (d1 > T(0));
+		T l21 = (h[5] - l20 * h[3]) / d1;
+		T d2 = h[2] - l20 * h[4] - l21 * l21 * d1;
+		pd = pd && (d2 > T(0));
+		if (pd) {
+			T y0 = -g[0], y1 = -g[1] - l10 * y0, y2 = -g[2] - l20 * y0 - l21 * y1;
+			T z2 = y2 / d2, z1 = y1 / d1 - l21 * z2, z0 = y0 / d0 - l10 * z1 - l20 * z2;
+			d[0] = z0; d[1] = z1; d[2] = z2;
+		} else {
+			T bound = fmax(fmax(fabs(h[0]) + fabs(h[3]) + fabs(h[4]), fabs(h[1]) + fabs(h[3]) + fabs(h[5])), fabs(h[2]) + fabs(h[4]) + fabs(h[5]));
+			T sc = T(1) / fmax(bound, T(1));
+			d[0] = -g[0] * sc; d[1] = -g[1] * sc; d[2] = -g[2] * sc;
+		}
+		T gd = g[0] * d[0] + g[1] * d[1] + g[2] * d[2];
+		// keep the iterate inside the feasible set (value() is +inf for x<0, src/TetEnergyTerm.cpp:184-188)
+		T t = T(1);
+#pragma unroll
+		for (int i = 0; i < 3; ++i) {
+			if (x[i] + d[i] < floor_x) {
+				T room = (x[i] - floor_x);
+				T ti = (NeedsPositive<MODEL>::value ? T(0.9) : T(1)) * room / (-d[i]);
+				t = fmin(t, ti);
+			}
+		}
+		T dx0 = x[0] - x0[0], dx1 = x[1] - x0[1], dx2 = x[2] - x0[2];
+		T phi0 = En::value(m, x) + T(0.5) * (dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+		T slack = T(8) * Num<T>::eps() * (fabs(phi0) + T(1));
+		T xn[3];
+#pragma unroll 1
+		for (int ls = 0; ls < 16; ++ls) {
+			xn[0] = x[0] + t * d[0]; xn[1] = x[1] + t * d[1]; xn[2] = x[2] + t * d[2];
+			T e0 = xn[0] - x0[0], e1 = xn[1] - x0[1], e2 = xn[2] - x0[2];
+			T phi = En::value(m, xn) + T(0.5) * (e0 * e0 + e1 * e1 + e2 * e2);
+			if (phi <= phi0 + T(1e-4) * t * gd + slack) break;
+			t *= T(0.5);
+		}
+		T step = t * fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2]));
+		x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
+		T scale = T(1) + fmax(fmax(fabs(x[0]), fabs(x[1])), fabs(x[2]));
+		if (step <= T(4) * Num<T>::eps() * scale) break;
+	}
+}
+
+// HyperElasticTet::prox (src/TetEnergyTerm.cpp:114-136) on a column-major 3x3 z (in/out).
+template <typename T, int MODEL>
+__device__ __forceinline__ void prox_tet(const Material<T> &m, T *z)
+{
+	T S[3], U[9], V[9];
+	svd3_signed(z, S, U, V);
+	if (MODEL == TET_LINEAR) {
+		// TetEnergyTerm::prox (src/TetEnergyTerm.cpp:73-92): p = U diag(1,1,sign det F) V^T with
+		// Eigen's unsigned factors = U V^T with the proper rotations computed here; z = (p+z)/2.
+		T one[3] = {T(1), T(1), T(1)}, P[9];
+		usvt(U, one, V, P);
+#pragma unroll
+		for (int i = 0; i < 9; ++i) z[i] = T(0.5) * (P[i] + z[i]);
+		return;
+	}
+	T x0[3] = {S[0], S[1], S[2]};
+	const T eps = T(1e-6);
+	if (fabs(S[0]) < eps && fabs(S[1]) < eps && fabs(S[2]) < eps) { S[0] = eps; S[1] = eps; S[2] = eps; }
+	if (S[2] < T(0)) S[2] = -S[2];
+	if (NeedsPositive<MODEL>::value) {
+		// the start point of the reference can sit exactly on the barrier (S[2]==0); nudge it inside
+		const T lo = T(1e-7);
+		S[0] = fmax(S[0], lo); S[1] = fmax(S[1], lo); S[2] = fmax(S[2], lo);
+	}
+	if (MODEL == TET_NEOHOOKEAN) prox_newton<T, TET_NEOHOOKEAN>(m, x0, S);
+	if (MODEL == TET_STVK) prox_newton<T, TET_STVK>(m, x0, S);
+	if (MODEL == TET_SPLINE_NH) prox_newton<T, TET_SPLINE_NH>(m, x0, S);
+	if (MODEL == TET_SPLINE_STVK) prox_newton<T, TET_SPLINE_STVK>(m, x0, S);
+	if (MODEL == TET_SPLINE_COROT) prox_newton<T, TET_SPLINE_COROT>(m, x0, S);
+	usvt(U, S, V, z);
+}
+
+// TriEnergyTerm::prox (src/TriEnergyTerm.cpp:73-101) on a column-major 3x2 z (in/out):
+// P = U[:, :2] V^T (nearest matrix with singular values 1,1), z = (P+z)/2, then the optional
+// column-norm strain limit.
+template <typename T>
+__device__ __forceinline__ void prox_tri(T limit_min, T limit_max, T *z)
+{
+	T a = z[0] * z[0] + z[1] * z[1] + z[2] * z[2];
+	T b = z[0] * z[3] + z[1] * z[4] + z[2] * z[5];
+	T d = z[3] * z[3] + z[4] * z[4] + z[5] * z[5];
+	T c = 1, s = 0;
+	if (fabs(b) > Num<T>::eps() * T(0.125) * (a + d) && fabs(b) > Num<T>::tiny()) {
+		T theta = (d - a) / (T(2) * b);
+		T t = copysign(T(1), theta) / (fabs(theta) + Num<T>::sqrt(theta * theta + T(1)));
+		c = Num<T>::rsqrt(t * t + T(1)); s = t * c;
+	}
+	// V = [c s; -s c] (columns v0 = (c,-s), v1 = (s,c)); B = F V
+	T b0[3] = {c * z[0] - s * z[3], c * z[1] - s * z[4], c * z[2] - s * z[5]};
+	T b1[3] = {s * z[0] + c * z[3], s * z[1] + c * z[4], s * z[2] + c * z[5]};
+	T n0 = b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2];
+	T n1 = b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2];
+	if (n0 < n1) { // order so that u0 belongs to the larger singular value (better conditioned first)
+		T t;
+		for (int i = 0; i < 3; ++i) { t = b0[i]; b0[i] = b1[i]; b1[i] = -t; }
+		t = c; T s_old = s; c = s_old; s = -t; // new v0 = old v1 = (s,c), new v1 = -old v0 = (-c, s)
+		t = n0; n0 = n1; n1 = t;
+	}
+	T u0[3], u1[3];
+	T s0 = Num<T>::sqrt(n0);
+	if (s0 > Num<T>::tiny()) { T i = T(1) / s0; u0[0] = b0[0] * i; u0[1] = b0[1] * i; u0[2] = b0[2] * i; }
+	else { u0[0] = 1; u0[1] = 0; u0[2] = 0; }
+	T dd = u0[0] * b1[0] + u0[1] * b1[1] + u0[2] * b1[2];
+	T w[3] = {b1[0] - dd * u0[0], b1[1] - dd * u0[1], b1[2] - dd * u0[2]};
+	T s1 = Num<T>::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+	if (s1 > T(4) * Num<T>::eps() * s0 && s1 > Num<T>::tiny()) { T i = T(1) / s1; u1[0] = w[0] * i; u1[1] = w[1] * i; u1[2] = w[2] * i; }
+	else {
+		T ax = fabs(u0[0]), ay = fabs(u0[1]), az = fabs(u0[2]);
+		T e[3] = {0, 0, 0};
+		if (ax <= ay && ax <= az) e[0] = 1; else if (ay <= az) e[1] = 1; else e[2] = 1;
+		w[0] = u0[1] * e[2] - u0[2] * e[1]; w[1] = u0[2] * e[0] - u0[0] * e[2]; w[2] = u0[0] * e[1] - u0[1] * e[0];
+		T i = Num<T>::rsqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+		u1[0] = w[0] * i; u1[1] = w[1] * i; u1[2] = w[2] * i;
+	}
+	// P = u0 v0^T + u1 v1^T with v0 = (c,-s), v1 = (s,c);  column 0 of P = u0*c + u1*s, column 1 = -u0*s + u1*c
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		T p0 = u0[i] * c + u1[i] * s;
+		T p1 = -u0[i] * s + u1[i] * c;
+		z[i] = T(0.5) * (p0 + z[i]);
+		z[3 + i] = T(0.5) * (p1 + z[3 + i]);
+	}
+	const bool check_strain = limit_min > T(0) || limit_max < T(99);
+	if (check_strain) {
+		T l0 = Num<T>::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+		T l1 = Num<T>::sqrt(z[3] * z[3] + z[4] * z[4] + z[5] * z[5]);
+		if (l0 < limit_min) { T f = limit_min / l0; z[0] *= f; z[1] *= f; z[2] *= f; }
+		if (l1 < limit_min) { T f = limit_min / l1; z[3] *= f; z[4] *= f; z[5] *= f; }
+		if (l0 > limit_max) { T f = limit_max / l0; z[0] *= f; z[1] *= f; z[2] *= f; }
+		if (l1 > limit_max) { T f = limit_max / l1; z[3] *= f; z[4] *= f; z[5] *= f; }
+	}
+}
+
+} // namespace admmb200
