@@ -1,0 +1,116 @@
+"""Host-side logic and the C-ABI surface, without a GPU: the libraries load, export every symbol
+include/admm_b200.h declares, the host colouring / ordering / factorisation are correct, and the
+compute entry points fail loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "admm_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(admm_b200_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = ctypes.CDLL(pkg.LIB_CUDA_PATH)
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+
+
+def test_no_cpu_fallback_without_device(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.AdmmError) as e:
+        pkg.DeviceSolver(0)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+    s = pkg.Solver()
+    V = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 0]], dtype=np.float64)
+    s.add_nodes(V, np.ones(4))
+    s.add_tets(V, np.array([[0, 1, 2, 3]], np.int32), pkg.TET_LINEAR, 1.0, 1.0)
+    with pytest.raises(pkg.AdmmError):
+        s.initialize(linsolver=0)
+
+
+def test_initialize_rejects_bad_node_data(pkg):
+    # "**Solver Error: Problem with node data!" -> false (src/Solver.cpp:180-183)
+    s = pkg.Solver()
+    assert s.initialize(linsolver=0) is False
+
+
+def test_inverted_rest_tet_throws(pkg):
+    s = pkg.Solver()
+    V = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 0]], dtype=np.float64)
+    s.add_nodes(V, np.ones(4))
+    with pytest.raises(pkg.AdmmError) as e:
+        s.add_tets(V, np.array([[0, 2, 1, 3]], np.int32), pkg.TET_LINEAR, 1.0, 1.0)
+    assert "Inverted initial tet" in str(e.value)
+
+
+def _beam_matrix(pkg, nx=6, ny=3, nz=3):
+    verts, tets = pkg.meshes.make_tet_blocks(nx, ny, nz)
+    n = len(verts)
+    rows = np.repeat(tets, 4, axis=1).ravel()
+    cols = np.tile(tets, (1, 4)).ravel()
+    A = sp.coo_matrix((np.ones(rows.size), (rows, cols)), shape=(n, n)).tocsr()
+    A.sum_duplicates()
+    L = sp.csr_matrix(-A)
+    L.setdiag(0)
+    L = L + sp.diags(np.asarray(abs(L).sum(axis=1)).ravel() + 1.0)
+    L = sp.csr_matrix(L)
+    L.sort_indices()
+    return verts.astype(np.float64), tets, L
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_coloring_is_valid(pkg, method):
+    # validity checks of deps/mclscene/src/tests/test_graphcolor.cpp:75-130: no two neighbours share
+    # a colour, no two vertices of a tet share a colour, every node coloured exactly once
+    verts, tets, L = _beam_matrix(pkg)
+    colors = pkg.color_matrix(L.indptr, L.indices, L.data, method)
+    color_of = np.full(L.shape[0], -1)
+    for c, nodes in enumerate(colors):
+        assert len(nodes) > 0
+        assert (color_of[nodes] == -1).all()
+        color_of[nodes] = c
+    assert (color_of >= 0).all()
+    coo = L.tocoo()
+    off = coo.row != coo.col
+    assert (color_of[coo.row[off]] != color_of[coo.col[off]]).all()
+    for t in tets:
+        assert len(set(color_of[t])) == 4
+    assert len(colors) <= 24
+
+
+def test_mesh_generator_matches_reference_pattern(pkg):
+    verts, tets = pkg.meshes.make_tet_blocks(3, 2, 2)
+    assert len(tets) == 3 * 2 * 2 * 5 and len(verts) == 4 * 3 * 3
+    v = verts.astype(np.float64)
+    e = np.stack([v[tets[:, 1]] - v[tets[:, 0]], v[tets[:, 2]] - v[tets[:, 0]], v[tets[:, 3]] - v[tets[:, 0]]], axis=2)
+    vol = np.linalg.det(e) / 6.0
+    assert (vol > 0).all()  # no inverted rest tets
+    assert abs(vol.sum() - np.prod(v.max(0) - v.min(0))) < 1e-5  # the 5 tets tile each cube
+    assert abs((v[:, 1].max() - v[:, 1].min()) - 1.0) < 1e-6  # 1 m tall (beams.cpp:61-68)
+    m = pkg.meshes.lumped_masses_tets(verts, tets)
+    assert abs(m.sum() - 1522.0 * vol.sum()) < 1e-2
+
+
+def test_nested_dissection_ldlt_solves(pkg):
+    verts, tets, L = _beam_matrix(pkg, 8, 3, 3)
+    rng = np.random.RandomState(0)
+    b = rng.randn(L.shape[0])
+    x, nnz = pkg.ldlt_solve_host(L.indptr, L.indices, L.data, verts, b)
+    assert np.abs(L @ x - b).max() < 1e-10
+    assert nnz > 0
+
+
+def test_reference_harness_has_no_product_dependency(pkg):
+    # the product libraries must not link against the checkers
+    import subprocess
+    for lib in (pkg.LIB_CUDA_PATH, pkg.LIB_HOST_PATH):
+        out = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
+        assert "liboracle" not in out and "libadmm_ref" not in out
