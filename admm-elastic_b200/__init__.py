@@ -317,9 +317,10 @@ class Solver(object):
         _host.admmhost_set_v(self.h, _dp(v))
 
     def runtime_data(self):
-        out = np.zeros(4)
+        out = np.zeros(6)
         _host.admmhost_runtime(self.h, _dp(out))
-        return {"global_ms": out[0], "local_ms": out[1], "collision_ms": out[2], "inner_iters": int(out[3])}
+        return {"global_ms": out[0], "local_ms": out[1], "collision_ms": out[2], "inner_iters": int(out[3]),
+                "assemble_ms": out[4], "step_ms": out[5]}
 
     def n_rows(self):
         return _host.admmhost_n_rows(self.h)

@@ -581,11 +581,13 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 	s->launches++;
 	zero_duals(s); // curr_u = 0 every step (src/Solver.cpp:71)
 	size_t ev = 0;
+	// events per ADMM iteration: [4it] local [4it+1] assemble [4it+2] solve [4it+3]
 	for (int it = 0; it < admm_iters; ++it) {
 		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
 		launch_local(s);
 		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
 		launch_assemble(s);
+		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
 		launch_global(s);
 		if (rt) {
 			CK(cudaEventRecord(get_event(s, ev++), s->stream));
@@ -599,17 +601,21 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 	CK(cudaGetLastError());
 	s->launches++;
 	if (rt) {
+		cudaEvent_t e_end = get_event(s, ev++);
+		CK(cudaEventRecord(e_end, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
-		rt->global_ms = rt->local_ms = rt->collision_ms = 0; rt->inner_iters = 0;
+		rt->global_ms = rt->local_ms = rt->collision_ms = rt->assemble_ms = rt->step_ms = 0; rt->inner_iters = 0;
 		for (int it = 0; it < admm_iters; ++it) {
-			float a = 0, b = 0;
-			CK(cudaEventElapsedTime(&a, s->events[3 * it], s->events[3 * it + 1]));
-			CK(cudaEventElapsedTime(&b, s->events[3 * it + 1], s->events[3 * it + 2]));
-			rt->local_ms += a; rt->global_ms += b;
+			float a = 0, b = 0, c = 0;
+			CK(cudaEventElapsedTime(&a, s->events[4 * it], s->events[4 * it + 1]));
+			CK(cudaEventElapsedTime(&b, s->events[4 * it + 1], s->events[4 * it + 2]));
+			CK(cudaEventElapsedTime(&c, s->events[4 * it + 2], s->events[4 * it + 3]));
+			rt->local_ms += a; rt->assemble_ms += b; rt->global_ms += b + c;
 		}
+		if (admm_iters > 0) { float t = 0; CK(cudaEventElapsedTime(&t, s->events[0], e_end)); rt->step_ms = t; }
 		if (s->linsolver == ADMM_B200_MCGS) {
 			std::vector<int> its(admm_iters);
-			CK(cudaMemcpy(its.data(), s->iter_log.p, sizeof(int) * admm_iters, cudaMemcpyDeviceToHost));
+			if (admm_iters) CK(cudaMemcpy(its.data(), s->iter_log.p, sizeof(int) * admm_iters, cudaMemcpyDeviceToHost));
 			for (int i : its) rt->inner_iters += i;
 		} else rt->inner_iters = admm_iters; // LDLT / empty-C Uzawa return 1 per solve
 	}
@@ -963,6 +969,19 @@ int admm_b200_upload_state(admm_b200_solver *s, const double *x, const double *v
 int admm_b200_download_state(admm_b200_solver *s, double *x, double *v)
 {
 	return guard(s, [&]() { require(s->n_nodes > 0, "no nodes"); download_state(s, x, v); });
+}
+
+int admm_b200_pin_host(admm_b200_solver *s, void *ptr, unsigned long long bytes)
+{
+	return guard(s, [&]() {
+		require(ptr && bytes > 0, "pin_host: null range");
+		CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+	});
+}
+
+int admm_b200_unpin_host(admm_b200_solver *s, void *ptr)
+{
+	return guard(s, [&]() { require(ptr != nullptr, "unpin_host: null"); CK(cudaHostUnregister(ptr)); });
 }
 
 int admm_b200_step_host(admm_b200_solver *s, int admm_iters, double gravity, double *x, double *v, admm_b200_runtime *runtime)

@@ -302,7 +302,8 @@ public:
 	};
 	struct RuntimeData { // src/Solver.hpp:54-61
 		double global_ms, local_ms, collision_ms; int inner_iters;
-		RuntimeData() : global_ms(0), local_ms(0), collision_ms(0), inner_iters(0) {}
+		double assemble_ms, step_ms; // not in the reference: assembly share of global_ms, device time of the step
+		RuntimeData() : global_ms(0), local_ms(0), collision_ms(0), inner_iters(0), assemble_ms(0), step_ms(0) {}
 		void print(const Settings &settings);
 	};
 	// GPU-side knobs that have no counterpart in Settings (kept out of it to preserve its layout)
@@ -319,7 +320,7 @@ public:
 	} device_options;
 
 	Solver() : initialized(false), handle(nullptr) {}
-	virtual ~Solver() { if (handle) admm_b200_destroy(handle); }
+	virtual ~Solver() { release_device(); }
 	Solver(const Solver &) = delete;
 	Solver &operator=(const Solver &) = delete;
 
@@ -364,6 +365,12 @@ protected:
 	int n_D_rows = 0;
 	bool state_on_device_newer = false;
 
+	bool host_pinned = false;
+	void release_device() {
+		if (!handle) return;
+		if (host_pinned) { admm_b200_unpin_host(handle, m_x.data()); admm_b200_unpin_host(handle, m_v.data()); host_pinned = false; }
+		admm_b200_destroy(handle); handle = nullptr;
+	}
 	void check(int rc, const char *what) {
 		if (rc) { std::stringstream ss; ss << "**admm_b200 " << what << ": " << admm_b200_last_error(handle); throw std::runtime_error(ss.str()); }
 	}
@@ -427,7 +434,7 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 	m_v.assign(dof, 0.0);
 	const int n_nodes = dof / 3;
 
-	if (handle) { admm_b200_destroy(handle); handle = nullptr; }
+	release_device();
 	if (admm_b200_create(device_options.device, &handle)) {
 		std::stringstream ss; ss << "**admm_b200::Solver Error: " << admm_b200_last_error(nullptr);
 		throw std::runtime_error(ss.str());
@@ -543,6 +550,11 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 	} break;
 	}
 	check(admm_b200_finalize(handle, m_settings.timestep_s, m_settings.linsolver, device_options.gs_max_iters, device_options.gs_omega, device_options.gs_tol, device_options.precision), "finalize");
+	// m_x / m_v are read and written by every step(): page-lock them (they do not move after initialize)
+	if (admm_b200_pin_host(handle, m_x.data(), sizeof(double) * m_x.size()) == 0) {
+		if (admm_b200_pin_host(handle, m_v.data(), sizeof(double) * m_v.size()) == 0) host_pinned = true;
+		else admm_b200_unpin_host(handle, m_x.data());
+	}
 	if (m_settings.verbose >= 1) printf("%d nodes, %d energy terms\n", (int)m_x.size() / 3, (int)energyterms.size());
 	initialized = true;
 	state_on_device_newer = false;
@@ -556,7 +568,7 @@ inline void Solver::step() { // src/Solver.cpp:35-110
 	admm_b200_runtime rt;
 	if (state_on_device_newer) sync_state();
 	check(admm_b200_step_host(handle, m_settings.admm_iters, m_settings.gravity, m_x.data(), m_v.data(), device_options.timers ? &rt : nullptr), "step");
-	if (device_options.timers) { m_runtime.global_ms = rt.global_ms; m_runtime.local_ms = rt.local_ms; m_runtime.collision_ms = rt.collision_ms; m_runtime.inner_iters = rt.inner_iters; }
+	if (device_options.timers) { m_runtime.global_ms = rt.global_ms; m_runtime.local_ms = rt.local_ms; m_runtime.collision_ms = rt.collision_ms; m_runtime.inner_iters = rt.inner_iters; m_runtime.assemble_ms = rt.assemble_ms; m_runtime.step_ms = rt.step_ms; }
 	if (m_settings.verbose > 0) m_runtime.print(m_settings);
 }
 

@@ -115,7 +115,7 @@ int admmhost_sync_state(void *h_) { Host *h = (Host *)h_; return guarded(h, [&](
 
 void admmhost_runtime(void *h_, double *out) {
 	const Solver::RuntimeData &r = ((Host *)h_)->solver.runtime_data();
-	out[0] = r.global_ms; out[1] = r.local_ms; out[2] = r.collision_ms; out[3] = r.inner_iters;
+	out[0] = r.global_ms; out[1] = r.local_ms; out[2] = r.collision_ms; out[3] = r.inner_iters; out[4] = r.assemble_ms; out[5] = r.step_ms;
 }
 int admmhost_dof(void *h_) { return (int)((Host *)h_)->solver.m_x.size(); }
 int admmhost_n_terms(void *h_) { return (int)((Host *)h_)->solver.energyterms.size(); }

@@ -61,6 +61,10 @@ typedef struct admm_b200_runtime {
 	double local_ms;
 	double collision_ms;
 	int inner_iters;
+	/* extra to the reference's fields: the b = M x_bar + D^T W (z-u) assembly share of global_ms,
+	 * and the device time of the whole step (first to last kernel) */
+	double assemble_ms;
+	double step_ms;
 } admm_b200_runtime;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -142,6 +146,11 @@ int admm_b200_step( admm_b200_solver *s, int admm_iters, double gravity, admm_b2
  * caller that reads m_x after every step() sees (samples/utils/Application.hpp:274-299). */
 int admm_b200_step_host( admm_b200_solver *s, int admm_iters, double gravity, double *x, double *v, admm_b200_runtime *runtime );
 int admm_b200_upload_state( admm_b200_solver *s, const double *x, const double *v );
+/* Page-locks a caller-owned host range (the storage behind m_x / m_v, src/Solver.hpp:66-67) so the
+ * per-step copies of admm_b200_step_host run at full PCIe/C2C rate and asynchronously; unpin before
+ * the memory is freed.  Pinning is an optimisation only: step_host accepts pageable memory too. */
+int admm_b200_pin_host( admm_b200_solver *s, void *ptr, unsigned long long bytes );
+int admm_b200_unpin_host( admm_b200_solver *s, void *ptr );
 int admm_b200_download_state( admm_b200_solver *s, double *x, double *v );
 
 /* ---- pieces of the path, for parity tests and micro-benchmarks ----------------------------- */

@@ -52,6 +52,7 @@ struct PeekSolver : public admm::Solver {
 		}
 		return ok;
 	}
+	void set_admm_iters( int it ){ m_settings.admm_iters = it; } // Settings are copied at initialize (src/Solver.cpp:168)
 	const SparseMat &D() const { return m_D; }
 	const VecX &W() const { return m_W_diag; }
 	const SparseMat &A() const { return solver_termA; }
@@ -208,6 +209,8 @@ int ref_initialize( void *h_, double dt, int admm_iters, double gravity, int lin
 	});
 	return e ? e : rc;
 }
+
+void ref_set_admm_iters( void *h_, int it ){ ((Handle*)h_)->solver.set_admm_iters( it ); }
 
 int ref_step( void *h_ ){ Handle *h=(Handle*)h_; return guarded( h, [&](){ h->solver.step(); } ); }
 
