@@ -197,8 +197,7 @@ template <typename E, int MODEL> void launch_tet_model(S *s, TetBatchH *t)
 	tb.u = (E *)t->d_u.p;
 	tb.z = (E *)t->d_z.p;
 	tb.f = (typename Vec4<E>::type *)s->f.p + t->slot_base;
-	double K = t->lambda + (2.0 / 3.0) * t->mu; // Lame::bulk_modulus (src/EnergyTerm.hpp:41)
-	tb.mat.a = E(t->mu / K); tb.mat.l = E(t->lambda / K); tb.mat.kap = E(t->kappa / K);
+	tb.mat = Material<E>::make(t->mu, t->lambda, t->kappa);
 	const int threads = 128;
 	int blocks = (t->n + threads - 1) / threads;
 	if (s->store_z && t->d_z.p) tet_local_kernel<E, MODEL, true><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
@@ -660,8 +659,7 @@ template <typename E> void prox_tets_impl(S *s, int model, double mu, double lam
 	std::vector<E> tmp((size_t)9 * n_pad, E(0));
 	for (int e = 0; e < n; ++e) for (int k = 0; k < 9; ++k) tmp[(size_t)k * n_pad + e] = E(z_in[(size_t)9 * e + k]);
 	DevBuf<E> d; d.upload(tmp, s->stream);
-	double K = lambda + (2.0 / 3.0) * mu;
-	Material<E> mat; mat.a = E(mu / K); mat.l = E(lambda / K); mat.kap = E(kappa / K);
+	Material<E> mat = Material<E>::make(mu, lambda, kappa);
 	int threads = 128, blocks = (n + threads - 1) / threads;
 	switch (model) {
 	case TET_LINEAR: tet_prox_only_kernel<E, TET_LINEAR><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;

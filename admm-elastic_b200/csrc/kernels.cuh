@@ -87,7 +87,7 @@ struct TetBatch {
 };
 
 template <typename E, int MODEL, bool STORE_Z>
-__global__ void __launch_bounds__(128) tet_local_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
+__global__ void __launch_bounds__(128, 4) tet_local_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
 {
 	int e = blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= tb.n) return;

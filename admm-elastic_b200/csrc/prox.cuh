@@ -19,26 +19,37 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+// Every function here is pure register arithmetic.  ADMMB200_FN is __device__ in the product build;
+// tests/tools/prox_host.cu recompiles the same source for the host (ADMMB200_HOST_SHIM) so that
+// parity problems can be studied without a GPU.  The product library never defines that macro.
+#ifdef ADMMB200_HOST_SHIM
+#define ADMMB200_FN __host__ __device__ __forceinline__
+#define ADMMB200_SLOWPATH __host__ __device__ __noinline__
+#else
+#define ADMMB200_FN __device__ __forceinline__
+#define ADMMB200_SLOWPATH __device__ __noinline__
+#endif
+
 namespace admmb200 {
 
 enum TetModel { TET_LINEAR = 0, TET_NEOHOOKEAN = 1, TET_STVK = 2, TET_SPLINE_NH = 3, TET_SPLINE_STVK = 4, TET_SPLINE_COROT = 5 };
 
 template <typename T> struct Num;
 template <> struct Num<float> {
-	static __device__ __forceinline__ float eps() { return 1.1920929e-7f; }
-	static __device__ __forceinline__ float tiny() { return 1e-30f; }
-	static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
-	static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
-	static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+	static ADMMB200_FN float eps() { return 1.1920929e-7f; }
+	static ADMMB200_FN float tiny() { return 1e-30f; }
+	static ADMMB200_FN float rsqrt(float x) { return ::rsqrtf(x); }
+	static ADMMB200_FN float sqrt(float x) { return ::sqrtf(x); }
+	static ADMMB200_FN float log(float x) { return ::logf(x); }
 	static constexpr int jacobi_sweeps = 5;
 	static constexpr int newton_iters = 24;
 };
 template <> struct Num<double> {
-	static __device__ __forceinline__ double eps() { return 2.220446049250313e-16; }
-	static __device__ __forceinline__ double tiny() { return 1e-290; }
-	static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
-	static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-	static __device__ __forceinline__ double log(double x) { return ::log(x); }
+	static ADMMB200_FN double eps() { return 2.220446049250313e-16; }
+	static ADMMB200_FN double tiny() { return 1e-290; }
+	static ADMMB200_FN double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+	static ADMMB200_FN double sqrt(double x) { return ::sqrt(x); }
+	static ADMMB200_FN double log(double x) { return ::log(x); }
 	static constexpr int jacobi_sweeps = 8;
 	static constexpr int newton_iters = 48;
 };
@@ -46,7 +57,7 @@ template <> struct Num<double> {
 // One Jacobi rotation in the (p,q) plane of a symmetric 3x3 matrix; r is the third index.
 // A' = P^T A P, V' = V P with P a proper rotation, so det V stays +1.
 template <typename T>
-__device__ __forceinline__ void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &arq,
+ADMMB200_FN void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &arq,
 	T &v0p, T &v0q, T &v1p, T &v1q, T &v2p, T &v2q)
 {
 	if (fabs(apq) <= Num<T>::eps() * T(0.125) * (fabs(app) + fabs(aqq)) || fabs(apq) < Num<T>::tiny()) { apq = (fabs(apq) < Num<T>::tiny()) ? T(0) : apq; return; }
@@ -68,7 +79,7 @@ __device__ __forceinline__ void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &ar
 // sign(S[2]) = sign(det F): the convention signed_svd (src/FastSVD.hpp:43-68) produces.
 // U, V are column-major too.
 template <typename T>
-__device__ __forceinline__ void svd3_signed(const T *F, T *S, T *U, T *V)
+ADMMB200_FN void svd3_signed(const T *F, T *S, T *U, T *V)
 {
 	// C = F^T F
 	T c00 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
@@ -130,7 +141,7 @@ __device__ __forceinline__ void svd3_signed(const T *F, T *S, T *U, T *V)
 
 // Z = U diag(s) V^T, column-major.
 template <typename T>
-__device__ __forceinline__ void usvt(const T *U, const T *s, const T *V, T *Z)
+ADMMB200_FN void usvt(const T *U, const T *s, const T *V, T *Z)
 {
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
@@ -147,17 +158,27 @@ __device__ __forceinline__ void usvt(const T *U, const T *s, const T *V, T *Z)
 // (HyperElasticTet::Prox::value = energy_density + k/2 |x-x0|^2; src/TetEnergyTerm.cpp:183-191).
 // Each model returns value, gradient g[3] and Hessian h = {h00,h11,h22,h01,h02,h12}.
 // ---------------------------------------------------------------------------------------------
-template <typename T> struct Material { T a, l, kap; }; // mu/K, lambda/K, kappa/K
+template <typename T> struct Material {
+	T a, l, kap;              // mu/K, lambda/K, kappa/K (the Newton path works on the objective divided by K)
+	double mu, lambda, kappa; // raw constants, only read by the reference-faithful path (prox_lbfgs_reference)
+	static Material make(double mu_, double lambda_, double kappa_) {
+		Material m;
+		double K = lambda_ + (2.0 / 3.0) * mu_; // Lame::bulk_modulus (src/EnergyTerm.hpp:41)
+		m.a = T(mu_ / K); m.l = T(lambda_ / K); m.kap = T(kappa_ / K);
+		m.mu = mu_; m.lambda = lambda_; m.kappa = kappa_;
+		return m;
+	}
+};
 
 template <typename T, int MODEL> struct Energy;
 
 // NHProx (src/TetEnergyTerm.cpp:173-204): Psi = mu/2 (I1 - log I3 - 3) + lambda/8 log^2 I3
 template <typename T> struct Energy<T, TET_NEOHOOKEAN> {
-	static __device__ __forceinline__ T value(const Material<T> &m, const T *x) {
+	static ADMMB200_FN T value(const Material<T> &m, const T *x) {
 		T lj = Num<T>::log(x[0] * x[1] * x[2]);
 		return T(0.5) * m.a * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] - T(2) * lj - T(3)) + T(0.5) * m.l * lj * lj;
 	}
-	static __device__ __forceinline__ void derivs(const Material<T> &m, const T *x, T *g, T *h) {
+	static ADMMB200_FN void derivs(const Material<T> &m, const T *x, T *g, T *h) {
 		T lj = Num<T>::log(x[0] * x[1] * x[2]);
 		T i0 = T(1) / x[0], i1 = T(1) / x[1], i2 = T(1) / x[2];
 		T q = m.l * lj - m.a; // (lambda log J - mu)
@@ -170,12 +191,12 @@ template <typename T> struct Energy<T, TET_NEOHOOKEAN> {
 
 // StVKProx (src/TetEnergyTerm.cpp:210-237): E = (x^2-1)/2, Psi = mu |E|^2 + lambda/2 tr(E)^2
 template <typename T> struct Energy<T, TET_STVK> {
-	static __device__ __forceinline__ T value(const Material<T> &m, const T *x) {
+	static ADMMB200_FN T value(const Material<T> &m, const T *x) {
 		T e0 = T(0.5) * (x[0] * x[0] - T(1)), e1 = T(0.5) * (x[1] * x[1] - T(1)), e2 = T(0.5) * (x[2] * x[2] - T(1));
 		T tr = e0 + e1 + e2;
 		return m.a * (e0 * e0 + e1 * e1 + e2 * e2) + T(0.5) * m.l * tr * tr;
 	}
-	static __device__ __forceinline__ void derivs(const Material<T> &m, const T *x, T *g, T *h) {
+	static ADMMB200_FN void derivs(const Material<T> &m, const T *x, T *g, T *h) {
 		T n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
 		T q = T(0.5) * m.l * (n2 - T(3));
 #pragma unroll
@@ -190,49 +211,49 @@ template <typename T> struct Energy<T, TET_STVK> {
 // xu::Spline materials (src/XuSpline.hpp:34-94): Psi = sum f(x_i) + sum g(x_i x_j) + h(x0 x1 x2)
 // (SplineProx::energy_density, src/TetEnergyTerm.cpp:243-247).  fgh[k] = {value, d, dd}.
 template <typename T, int MODEL> struct Spline;
-template <typename T> __device__ __forceinline__ void compress_term(T kap, T x, T *o) {
+template <typename T> ADMMB200_FN void compress_term(T kap, T x, T *o) {
 	T s = (T(1) - x) / T(6);
 	o[0] += (kap / T(12)) * s * s * s; o[1] += (-kap / T(24)) * s * s; o[2] += (kap / T(72)) * s;
 }
 template <typename T> struct Spline<T, TET_SPLINE_NH> {
-	static __device__ __forceinline__ void f(const Material<T> &m, T x, T *o) { o[0] = T(0.5) * m.a * (x * x - T(1)); o[1] = m.a * x; o[2] = m.a; }
-	static __device__ __forceinline__ void g(const Material<T> &, T, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; }
-	static __device__ __forceinline__ void h(const Material<T> &m, T x, T *o) {
+	static ADMMB200_FN void f(const Material<T> &m, T x, T *o) { o[0] = T(0.5) * m.a * (x * x - T(1)); o[1] = m.a * x; o[2] = m.a; }
+	static ADMMB200_FN void g(const Material<T> &, T, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; }
+	static ADMMB200_FN void h(const Material<T> &m, T x, T *o) {
 		T lx = Num<T>::log(x), ix = T(1) / x;
 		o[0] = -m.a * lx + T(0.5) * m.l * lx * lx; o[1] = (m.l * lx - m.a) * ix; o[2] = (m.a + m.l - m.l * lx) * ix * ix;
 		compress_term(m.kap, x, o);
 	}
 };
 template <typename T> struct Spline<T, TET_SPLINE_STVK> {
-	static __device__ __forceinline__ void f(const Material<T> &m, T x, T *o) {
+	static ADMMB200_FN void f(const Material<T> &m, T x, T *o) {
 		T x2 = x * x;
 		o[0] = T(0.125) * m.l * (x2 * x2 - T(6) * x2 + T(5)) + T(0.25) * m.a * (x2 - T(1)) * (x2 - T(1));
 		o[1] = T(0.125) * m.l * (T(4) * x2 * x - T(12) * x) + m.a * x * (x2 - T(1));
 		o[2] = T(0.125) * m.l * (T(12) * x2 - T(12)) + m.a * (T(3) * x2 - T(1));
 	}
-	static __device__ __forceinline__ void g(const Material<T> &m, T x, T *o) { o[0] = T(0.25) * m.l * (x * x - T(1)); o[1] = T(0.5) * m.l * x; o[2] = T(0.5) * m.l; }
-	static __device__ __forceinline__ void h(const Material<T> &m, T x, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; compress_term(m.kap, x, o); }
+	static ADMMB200_FN void g(const Material<T> &m, T x, T *o) { o[0] = T(0.25) * m.l * (x * x - T(1)); o[1] = T(0.5) * m.l * x; o[2] = T(0.5) * m.l; }
+	static ADMMB200_FN void h(const Material<T> &m, T x, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; compress_term(m.kap, x, o); }
 };
 template <typename T> struct Spline<T, TET_SPLINE_COROT> {
-	static __device__ __forceinline__ void f(const Material<T> &m, T x, T *o) {
+	static ADMMB200_FN void f(const Material<T> &m, T x, T *o) {
 		o[0] = T(0.5) * m.l * (x * x - T(6) * x + T(5)) + m.a * (x - T(1)) * (x - T(1));
 		o[1] = T(0.5) * m.l * (T(2) * x - T(6)) + T(2) * m.a * (x - T(1));
 		o[2] = m.l + T(2) * m.a;
 	}
-	static __device__ __forceinline__ void g(const Material<T> &m, T x, T *o) { o[0] = m.l * (x - T(1)); o[1] = m.l; o[2] = 0; }
-	static __device__ __forceinline__ void h(const Material<T> &m, T x, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; compress_term(m.kap, x, o); }
+	static ADMMB200_FN void g(const Material<T> &m, T x, T *o) { o[0] = m.l * (x - T(1)); o[1] = m.l; o[2] = 0; }
+	static ADMMB200_FN void h(const Material<T> &m, T x, T *o) { o[0] = 0; o[1] = 0; o[2] = 0; compress_term(m.kap, x, o); }
 };
 
 template <typename T, int MODEL> struct SplineEnergy {
 	typedef Spline<T, MODEL> Sp;
-	static __device__ __forceinline__ T value(const Material<T> &m, const T *x) {
+	static ADMMB200_FN T value(const Material<T> &m, const T *x) {
 		T o[3], v = 0;
 		Sp::f(m, x[0], o); v += o[0]; Sp::f(m, x[1], o); v += o[0]; Sp::f(m, x[2], o); v += o[0];
 		Sp::g(m, x[0] * x[1], o); v += o[0]; Sp::g(m, x[1] * x[2], o); v += o[0]; Sp::g(m, x[2] * x[0], o); v += o[0];
 		Sp::h(m, x[0] * x[1] * x[2], o); v += o[0];
 		return v;
 	}
-	static __device__ __forceinline__ void derivs(const Material<T> &m, const T *x, T *g, T *h) {
+	static ADMMB200_FN void derivs(const Material<T> &m, const T *x, T *g, T *h) {
 		T f0[3], f1[3], f2[3], g01[3], g12[3], g20[3], hh[3];
 		Sp::f(m, x[0], f0); Sp::f(m, x[1], f1); Sp::f(m, x[2], f2);
 		Sp::g(m, x[0] * x[1], g01); Sp::g(m, x[1] * x[2], g12); Sp::g(m, x[2] * x[0], g20);
@@ -257,9 +278,12 @@ template <typename T> struct Energy<T, TET_SPLINE_COROT> : SplineEnergy<T, TET_S
 template <int MODEL> struct NeedsPositive { static constexpr bool value = (MODEL == TET_NEOHOOKEAN || MODEL == TET_SPLINE_NH); };
 
 // argmin_x>=0 phi(x), started at x (already made feasible), quadratic centre x0.
+// Returns true when the result is NOT a converged interior minimiser (a stretch ended on the bound
+// x = 0, or the iteration budget ran out): the caller then reproduces the reference's own optimiser.
 template <typename T, int MODEL>
-__device__ __forceinline__ void prox_newton(const Material<T> &m, const T *x0, T *x)
+ADMMB200_FN bool prox_newton(const Material<T> &m, const T *x0, T *x)
 {
+	bool converged = false;
 	typedef Energy<T, MODEL> En;
 	const T floor_x = NeedsPositive<MODEL>::value ? T(1e-12) : T(0);
 #pragma unroll 1
@@ -268,6 +292,16 @@ __device__ __forceinline__ void prox_newton(const Material<T> &m, const T *x0, T
 		En::derivs(m, x, g, h);
 		g[0] += x[0] - x0[0]; g[1] += x[1] - x0[1]; g[2] += x[2] - x0[2];
 		h[0] += T(1); h[1] += T(1); h[2] += T(1);
+		// Active set of the bound x >= 0 (value() is +inf for x<0, src/TetEnergyTerm.cpp:184-188): a
+		// stretch that sits on the bound with the objective still decreasing outwards stays there and
+		// the Newton system is solved for the free stretches only (inverted StVK / spline elements end
+		// on the face x2 = 0, where the reference's barrier line search creeps to as well).
+		if (!NeedsPositive<MODEL>::value) {
+			const T on_bound = T(1e-7);
+			if (x[0] <= on_bound && g[0] > T(0)) { x[0] = T(0); g[0] = T(0); h[0] = T(1); h[3] = T(0); h[4] = T(0); }
+			if (x[1] <= on_bound && g[1] > T(0)) { x[1] = T(0); g[1] = T(0); h[1] = T(1); h[3] = T(0); h[5] = T(0); }
+			if (x[2] <= on_bound && g[2] > T(0)) { x[2] = T(0); g[2] = T(0); h[2] = T(1); h[4] = T(0); h[5] = T(0); }
+		}
 		// Newton direction by LDL^T; if H is not positive definite fall back to a scaled gradient step
 		T d[3];
 		bool pd = true;
@@ -305,7 +339,7 @@ __device__ __forceinline__ void prox_newton(const Material<T> &m, const T *x0, T
 		T xn[3];
 #pragma unroll 1
 		for (int ls = 0; ls < 16; ++ls) {
-			xn[0] = x[0] + t * d[0]; xn[1] = x[1] + t * d[1]; xn[2] = x[2] + t * d[2];
+			xn[0] = fmax(x[0] + t * d[0], floor_x); xn[1] = fmax(x[1] + t * d[1], floor_x); xn[2] = fmax(x[2] + t * d[2], floor_x);
 			T e0 = xn[0] - x0[0], e1 = xn[1] - x0[1], e2 = xn[2] - x0[2];
 			T phi = En::value(m, xn) + T(0.5) * (e0 * e0 + e1 * e1 + e2 * e2);
 			if (phi <= phi0 + T(1e-4) * t * gd + slack) break;
@@ -314,13 +348,133 @@ __device__ __forceinline__ void prox_newton(const Material<T> &m, const T *x0, T
 		T step = t * fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2]));
 		x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
 		T scale = T(1) + fmax(fmax(fabs(x[0]), fabs(x[1])), fabs(x[2]));
-		if (step <= T(4) * Num<T>::eps() * scale) break;
+		if (step <= T(4) * Num<T>::eps() * scale) { converged = true; break; }
+	}
+	// "near the bound" is generous on purpose: the slow path IS the reference's algorithm
+	return !converged || (!NeedsPositive<MODEL>::value && (x[0] < T(1e-3) || x[1] < T(1e-3) || x[2] < T(1e-3)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-faithful path for DEGENERATE elements only.
+//
+// When the minimiser of the prox objective lies on the bound x = 0 (inverted or nearly flat StVK /
+// spline elements) the reference does not reach it: its L-BFGS creeps towards the bound through a
+// line search whose trial points beyond x = 0 evaluate to FLT_MAX, and stops by |dx| < 1e-6
+// (src/TetEnergyTerm.hpp:93-95).  The answer is then a property of the optimiser's path, so the only
+// way to agree with it is to walk the same path: LBFGS<double,3,8>::minimize
+// (deps/mcloptlib/include/MCL/LBFGS.hpp:52-152: history 8, max 50 iterations, steepest-descent restart
+// with alpha = min(1, 1/|g|_inf) on a non-descent direction, FAILURE on rate <= 0) with
+// BacktrackingCubic::search (Backtracking.hpp:79-143; ls_decrease 1e-4, ls_max_iters 100000,
+// Minimizer.hpp:66-70), in fp64 and in the reference's unscaled units.  Out of line and never inlined:
+// the hot path pays one predicted-not-taken branch.
+// ---------------------------------------------------------------------------------------------
+template <int MODEL> struct RefProblem {
+	Material<double> m; // a = mu, l = lambda, kap = kappa (raw)
+	double k, x0[3];
+	ADMMB200_FN double value(const double *x) const { // Prox::value (src/TetEnergyTerm.cpp:184-192, 210-218, 249-257)
+		if (x[0] < 0.0 || x[1] < 0.0 || x[2] < 0.0) return 3.4028234663852886e38; // numeric_limits<float>::max()
+		double d0 = x[0] - x0[0], d1 = x[1] - x0[1], d2 = x[2] - x0[2];
+		return Energy<double, MODEL>::value(m, x) + (k * 0.5) * (d0 * d0 + d1 * d1 + d2 * d2);
+	}
+	ADMMB200_FN double gradient(const double *x, double *g) const { // Prox::gradient (:195-204, 228-237, 259-265)
+		double h[6];
+		Energy<double, MODEL>::derivs(m, x, g, h);
+		g[0] += k * (x[0] - x0[0]); g[1] += k * (x[1] - x0[1]); g[2] += k * (x[2] - x0[2]);
+		return value(x);
+	}
+};
+
+template <int MODEL>
+ADMMB200_SLOWPATH void prox_lbfgs_reference(double mu, double lambda, double kappa, const double *x0, double *x)
+{
+	RefProblem<MODEL> P;
+	P.m.a = mu; P.m.l = lambda; P.m.kap = kappa; P.m.mu = mu; P.m.lambda = lambda; P.m.kappa = kappa;
+	P.k = lambda + (2.0 / 3.0) * mu;
+	P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
+	const int M = 8;
+	double s[M][3], y[M][3], alpha[M], rho[M];
+	double grad[3], q[3], grad_old[3], x_old[3];
+	double gamma_k = 1.0, alpha_init = 1.0;
+	int max_iters = 50;
+	for (int i = 0; i < M; ++i) for (int j = 0; j < 3; ++j) { s[i][j] = 0.0; y[i][j] = 0.0; }
+	if (NeedsPositive<MODEL>::value && x[0] * x[1] * x[2] <= 0.0) return; // the reference's gradient() throws here
+	P.gradient(x, grad);
+	for (int k = 0; k < max_iters; ++k) {
+		const int iter = k < M ? k : M;
+		for (int j = 0; j < 3; ++j) { x_old[j] = x[j]; grad_old[j] = grad[j]; q[j] = grad[j]; }
+		for (int i = iter - 1; i >= 0; --i) { // two-loop recursion (LBFGS.hpp:87-100)
+			rho[i] = 1.0 / (s[i][0] * y[i][0] + s[i][1] * y[i][1] + s[i][2] * y[i][2]);
+			alpha[i] = rho[i] * (s[i][0] * q[0] + s[i][1] * q[1] + s[i][2] * q[2]);
+			for (int j = 0; j < 3; ++j) q[j] -= alpha[i] * y[i][j];
+		}
+		for (int j = 0; j < 3; ++j) q[j] *= gamma_k;
+		for (int i = 0; i < iter; ++i) {
+			double beta = rho[i] * (q[0] * y[i][0] + q[1] * y[i][1] + q[2] * y[i][2]);
+			for (int j = 0; j < 3; ++j) q[j] += (alpha[i] - beta) * s[i][j];
+		}
+		if (q[0] * grad[0] + q[1] * grad[1] + q[2] * grad[2] <= 0.0) { // not a descent direction: restart (:102-109)
+			double inf = fmax(fabs(grad[0]), fmax(fabs(grad[1]), fabs(grad[2])));
+			for (int j = 0; j < 3; ++j) q[j] = grad[j];
+			max_iters -= k; k = 0;
+			alpha_init = fmin(1.0, 1.0 / inf);
+		}
+		// BacktrackingCubic::search along -q
+		double dir[3] = {-q[0], -q[1], -q[2]};
+		double rate;
+		if (sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]) <= 2.220446049250313e-16) rate = 1e-4;
+		else {
+			double g0[3];
+			if (NeedsPositive<MODEL>::value && x[0] * x[1] * x[2] <= 0.0) return;
+			const double fx0 = P.gradient(x, g0);
+			const double gtp = g0[0] * dir[0] + g0[1] * dir[1] + g0[2] * dir[2];
+			double fxp = fx0, a = alpha_init, ap = alpha_init;
+			int it = 0;
+			const int ls_max = 100000;
+			for (; it < ls_max; ++it) {
+				double xa[3] = {x[0] + a * dir[0], x[1] + a * dir[1], x[2] + a * dir[2]};
+				double fxa = P.value(xa);
+				if (fxa <= fx0 + a * 1e-4 * gtp) break;
+				double at;
+				if (it == 0) at = gtp / (2.0 * (fx0 + gtp - fxa));
+				else { // cubic interpolation through the last two trials (Backtracking.hpp:129-143)
+					double mult = 1.0 / (a * a * ap * ap * (a - ap));
+					double B0 = fxa - fx0 - a * gtp, B1 = fxp - fx0 - ap * gtp;
+					double r0 = mult * (ap * ap * B0 - a * a * B1), r1 = mult * (-ap * ap * ap * B0 + a * a * a * B1);
+					if (fabs(r0) <= 0.0) at = -gtp / (2.0 * r1);
+					else at = (-r1 + sqrt(r1 * r1 - 3.0 * r0 * gtp)) / (3.0 * r0);
+				}
+				fxp = fxa; ap = a;
+				if (at != at) a = at; // range() hands a NaN through
+				else { double lo = 0.1 * a, hi = 0.5 * a; a = at < lo ? lo : (at > hi ? hi : at); }
+			}
+			rate = it >= ls_max ? -1.0 : a;
+		}
+		if (!(rate > 0.0)) return; // Minimizer::FAILURE: x stays at the last iterate (:113-116)
+		double xl[3] = {x[0], x[1], x[2]};
+		for (int j = 0; j < 3; ++j) x[j] -= rate * q[j];
+		{ // converged(x_last, x, grad of the previous iterate) (:120, src/TetEnergyTerm.hpp:93-95)
+			double d0 = xl[0] - x[0], d1 = xl[1] - x[1], d2 = xl[2] - x[2];
+			if (sqrt(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]) < 1e-6 || sqrt(d0 * d0 + d1 * d1 + d2 * d2) < 1e-6) break;
+		}
+		if (NeedsPositive<MODEL>::value && x[0] * x[1] * x[2] <= 0.0) return;
+		P.gradient(x, grad);
+		double st[3], yt[3];
+		for (int j = 0; j < 3; ++j) { st[j] = x[j] - x_old[j]; yt[j] = grad[j] - grad_old[j]; }
+		if (k < M) { for (int j = 0; j < 3; ++j) { s[k][j] = st[j]; y[k][j] = yt[j]; } }
+		else {
+			for (int i = 0; i < M - 1; ++i) for (int j = 0; j < 3; ++j) { s[i][j] = s[i + 1][j]; y[i][j] = y[i + 1][j]; }
+			for (int j = 0; j < 3; ++j) { s[M - 1][j] = st[j]; y[M - 1][j] = yt[j]; }
+		}
+		double denom = yt[0] * yt[0] + yt[1] * yt[1] + yt[2] * yt[2];
+		if (fabs(denom) <= 0.0) break;
+		gamma_k = (st[0] * yt[0] + st[1] * yt[1] + st[2] * yt[2]) / denom;
+		alpha_init = 1.0;
 	}
 }
 
 // HyperElasticTet::prox (src/TetEnergyTerm.cpp:114-136) on a column-major 3x3 z (in/out).
 template <typename T, int MODEL>
-__device__ __forceinline__ void prox_tet(const Material<T> &m, T *z)
+ADMMB200_FN void prox_tet(const Material<T> &m, T *z)
 {
 	T S[3], U[9], V[9];
 	svd3_signed(z, S, U, V);
@@ -335,18 +489,31 @@ __device__ __forceinline__ void prox_tet(const Material<T> &m, T *z)
 	}
 	T x0[3] = {S[0], S[1], S[2]};
 	const T eps = T(1e-6);
-	if (fabs(S[0]) < eps && fabs(S[1]) < eps && fabs(S[2]) < eps) { S[0] = eps; S[1] = eps; S[2] = eps; }
+	bool collapsed = false;
+	if (fabs(S[0]) < eps && fabs(S[1]) < eps && fabs(S[2]) < eps) { S[0] = eps; S[1] = eps; S[2] = eps; collapsed = true; }
 	if (S[2] < T(0)) S[2] = -S[2];
 	if (NeedsPositive<MODEL>::value) {
 		// the start point of the reference can sit exactly on the barrier (S[2]==0); nudge it inside
 		const T lo = T(1e-7);
 		S[0] = fmax(S[0], lo); S[1] = fmax(S[1], lo); S[2] = fmax(S[2], lo);
 	}
-	if (MODEL == TET_NEOHOOKEAN) prox_newton<T, TET_NEOHOOKEAN>(m, x0, S);
-	if (MODEL == TET_STVK) prox_newton<T, TET_STVK>(m, x0, S);
-	if (MODEL == TET_SPLINE_NH) prox_newton<T, TET_SPLINE_NH>(m, x0, S);
-	if (MODEL == TET_SPLINE_STVK) prox_newton<T, TET_SPLINE_STVK>(m, x0, S);
-	if (MODEL == TET_SPLINE_COROT) prox_newton<T, TET_SPLINE_COROT>(m, x0, S);
+	T start[3] = {S[0], S[1], S[2]};
+	// an element collapsed to a point starts 6 decades from its minimiser: where the reference's
+	// optimiser stops from there is path-dependent too (src/TetEnergyTerm.cpp:126-129)
+	bool degenerate = collapsed;
+	if (!collapsed) {
+	if (MODEL == TET_NEOHOOKEAN) degenerate = prox_newton<T, TET_NEOHOOKEAN>(m, x0, S);
+	if (MODEL == TET_STVK) degenerate = prox_newton<T, TET_STVK>(m, x0, S);
+	if (MODEL == TET_SPLINE_NH) degenerate = prox_newton<T, TET_SPLINE_NH>(m, x0, S);
+	if (MODEL == TET_SPLINE_STVK) degenerate = prox_newton<T, TET_SPLINE_STVK>(m, x0, S);
+	if (MODEL == TET_SPLINE_COROT) degenerate = prox_newton<T, TET_SPLINE_COROT>(m, x0, S);
+	}
+	if (degenerate) {
+		// minimiser on the bound (or no convergence): walk the reference optimiser's own path in fp64
+		double xs[3] = {double(start[0]), double(start[1]), double(start[2])}, xc[3] = {double(x0[0]), double(x0[1]), double(x0[2])};
+		if (MODEL != TET_LINEAR) prox_lbfgs_reference<MODEL == TET_LINEAR ? TET_STVK : MODEL>(m.mu, m.lambda, m.kappa, xc, xs);
+		S[0] = T(xs[0]); S[1] = T(xs[1]); S[2] = T(xs[2]);
+	}
 	usvt(U, S, V, z);
 }
 
@@ -354,7 +521,7 @@ __device__ __forceinline__ void prox_tet(const Material<T> &m, T *z)
 // P = U[:, :2] V^T (nearest matrix with singular values 1,1), z = (P+z)/2, then the optional
 // column-norm strain limit.
 template <typename T>
-__device__ __forceinline__ void prox_tri(T limit_min, T limit_max, T *z)
+ADMMB200_FN void prox_tri(T limit_min, T limit_max, T *z)
 {
 	T a = z[0] * z[0] + z[1] * z[1] + z[2] * z[2];
 	T b = z[0] * z[3] + z[1] * z[4] + z[2] * z[5];
