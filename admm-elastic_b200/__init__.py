@@ -288,6 +288,10 @@ class Solver(object):
     def step_device(self):
         self._ck(_host.admmhost_step_device(self.h))
 
+    def upload_state(self):
+        """Host m_x / m_v -> device (step_device() does not look at the host copies)."""
+        self._ck(_host.admmhost_upload_state(self.h))
+
     def sync_state(self):
         self._ck(_host.admmhost_sync_state(self.h))
 

@@ -344,8 +344,10 @@ public:
 
 	// device-resident stepping for callers that do not need m_x every frame: step_device() leaves the
 	// state on the GPU, sync_state() brings m_x / m_v back.
+	// step_device() does NOT look at m_x / m_v: after writing to them call upload_state() first.
 	void step_device();
 	void sync_state();
+	void upload_state();
 	admm_b200_solver *device_handle() { return handle; }
 	const sparse::Csr &system_matrix() const { return scalarL; }
 	const std::vector<std::vector<int>> &colors() const { return m_colors; }
@@ -576,6 +578,12 @@ inline void Solver::step_device() {
 	if (!initialized) throw std::runtime_error("**Solver::step Error: not initialized");
 	check(admm_b200_step(handle, m_settings.admm_iters, m_settings.gravity, nullptr), "step");
 	state_on_device_newer = true;
+}
+
+inline void Solver::upload_state() {
+	if (!initialized) throw std::runtime_error("**Solver::upload_state Error: not initialized");
+	check(admm_b200_upload_state(handle, m_x.data(), m_v.data()), "upload_state");
+	state_on_device_newer = false;
 }
 
 inline void Solver::sync_state() {

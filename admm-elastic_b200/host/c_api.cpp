@@ -111,6 +111,7 @@ int admmhost_set_admm_iters(void *h_, int it) {
 
 int admmhost_step(void *h_) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.step(); }); }
 int admmhost_step_device(void *h_) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.step_device(); }); }
+int admmhost_upload_state(void *h_) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.upload_state(); }); }
 int admmhost_sync_state(void *h_) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.sync_state(); }); }
 
 void admmhost_runtime(void *h_, double *out) {

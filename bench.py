@@ -321,7 +321,7 @@ def run_b200(args):
         return ms, acc
 
     # ---- resident path: state stays in HBM -------------------------------------------------------
-    sol.step()  # first call: uploads x0
+    sol.upload_state()  # x0 -> device
     for _ in range(W):
         sol.step_device()
     clocks = ClockSampler(local_rank)

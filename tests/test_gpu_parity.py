@@ -439,6 +439,8 @@ def test_device_resident_steps_equal_host_steps(pkg):
         s = gpu_solver(pkg, 0)
         scenes.build_tet_scene(s, scene, 1, linsolver=1, iters=5)
         s.set_x(scenes.bend(scene[0]).ravel())
+        if resident:
+            s.upload_state()
         for _ in range(3):
             s.step_device() if resident else s.step()
         if resident:
