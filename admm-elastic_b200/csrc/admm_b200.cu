@@ -117,6 +117,7 @@ struct admm_b200_solver {
 	DevBuf<int> d_pin_slot;
 	DevBuf<double> d_pin_pos;
 	std::vector<Obstacle> obstacles;
+	DevBuf<Obstacle> d_obstacles;
 
 	// mcgs device
 	int gs_lanes = 4;
@@ -273,12 +274,12 @@ void launch_assemble(S *s)
 template <int T> void mcgs_launch_T(S *s, McgsParams &P)
 {
 	void *args[] = {&P};
-	CK(cudaLaunchCooperativeKernel((void *)mcgs_kernel<T>, dim3(s->gs_grid), dim3(512), args, 0, s->stream));
+	CK(cudaLaunchCooperativeKernel((void *)mcgs_kernel<T>, dim3(s->gs_grid), dim3(ADMMB200_MCGS_THREADS), args, 0, s->stream));
 }
 template <int T> int mcgs_occupancy()
 {
 	int nb = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mcgs_kernel<T>, 512, 0));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mcgs_kernel<T>, ADMMB200_MCGS_THREADS, 0));
 	return nb;
 }
 
@@ -291,8 +292,8 @@ void launch_mcgs(S *s)
 	P.ell_col = s->gs_ell_col.p; P.ell_val = s->gs_ell_val.p; P.diag = s->gs_diag.p;
 	P.pin_slot = s->d_pin_slot.p; P.pin_pos = s->d_pin_pos.p; P.has_pins = s->gs_pin_idx.empty() ? 0 : 1;
 	P.n_obstacles = (int)s->obstacles.size();
-	for (int i = 0; i < P.n_obstacles; ++i) P.obs[i] = s->obstacles[i];
-	P.x = s->cx.p; P.b = s->b.p; P.barrier = s->barrier.p; P.resid = s->gs_resid.p; P.iters_done = s->gs_iters_done.p;
+	P.obs = s->d_obstacles.p;
+	P.x = s->cx.p; P.b = s->b.p; P.barrier = s->barrier.p; P.resid = s->gs_resid.p; P.resid_lb = s->gs_resid.p + (s->gs_iters + 2); P.iters_done = s->gs_iters_done.p;
 	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
 	if (P.tol2 > 0) CK(cudaMemsetAsync(s->gs_resid.p, 0, s->gs_resid.n * sizeof(double), s->stream));
 	switch (s->gs_lanes) {
@@ -497,7 +498,7 @@ void build_mcgs(S *s)
 	s->gs_ell_col.upload(ell_col, s->stream);
 	s->gs_ell_val.upload(ell_val, s->stream);
 	s->gs_diag.upload(diag, s->stream);
-	s->gs_resid.alloc(s->gs_iters + 2);
+	s->gs_resid.alloc(2 * (size_t)s->gs_iters + 4); // [0] |b|^2, [1..iters] residuals, then iters lower bounds
 	s->gs_iters_done.alloc(1);
 	CK(cudaStreamSynchronize(s->stream));
 	int occ = 1;
@@ -506,6 +507,7 @@ void build_mcgs(S *s)
 	const char *envb = getenv("ADMM_B200_GS_BLOCKS_PER_SM");
 	int bps = envb ? std::max(1, std::min(occ, atoi(envb))) : 1;
 	s->gs_grid = s->n_sms * bps;
+	if (!s->obstacles.empty()) { s->d_obstacles.upload(s->obstacles, s->stream); CK(cudaStreamSynchronize(s->stream)); }
 	upload_gs_pins(s);
 }
 

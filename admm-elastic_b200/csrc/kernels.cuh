@@ -306,11 +306,12 @@ struct McgsParams {
 	const double *pin_pos;      // [3*n_pins]
 	int has_pins;
 	int n_obstacles;
-	Obstacle obs[ADMMB200_MAX_OBSTACLES];
+	const Obstacle *obs;        // [n_obstacles] in global memory
 	double4 *x;                 // curr_x, in/out
 	const double4 *b;
 	unsigned int *barrier;      // zeroed before launch
 	double *resid;              // [iters+1], zeroed before launch: [0] = |b|^2, [1+it] = |b-Ax|^2 after sweep it
+	double *resid_lb;           // [iters], zeroed before launch: lower bound of |b-Ax|^2 after sweep it
 	int *iters_done;            // return value of solve()
 };
 
@@ -346,11 +347,11 @@ __device__ __forceinline__ void plane_project(const double *n, const double *p, 
 }
 
 // Collider::detect_passive (src/Collider.hpp:137-150) for Floor / Sphere (src/PassiveObject.hpp:32-64)
-__device__ __forceinline__ bool detect_passive(const McgsParams &P, const double *x, double *n, double *p)
+__device__ __forceinline__ bool detect_passive(const Obstacle *obs, int n_obstacles, const double *x, double *n, double *p)
 {
 	double dx = 1.7976931348623157e308;
-	for (int j = 0; j < P.n_obstacles; ++j) {
-		const Obstacle &o = P.obs[j];
+	for (int j = 0; j < n_obstacles; ++j) {
+		const Obstacle o = obs[j];
 		if (o.kind == 0) {
 			double d = x[1] - o.p[0];
 			if (!(d > dx)) { dx = d; p[0] = x[0]; p[1] = o.p[0]; p[2] = x[2]; n[0] = 0; n[1] = 1; n[2] = 0; }
@@ -369,8 +370,63 @@ __device__ __forceinline__ bool detect_passive(const McgsParams &P, const double
 	return false;
 }
 
+#define ADMMB200_MCGS_THREADS 768
+
+// One gather over the sliced-ELL rows [r0, r1) of a slice: every lane accumulates its entries, then the
+// T lanes of a node are summed with shuffles.  x is read with L2-coherent loads (other SMs wrote it in
+// the previous colour pass); col/val/b/diag never change during the kernel and take the read-only path.
 template <int T>
-__global__ void __launch_bounds__(512, 1) mcgs_kernel(McgsParams P)
+__device__ __forceinline__ void mcgs_row_gather(const McgsParams &P, int r0, int r1, int lane, double &sx, double &sy, double &sz)
+{
+	sx = 0; sy = 0; sz = 0;
+	const int *col = P.ell_col + (size_t)r0 * 32 + lane;
+	const double *val = P.ell_val + (size_t)r0 * 32 + lane;
+	const int n = r1 - r0;
+#pragma unroll 4
+	for (int r = 0; r < n; ++r) {
+		int c = __ldg(col + (size_t)r * 32);
+		double a = __ldg(val + (size_t)r * 32);
+		double4 xc = ld_node_cg(&P.x[c]);
+		sx += a * xc.x; sy += a * xc.y; sz += a * xc.z;
+	}
+#pragma unroll
+	for (int o = 1; o < T; o <<= 1) {
+		sx += __shfl_xor_sync(0xffffffffu, sx, o);
+		sy += __shfl_xor_sync(0xffffffffu, sy, o);
+		sz += __shfl_xor_sync(0xffffffffu, sz, o);
+	}
+}
+
+// Passive obstacles inside the sweep (src/NodalMultiColorGS.hpp:124-127), out of line: rare.
+__device__ __noinline__ bool mcgs_collide(const Obstacle *obs, int n_obstacles, const double *gs, double *nx)
+{
+	double nrm[3], pt[3];
+	if (!detect_passive(obs, n_obstacles, nx, nrm, pt)) return false;
+	double out[3];
+	plane_project(nrm, pt, gs, out); // constrained_segment_update (:218-262): no over-relaxation
+	nx[0] = out[0]; nx[1] = out[1]; nx[2] = out[2];
+	return true;
+}
+
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0;
+	if (threadIdx.x == 0) for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+	return s; // valid in thread 0
+}
+
+// The convergence test of the reference, |b - A x|^2 / |b|^2 < tol^2 after every sweep
+// (src/NodalMultiColorGS.hpp:136-139), costs a full extra pass over the matrix and in practice never
+// fires.  It is evaluated lazily without changing its outcome: a node i of the LAST
+// colour has, right after its SOR update, the residual row r_i = a_ii (1/omega - 1) dx_i exactly (no
+// later colour touches its neighbours), and the sum of r_i^2 over any subset of rows is a lower bound of
+// |b - A x|^2.  Only when that bound is below 4x the threshold is the exact residual computed.
+template <int T>
+__global__ void __launch_bounds__(ADMMB200_MCGS_THREADS, 1) mcgs_kernel(McgsParams P)
 {
 	constexpr int G = 32 / T; // nodes per slice
 	const int lane = threadIdx.x & 31;
@@ -382,103 +438,91 @@ __global__ void __launch_bounds__(512, 1) mcgs_kernel(McgsParams P)
 	unsigned int bar_target = 0;
 	__shared__ double red[32];
 	const bool check = P.tol2 > 0.0;
+	const double omega = P.omega, one_m_omega = 1.0 - P.omega, lb_scale = 1.0 / P.omega - 1.0;
 
 	if (check) {
 		// b_norm = |b|^2 (src/NodalMultiColorGS.hpp:92)
 		double acc = 0;
 		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_nodes; i += gridDim.x * blockDim.x) {
-			double4 bi = P.b[i];
+			double4 bi = ld_node(&P.b[i]);
 			acc += bi.x * bi.x + bi.y * bi.y + bi.z * bi.z;
 		}
-		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-		if (lane == 0) red[threadIdx.x >> 5] = acc;
-		__syncthreads();
-		if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < warps_per_block; ++w) s += red[w]; atomicAdd(&P.resid[0], s); }
+		double s = block_sum(acc, red);
+		if (threadIdx.x == 0) atomicAdd(&P.resid[0], s);
 	}
 
 	int it = 0;
 	for (; it < P.iters; ++it) {
+		double lb = 0;
 		for (int color = 0; color < P.n_colors; ++color) {
-			const int s0 = P.color_first_slice[color], s1 = P.color_first_slice[color + 1];
+			const int s0 = __ldg(&P.color_first_slice[color]), s1 = __ldg(&P.color_first_slice[color + 1]);
+			const bool last = check && (color == P.n_colors - 1);
 			for (int sl = s0 + warp_global; sl < s1; sl += n_warps) {
-				const int node = P.slice_node[sl * G + grp];
-				const int r0 = P.slice_ptr[sl], r1 = P.slice_ptr[sl + 1];
-				double sx = 0, sy = 0, sz = 0;
-				for (int r = r0; r < r1; ++r) {
-					int c = __ldg(&P.ell_col[(size_t)r * 32 + lane]);
-					double a = __ldg(&P.ell_val[(size_t)r * 32 + lane]);
-					double4 xc = ld_node_cg(&P.x[c]);
-					sx += a * xc.x; sy += a * xc.y; sz += a * xc.z;
+				const int node = __ldg(&P.slice_node[sl * G + grp]);
+				const int r0 = __ldg(&P.slice_ptr[sl]), r1 = __ldg(&P.slice_ptr[sl + 1]);
+				const bool owner = (sub == 0 && node >= 0);
+				// the node's own data does not depend on the gather: issue these loads first
+				double4 bi = make_double4(0, 0, 0, 0), xi = bi;
+				double a0 = 1, a1 = 1, a2 = 1;
+				int ps = -1;
+				if (owner) {
+					bi = ld_node(&P.b[node]);
+					xi = ld_node_cg(&P.x[node]);
+					a0 = __ldg(&P.diag[3 * node]); a1 = __ldg(&P.diag[3 * node + 1]); a2 = __ldg(&P.diag[3 * node + 2]);
+					if (P.has_pins) ps = __ldg(&P.pin_slot[node]);
 				}
-#pragma unroll
-				for (int o = 1; o < T; o <<= 1) {
-					sx += __shfl_xor_sync(0xffffffffu, sx, o);
-					sy += __shfl_xor_sync(0xffffffffu, sy, o);
-					sz += __shfl_xor_sync(0xffffffffu, sz, o);
-				}
-				if (sub == 0 && node >= 0) {
-					int ps = P.has_pins ? P.pin_slot[node] : -1;
+				double sx, sy, sz;
+				mcgs_row_gather<T>(P, r0, r1, lane, sx, sy, sz);
+				if (owner) {
 					if (ps >= 0) {
 						st_node(&P.x[node], P.pin_pos[3 * ps], P.pin_pos[3 * ps + 1], P.pin_pos[3 * ps + 2]);
 					} else {
-						double4 bi = P.b[node];
-						double4 xi = ld_node_cg(&P.x[node]);
-						double a0 = P.diag[3 * node], a1 = P.diag[3 * node + 1], a2 = P.diag[3 * node + 2];
 						// segment_update (src/NodalMultiColorGS.hpp:180-215)
 						double gs[3] = {(bi.x - sx) / a0, (bi.y - sy) / a1, (bi.z - sz) / a2};
-						double nx[3] = {(1.0 - P.omega) * xi.x + P.omega * gs[0], (1.0 - P.omega) * xi.y + P.omega * gs[1], (1.0 - P.omega) * xi.z + P.omega * gs[2]};
-						if (P.n_obstacles > 0) {
-							double nrm[3], pt[3];
-							if (detect_passive(P, nx, nrm, pt)) {
-								// constrained_segment_update (:218-262): no over-relaxation
-								double out[3];
-								plane_project(nrm, pt, gs, out);
-								nx[0] = out[0]; nx[1] = out[1]; nx[2] = out[2];
-							}
-						}
+						double nx[3] = {one_m_omega * xi.x + omega * gs[0], one_m_omega * xi.y + omega * gs[1], one_m_omega * xi.z + omega * gs[2]};
+						bool hit = false;
+						if (P.n_obstacles > 0) hit = mcgs_collide(P.obs, P.n_obstacles, gs, nx);
 						st_node(&P.x[node], nx[0], nx[1], nx[2]);
+						if (last && !hit) {
+							double rx = a0 * lb_scale * (nx[0] - xi.x), ry = a1 * lb_scale * (nx[1] - xi.y), rz = a2 * lb_scale * (nx[2] - xi.z);
+							lb += rx * rx + ry * ry + rz * rz;
+						}
 					}
 				}
+			}
+			if (last) {
+				double s = block_sum(lb, red);
+				if (threadIdx.x == 0 && s > 0.0) atomicAdd(&P.resid_lb[it], s);
 			}
 			grid_barrier(P.barrier, bar_target, gridDim.x);
 		}
 		if (check) {
-			// residual = b - A x (src/NodalMultiColorGS.hpp:136-139), every row including pinned ones
-			double acc = 0;
-			const int n_slices = P.color_first_slice[P.n_colors];
-			for (int sl = warp_global; sl < n_slices; sl += n_warps) {
-				const int node = P.slice_node[sl * G + grp];
-				const int r0 = P.slice_ptr[sl], r1 = P.slice_ptr[sl + 1];
-				double sx = 0, sy = 0, sz = 0;
-				for (int r = r0; r < r1; ++r) {
-					int c = __ldg(&P.ell_col[(size_t)r * 32 + lane]);
-					double a = __ldg(&P.ell_val[(size_t)r * 32 + lane]);
-					double4 xc = ld_node_cg(&P.x[c]);
-					sx += a * xc.x; sy += a * xc.y; sz += a * xc.z;
+			const double b2 = __ldcg(&P.resid[0]);
+			const double bound = __ldcg(&P.resid_lb[it]);
+			if (!(bound >= 4.0 * P.tol2 * b2)) {
+				// exact residual = b - A x (src/NodalMultiColorGS.hpp:136-139), every row including pinned ones
+				double acc = 0;
+				const int n_slices = P.color_first_slice[P.n_colors];
+				for (int sl = warp_global; sl < n_slices; sl += n_warps) {
+					const int node = __ldg(&P.slice_node[sl * G + grp]);
+					const int r0 = __ldg(&P.slice_ptr[sl]), r1 = __ldg(&P.slice_ptr[sl + 1]);
+					double sx, sy, sz;
+					mcgs_row_gather<T>(P, r0, r1, lane, sx, sy, sz);
+					if (sub == 0 && node >= 0) {
+						double4 bi = ld_node(&P.b[node]);
+						double4 xi = ld_node_cg(&P.x[node]);
+						double rx = bi.x - (sx + P.diag[3 * node] * xi.x);
+						double ry = bi.y - (sy + P.diag[3 * node + 1] * xi.y);
+						double rz = bi.z - (sz + P.diag[3 * node + 2] * xi.z);
+						acc += rx * rx + ry * ry + rz * rz;
+					}
 				}
-#pragma unroll
-				for (int o = 1; o < T; o <<= 1) {
-					sx += __shfl_xor_sync(0xffffffffu, sx, o);
-					sy += __shfl_xor_sync(0xffffffffu, sy, o);
-					sz += __shfl_xor_sync(0xffffffffu, sz, o);
-				}
-				if (sub == 0 && node >= 0) {
-					double4 bi = P.b[node];
-					double4 xi = ld_node_cg(&P.x[node]);
-					double rx = bi.x - (sx + P.diag[3 * node] * xi.x);
-					double ry = bi.y - (sy + P.diag[3 * node + 1] * xi.y);
-					double rz = bi.z - (sz + P.diag[3 * node + 2] * xi.z);
-					acc += rx * rx + ry * ry + rz * rz;
-				}
+				double s = block_sum(acc, red);
+				if (threadIdx.x == 0) atomicAdd(&P.resid[1 + it], s);
+				grid_barrier(P.barrier, bar_target, gridDim.x);
+				double r2 = __ldcg(&P.resid[1 + it]);
+				if (r2 / b2 < P.tol2) break;
 			}
-			for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-			__syncthreads();
-			if (lane == 0) red[threadIdx.x >> 5] = acc;
-			__syncthreads();
-			if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < warps_per_block; ++w) s += red[w]; atomicAdd(&P.resid[1 + it], s); }
-			grid_barrier(P.barrier, bar_target, gridDim.x);
-			double r2 = __ldcg(&P.resid[1 + it]), b2 = __ldcg(&P.resid[0]);
-			if (r2 / b2 < P.tol2) break;
 		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) *P.iters_done = it;
