@@ -62,6 +62,8 @@ def _load():
     cuda.admm_b200_last_error.argtypes = [ctypes.c_void_p]
     cuda.admm_b200_launch_count.restype = ctypes.c_longlong
     cuda.admm_b200_launch_count.argtypes = [ctypes.c_void_p]
+    cuda.admm_b200_solver_info.restype = ctypes.c_char_p
+    cuda.admm_b200_solver_info.argtypes = [ctypes.c_void_p]
     host.admmhost_create.restype = ctypes.c_void_p
     host.admmhost_last_error.restype = ctypes.c_char_p
     host.admmhost_last_error.argtypes = [ctypes.c_void_p]
@@ -194,6 +196,9 @@ class DeviceSolver(object):
         out = np.zeros(3)
         self._ck(_cuda.admm_b200_time_kernels(self.h, int(reps), _dp(out)))
         return {"local_ms": out[0], "assemble_ms": out[1], "global_ms": out[2]}
+
+    def info(self):
+        return _cuda.admm_b200_solver_info(self.h).decode()
 
     def launch_count(self):
         return int(_cuda.admm_b200_launch_count(self.h))

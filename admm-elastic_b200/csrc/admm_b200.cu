@@ -3,6 +3,7 @@
 #include "../../include/admm_b200.h"
 #include "kernels.cuh"
 #include "sptrsv.cuh"
+#include "mcgs_resident.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -127,6 +128,16 @@ struct admm_b200_solver {
 	DevBuf<int> gs_iters_done, iter_log;
 	int gs_grid = 0;
 	size_t gs_nnz = 0, gs_ell_entries = 0;
+	// mcgs, shared-memory-resident variant (mcgs_resident.cuh)
+	bool gs_resident = false;
+	size_t gs_res_smem = 0;
+	DevBuf<PartDesc> res_parts;
+	DevBuf<uint16_t> res_col;
+	DevBuf<char> res_val;
+	DevBuf<int> res_gid, res_slice_row, res_color_slice;
+	DevBuf<short> res_slice_node;
+	std::vector<double> h_x0; // rest positions (partitioning)
+	std::string gs_info;
 
 	// ldlt
 	bool have_ldlt = false;
@@ -283,9 +294,24 @@ template <int T> int mcgs_occupancy()
 	return nb;
 }
 
-void launch_mcgs(S *s)
+void fill_mcgs_params(S *s, McgsParams &P);
+
+void launch_mcgs_resident(S *s)
 {
-	McgsParams P;
+	McgsResParams R;
+	fill_mcgs_params(s, R.base);
+	R.parts = s->res_parts.p; R.col = s->res_col.p; R.val = s->res_val.p; R.gid = s->res_gid.p;
+	R.slice_row = s->res_slice_row.p; R.color_slice = s->res_color_slice.p; R.slice_node = s->res_slice_node.p;
+	void *args[] = {&R};
+	if (s->precision == ADMM_B200_FP64)
+		CK(cudaLaunchCooperativeKernel((void *)mcgs_resident_kernel<double>, dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
+	else
+		CK(cudaLaunchCooperativeKernel((void *)mcgs_resident_kernel<float>, dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
+	s->launches++;
+}
+
+void fill_mcgs_params(S *s, McgsParams &P)
+{
 	P.n_nodes = s->n_nodes; P.n_colors = s->n_colors; P.iters = s->gs_iters; P.omega = s->gs_omega;
 	P.tol2 = s->gs_tol > 0 ? s->gs_tol * s->gs_tol : 0.0;
 	P.color_first_slice = s->gs_color_first.p; P.slice_ptr = s->gs_slice_ptr.p; P.slice_node = s->gs_slice_node.p;
@@ -296,6 +322,13 @@ void launch_mcgs(S *s)
 	P.x = s->cx.p; P.b = s->b.p; P.barrier = s->barrier.p; P.resid = s->gs_resid.p; P.resid_lb = s->gs_resid.p + (s->gs_iters + 2); P.iters_done = s->gs_iters_done.p;
 	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
 	if (P.tol2 > 0) CK(cudaMemsetAsync(s->gs_resid.p, 0, s->gs_resid.n * sizeof(double), s->stream));
+}
+
+void launch_mcgs(S *s)
+{
+	if (s->gs_resident) { launch_mcgs_resident(s); return; }
+	McgsParams P;
+	fill_mcgs_params(s, P);
 	switch (s->gs_lanes) {
 	case 1: mcgs_launch_T<1>(s, P); break;
 	case 2: mcgs_launch_T<2>(s, P); break;
@@ -426,6 +459,62 @@ void upload_gs_pins(S *s)
 	CK(cudaStreamSynchronize(s->stream));
 }
 
+// Plans the shared-memory-resident variant and uses it when every part fits one SM's shared memory
+// with the chosen value precision; otherwise the streaming kernel (any size) stays in charge.
+// ADMM_B200_GS_KERNEL=stream|resident overrides the choice (resident fails loudly if it does not fit).
+void build_mcgs_resident(S *s)
+{
+	const char *env = getenv("ADMM_B200_GS_KERNEL");
+	const std::string want = env ? env : "auto";
+	s->gs_resident = false;
+	if (want == "stream") { s->gs_info = "stream (forced)"; return; }
+	const int val_bytes = s->precision == ADMM_B200_FP64 ? 8 : 4;
+	int max_optin = 0;
+	CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+	cudaFuncAttributes fa;
+	if (val_bytes == 8) CK(cudaFuncGetAttributes(&fa, mcgs_resident_kernel<double>)); else CK(cudaFuncGetAttributes(&fa, mcgs_resident_kernel<float>));
+	const size_t budget = (size_t)max_optin - fa.sharedSizeBytes;
+	ResidentPlan R;
+	try {
+		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->n_sms);
+	} catch (std::exception &e) {
+		if (want == "resident") throw;
+		s->gs_info = std::string("stream (") + e.what() + ")";
+		return;
+	}
+	const size_t need = R.smem_bytes(s->n_colors, val_bytes);
+	char buf[256];
+	snprintf(buf, sizeof(buf), "%zu B shared memory per part needed (max own %zu, halo %zu, rows %zu; ELL fill %.3f), budget %zu B", need, R.max_own, R.max_halo, R.max_rows,
+		R.entries ? (double)R.nnz / (double)R.entries : 1.0, budget);
+	if (need > budget) {
+		if (want == "resident") throw std::runtime_error(std::string("resident MCGS does not fit: ") + buf);
+		s->gs_info = std::string("stream: ") + buf;
+		return;
+	}
+	s->res_parts.upload(R.parts, s->stream);
+	s->res_col.upload(R.col, s->stream);
+	s->res_gid.upload(R.gid, s->stream);
+	s->res_slice_row.upload(R.slice_row, s->stream);
+	s->res_color_slice.upload(R.color_slice, s->stream);
+	s->res_slice_node.upload(R.slice_node, s->stream);
+	if (val_bytes == 8) {
+		s->res_val.alloc(std::max<size_t>(R.val.size(), 1) * 8);
+		if (!R.val.empty()) CK(cudaMemcpyAsync(s->res_val.p, R.val.data(), R.val.size() * 8, cudaMemcpyHostToDevice, s->stream));
+		CK(cudaFuncSetAttribute(mcgs_resident_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+		CK(cudaStreamSynchronize(s->stream));
+	} else {
+		std::vector<float> v32(R.val.begin(), R.val.end());
+		s->res_val.alloc(std::max<size_t>(v32.size(), 1) * 4);
+		if (!v32.empty()) CK(cudaMemcpyAsync(s->res_val.p, v32.data(), v32.size() * 4, cudaMemcpyHostToDevice, s->stream));
+		CK(cudaFuncSetAttribute(mcgs_resident_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+		CK(cudaStreamSynchronize(s->stream));
+	}
+	CK(cudaStreamSynchronize(s->stream));
+	s->gs_res_smem = need;
+	s->gs_resident = true;
+	s->gs_info = std::string("resident: ") + buf;
+}
+
 void build_mcgs(S *s)
 {
 	const int n = s->n_nodes;
@@ -509,6 +598,7 @@ void build_mcgs(S *s)
 	s->gs_grid = s->n_sms * bps;
 	if (!s->obstacles.empty()) { s->d_obstacles.upload(s->obstacles, s->stream); CK(cudaStreamSynchronize(s->stream)); }
 	upload_gs_pins(s);
+	build_mcgs_resident(s);
 }
 
 void build_ldlt(S *s)
@@ -785,6 +875,7 @@ int admm_b200_set_nodes(admm_b200_solver *s, int n_nodes, const double *x, const
 		require(n_nodes >= 1 && x && m, "**Solver Error: Problem with node data!");
 		s->n_nodes = n_nodes;
 		s->h_m.assign(m, m + (size_t)3 * n_nodes);
+		s->h_x0.assign(x, x + (size_t)3 * n_nodes);
 		s->x.alloc(n_nodes); s->v.alloc(n_nodes); s->cx.alloc(n_nodes); s->mxbar.alloc(n_nodes); s->b.alloc(n_nodes); s->m.alloc(n_nodes);
 		s->stage3.alloc((size_t)3 * n_nodes); s->stage3b.alloc(std::max<size_t>((size_t)3 * n_nodes, 4096));
 		s->v.zero(s->stream); s->b.zero(s->stream); s->mxbar.zero(s->stream);
@@ -1081,5 +1172,56 @@ int admm_b200_time_kernels(admm_b200_solver *s, int reps, double *out_ms)
 }
 
 long long admm_b200_launch_count(const admm_b200_solver *s) { return s ? s->launches : 0; }
+
+// Host-only check of the resident plan (no device): builds the plan, walks it exactly like
+// mcgs_resident_kernel's gather and returns max |(L_offdiag x)_plan - (L_offdiag x)_csr| over all nodes
+// for the given x (n values); stats = {shared bytes needed, max own, max halo, entries, nnz, parts used}.
+int admm_b200_plan_check(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int n_parts, int val_bytes, const double *x, double *max_err, long long *stats, int *part_of)
+{
+	try {
+		ResidentPlan R = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts);
+		const int G = 8;
+		double worst = 0;
+		std::vector<char> seen(n, 0);
+		long long used = 0;
+		for (const PartDesc &d : R.parts) {
+			if (d.n_own) ++used;
+			const int *gid = R.gid.data() + d.gid_off;
+			const int *srow = R.slice_row.data() + d.slice_off;
+			const short *snode = R.slice_node.data() + d.snode_off;
+			const int *cs = R.color_slice.data() + d.cslice_off;
+			if (cs[n_colors] != d.n_slices) throw std::runtime_error("plan: colour table does not cover all slices");
+			for (int c = 0; c < n_colors; ++c) for (int sl = cs[c]; sl < cs[c + 1]; ++sl) for (int g = 0; g < G; ++g) {
+				int l = snode[sl * G + g];
+				if (l < 0) continue;
+				int node = gid[l];
+				if (seen[node]) throw std::runtime_error("plan: node updated twice");
+				seen[node] = 1;
+				double acc = 0;
+				for (int r = srow[sl]; r < srow[sl + 1]; ++r) for (int t = 0; t < 4; ++t) {
+					size_t e = (size_t)d.ent_off + (size_t)r * 32 + g * 4 + t;
+					int cl = R.col[e];
+					if (cl >= d.n_own + d.n_halo) throw std::runtime_error("plan: column out of range");
+					double v = val_bytes == 4 ? (double)(float)R.val[e] : R.val[e];
+					acc += v * x[gid[cl]];
+				}
+				double ref = 0;
+				for (int q = rowptr[node]; q < rowptr[node + 1]; ++q) if (cols[q] != node) ref += (val_bytes == 4 ? (double)(float)vals[q] : vals[q]) * x[cols[q]];
+				worst = std::max(worst, std::abs(acc - ref));
+			}
+		}
+		for (int i = 0; i < n; ++i) if (!seen[i]) throw std::runtime_error("plan: a node is never updated");
+		if (max_err) *max_err = worst;
+		if (stats) { stats[0] = (long long)R.smem_bytes(n_colors, val_bytes); stats[1] = (long long)R.max_own; stats[2] = (long long)R.max_halo; stats[3] = (long long)R.entries; stats[4] = (long long)R.nnz; stats[5] = used; }
+		if (part_of) std::copy(R.part_of.begin(), R.part_of.end(), part_of);
+		return 0;
+	} catch (std::exception &e) {
+		g_create_error = e.what();
+		return 1;
+	}
+}
+
+const char *admm_b200_solver_info(const admm_b200_solver *s) { return s ? s->gs_info.c_str() : ""; }
 
 } // extern "C"

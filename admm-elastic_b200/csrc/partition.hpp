@@ -1,0 +1,196 @@
+// partition.hpp -- host-side planning of the shared-memory-resident multi-colour Gauss-Seidel.
+//
+// The constant system matrix of one ADMM solve sequence (A = L (x) I3 + M, src/Solver.cpp:226) is cut
+// into one part per SM.  A part owns a spatially compact set of nodes (recursive coordinate bisection
+// on the rest positions, balanced by row length), keeps the rows of those nodes AND their current
+// positions in the SM's shared memory for all sweeps x colours of a solve, and only touches L2/HBM for
+// the halo (neighbours owned by other parts), the right-hand side and the result.
+// Colours stay global (graphcolor::color_matrix semantics, deps/mclscene/include/MCL/GraphColor.hpp:
+// 66-72): all parts sweep the same colour between two grid barriers, so the update order -- and with
+// it the result -- is the same as in the reference's NodalMultiColorGS::solve
+// (src/NodalMultiColorGS.hpp:96-131) for the same colouring.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <vector>
+
+namespace admmb200 {
+
+struct PartDesc {
+	int n_own, n_halo, n_slices, n_rows; // owned nodes, halo nodes, slices (warps' work items), 32-entry ELL rows
+	long long ent_off;                   // first entry of this part in the global col/val arrays
+	int gid_off;                         // into gid[]: n_own owned ids (local order) then n_halo halo ids
+	int slice_off;                       // into slice_row[] (n_slices + 1 entries, relative row numbers)
+	int snode_off;                       // into slice_node[] (n_slices * G local ids, -1 = padding)
+	int cslice_off;                      // into color_slice[] (n_colors + 1 entries)
+	int pad_;
+};
+
+struct ResidentPlan {
+	int n_parts = 0, lanes = 4;
+	std::vector<PartDesc> parts;
+	std::vector<uint16_t> col;     // local index: < n_own -> shared-memory x, else halo (gid[col])
+	std::vector<double> val;       // converted to the storage precision at upload
+	std::vector<int> gid, slice_row, color_slice;
+	std::vector<short> slice_node;
+	std::vector<int> part_of;      // node -> part (for tests / diagnostics)
+	size_t max_rows = 0, max_own = 0, max_halo = 0, max_slices = 0, entries = 0, nnz = 0;
+	// dynamic shared memory one CTA needs with `val_bytes`-wide matrix values
+	size_t smem_bytes(int n_colors, int val_bytes) const {
+		size_t worst = 0;
+		for (const PartDesc &d : parts) worst = std::max(worst, layout(d, n_colors, val_bytes, nullptr));
+		return worst;
+	}
+	// byte offsets of the shared-memory arrays of one part (the kernel computes the same)
+	static size_t layout(const PartDesc &d, int n_colors, int val_bytes, size_t *off /* [7] or null */) {
+		const int G = 8; // nodes per slice at 4 lanes per node
+		size_t o = 0, tmp[7];
+		auto take = [&](int i, size_t bytes) { tmp[i] = o; o += (bytes + 15) & ~(size_t)15; };
+		take(0, sizeof(double) * 3 * (size_t)d.n_own);         // xs
+		take(1, (size_t)val_bytes * 32 * (size_t)d.n_rows);    // val
+		take(2, sizeof(uint16_t) * 32 * (size_t)d.n_rows);     // col
+		take(3, sizeof(int) * ((size_t)d.n_own + d.n_halo));   // gid
+		take(4, sizeof(int) * ((size_t)d.n_slices + 1));       // slice_row
+		take(5, sizeof(short) * (size_t)G * d.n_slices);       // slice_node
+		take(6, sizeof(int) * ((size_t)n_colors + 1));         // color_slice
+		if (off) std::memcpy(off, tmp, sizeof(tmp));
+		return o;
+	}
+};
+
+namespace detail {
+inline void rcb(std::vector<int> &ids, int lo, int hi, int k, int part0, const double *pos, const std::vector<double> &w, std::vector<int> &part_of)
+{
+	if (k <= 1 || hi - lo <= 0) { for (int i = lo; i < hi; ++i) part_of[ids[i]] = part0; return; }
+	double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, total = 0;
+	for (int i = lo; i < hi; ++i) {
+		const double *p = pos + 3 * (size_t)ids[i];
+		for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
+		total += w[ids[i]];
+	}
+	int axis = 0;
+	for (int a = 1; a < 3; ++a) if (mx[a] - mn[a] > mx[axis] - mn[axis]) axis = a;
+	std::sort(ids.begin() + lo, ids.begin() + hi, [&](int a, int b) {
+		double pa = pos[3 * (size_t)a + axis], pb = pos[3 * (size_t)b + axis];
+		return pa < pb || (pa == pb && a < b);
+	});
+	const int kl = k / 2, kr = k - kl;
+	const double target = total * (double)kl / (double)k;
+	double acc = 0;
+	int mid = lo;
+	while (mid < hi && acc + 0.5 * w[ids[mid]] < target) { acc += w[ids[mid]]; ++mid; }
+	// keep at least one node per side when there are enough nodes
+	if (hi - lo >= 2) mid = std::min(std::max(mid, lo + 1), hi - 1);
+	rcb(ids, lo, mid, kl, part0, pos, w, part_of);
+	rcb(ids, mid, hi, kr, part0 + kl, pos, w, part_of);
+}
+} // namespace detail
+
+// rowptr/cols/vals: scalar matrix L (both triangles); color_of_list: colour -> node lists (offsets, nodes)
+inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off,
+	const int *color_nodes, const double *pos3, int n_parts, int lanes = 4)
+{
+	ResidentPlan R;
+	R.n_parts = n_parts; R.lanes = lanes;
+	const int T = lanes, G = 32 / T;
+	std::vector<int> color_of(n, -1);
+	for (int c = 0; c < n_colors; ++c) for (int k = color_off[c]; k < color_off[c + 1]; ++k) color_of[color_nodes[k]] = c;
+	std::vector<int> rowlen(n, 0);
+	std::vector<double> w(n);
+	for (int i = 0; i < n; ++i) {
+		int len = 0;
+		for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) if (cols[q] != i && vals[q] != 0.0) ++len;
+		rowlen[i] = len;
+		w[i] = (double)((len + T - 1) / T * T) + 2.0; // padded row + the node's own update
+	}
+	R.part_of.assign(n, 0);
+	std::vector<int> ids(n);
+	std::iota(ids.begin(), ids.end(), 0);
+	detail::rcb(ids, 0, n, n_parts, 0, pos3, w, R.part_of);
+
+	std::vector<std::vector<int>> own(n_parts);
+	for (int i = 0; i < n; ++i) own[R.part_of[i]].push_back(i);
+	std::vector<int> local_of(n, -1);
+	R.parts.resize(n_parts);
+	for (int p = 0; p < n_parts; ++p) {
+		std::vector<int> &nodes = own[p];
+		// colour-major, long rows first inside a colour (uniform slices -> little ELL padding), ids last
+		std::sort(nodes.begin(), nodes.end(), [&](int a, int b) {
+			if (color_of[a] != color_of[b]) return color_of[a] < color_of[b];
+			if (rowlen[a] != rowlen[b]) return rowlen[a] > rowlen[b];
+			return a < b;
+		});
+		PartDesc d;
+		std::memset(&d, 0, sizeof(d));
+		d.n_own = (int)nodes.size();
+		d.gid_off = (int)R.gid.size();
+		d.slice_off = (int)R.slice_row.size();
+		d.snode_off = (int)R.slice_node.size();
+		d.cslice_off = (int)R.color_slice.size();
+		d.ent_off = (long long)R.col.size();
+		for (int l = 0; l < d.n_own; ++l) { local_of[nodes[l]] = l; R.gid.push_back(nodes[l]); }
+		// halo numbering in order of first use
+		std::vector<int> halo;
+		auto local_index = [&](int g) -> int {
+			if (R.part_of[g] == p) return local_of[g];
+			if (local_of[g] < 0) { local_of[g] = d.n_own + (int)halo.size(); halo.push_back(g); }
+			return local_of[g];
+		};
+		int rows = 0, slices = 0;
+		R.slice_row.push_back(0);
+		int k = 0;
+		for (int c = 0; c < n_colors; ++c) {
+			R.color_slice.push_back(slices);
+			int k1 = k;
+			while (k1 < d.n_own && color_of[nodes[k1]] == c) ++k1;
+			for (; k < k1; k += G) {
+				int width = 0;
+				for (int g = 0; g < G && k + g < k1; ++g) width = std::max(width, (rowlen[nodes[k + g]] + T - 1) / T);
+				size_t base = R.col.size();
+				R.col.resize(base + (size_t)width * 32, 0);
+				R.val.resize(base + (size_t)width * 32, 0.0);
+				for (int g = 0; g < G; ++g) {
+					int node = (k + g < k1) ? nodes[k + g] : -1;
+					R.slice_node.push_back(node < 0 ? (short)-1 : (short)(k + g));
+					int self = node < 0 ? (k < k1 ? k : 0) : k + g; // padding entries read an owned node with a zero coefficient
+					int j = 0;
+					if (node >= 0) {
+						for (int q = rowptr[node]; q < rowptr[node + 1]; ++q) {
+							int cg = cols[q];
+							if (cg == node || vals[q] == 0.0) continue;
+							int li = local_index(cg);
+							if (li > 65535) throw std::runtime_error("resident plan: part too large for 16-bit local indices");
+							R.col[base + (size_t)(j / T) * 32 + g * T + (j % T)] = (uint16_t)li;
+							R.val[base + (size_t)(j / T) * 32 + g * T + (j % T)] = vals[q];
+							++j; ++R.nnz;
+						}
+					}
+					for (; j < width * T; ++j) R.col[base + (size_t)(j / T) * 32 + g * T + (j % T)] = (uint16_t)self;
+				}
+				rows += width;
+				++slices;
+				R.slice_row.push_back(rows);
+			}
+			k = k1;
+		}
+		R.color_slice.push_back(slices);
+		d.n_halo = (int)halo.size();
+		d.n_slices = slices;
+		d.n_rows = rows;
+		for (int g : halo) { R.gid.push_back(g); local_of[g] = -1; }
+		for (int l = 0; l < d.n_own; ++l) local_of[nodes[l]] = -1;
+		if (d.n_own > 32767) throw std::runtime_error("resident plan: part too large for 16-bit slice nodes");
+		R.parts[p] = d;
+		R.max_rows = std::max(R.max_rows, (size_t)rows);
+		R.max_own = std::max(R.max_own, (size_t)d.n_own);
+		R.max_halo = std::max(R.max_halo, (size_t)d.n_halo);
+		R.max_slices = std::max(R.max_slices, (size_t)slices);
+	}
+	R.entries = R.col.size();
+	return R;
+}
+
+} // namespace admmb200

@@ -576,7 +576,10 @@ inline void Solver::step() { // src/Solver.cpp:35-110
 
 inline void Solver::step_device() {
 	if (!initialized) throw std::runtime_error("**Solver::step Error: not initialized");
-	check(admm_b200_step(handle, m_settings.admm_iters, m_settings.gravity, nullptr), "step");
+	m_runtime = RuntimeData();
+	admm_b200_runtime rt;
+	check(admm_b200_step(handle, m_settings.admm_iters, m_settings.gravity, device_options.timers ? &rt : nullptr), "step");
+	if (device_options.timers) { m_runtime.global_ms = rt.global_ms; m_runtime.local_ms = rt.local_ms; m_runtime.collision_ms = rt.collision_ms; m_runtime.inner_iters = rt.inner_iters; m_runtime.assemble_ms = rt.assemble_ms; m_runtime.step_ms = rt.step_ms; }
 	state_on_device_newer = true;
 }
 

@@ -381,7 +381,7 @@ def run_b200(args):
                    "n_colors": n_colors, "admm_iters_per_step": iters,
                    "multi_gpu": "one independent beam per GPU, no data-path collective" if world > 1 else "single GPU",
                    "l2": "no explicit flush: one ADMM iteration streams ~%.0f MB of element data (> 126 MB L2) between reuses" % (n_tets * (16 + 19 * esz + 16 * 4 + 4) / 1e6),
-                   "init_s": init_s},
+                   "init_s": init_s, "global_solve_kernel": dev.info()},
         "tet_prox_per_s": world * n_tets / t_local,
         "e2e": {"value": e2e, "unit": "ADMM iters/s", "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                 "ms_per_step": ms_e2e / K, "api": "admm_b200::Solver::step() -> admm_b200_step_host"},

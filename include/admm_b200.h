@@ -179,6 +179,15 @@ int admm_b200_time_kernels( admm_b200_solver *s, int reps, double *out_ms );
 /* Counts of kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long admm_b200_launch_count( const admm_b200_solver *s );
 
+/* Host-only self check of the shared-memory-resident Gauss-Seidel plan (no device needed): see
+ * csrc/partition.hpp.  Returns 0 when the plan covers every node exactly once and reproduces
+ * L_offdiag * x; the message of a failure is available from admm_b200_last_error(NULL). */
+int admm_b200_plan_check( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int n_parts, int val_bytes, const double *x, double *max_err, long long *stats, int *part_of );
+
+/* One line describing which global-solve kernel finalize chose and why (diagnostics). */
+const char *admm_b200_solver_info( const admm_b200_solver *s );
+
 int admm_b200_version( void );
 
 #ifdef __cplusplus

@@ -114,3 +114,37 @@ def test_reference_harness_has_no_product_dependency(pkg):
     for lib in (pkg.LIB_CUDA_PATH, pkg.LIB_HOST_PATH):
         out = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
         assert "liboracle" not in out and "libadmm_ref" not in out
+
+
+@pytest.mark.parametrize("dims,parts", [((6, 2, 2), 148), ((20, 6, 5), 148), ((3, 1, 1), 148), ((12, 4, 4), 7)])
+def test_resident_gauss_seidel_plan(pkg, dims, parts):
+    """csrc/partition.hpp: the shared-memory-resident MCGS plan covers every node exactly once,
+    colour by colour, and reproduces L_offdiag * x (walked on the host exactly like the kernel's gather)."""
+    import ctypes
+    import scipy.sparse as sp
+    verts, tets = pkg.meshes.make_tet_blocks(*dims)
+    n = len(verts)
+    rows, cols = np.repeat(tets, 4, axis=1).ravel(), np.tile(tets, (1, 4)).ravel()
+    A = sp.csr_matrix((np.random.RandomState(0).rand(rows.size) + 0.1, (rows, cols)), shape=(n, n))
+    A = (A + A.T).tocsr()
+    A.sort_indices()
+    colors = pkg.color_matrix(A.indptr, A.indices, A.data, 0)
+    off = np.zeros(len(colors) + 1, np.int32)
+    off[1:] = np.cumsum([len(c) for c in colors])
+    nodes = np.concatenate(colors).astype(np.int32)
+    x = np.random.RandomState(1).randn(n)
+    pos = np.ascontiguousarray(verts.astype(np.float64))
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    for val_bytes, tol in ((8, 1e-12), (4, 1e-12)):
+        err, stats, part = ctypes.c_double(0), (ctypes.c_longlong * 6)(), np.zeros(n, np.int32)
+        rc = pkg.cuda_lib.admm_b200_plan_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), parts, val_bytes,
+                                               dp(x), ctypes.byref(err), stats, ip(part))
+        assert rc == 0, pkg.cuda_lib.admm_b200_last_error(None)
+        assert err.value < tol
+        assert stats[4] == A.nnz - n          # every off-diagonal entry placed exactly once
+        assert 0 <= part.min() and part.max() < parts
+        sizes = np.bincount(part, minlength=parts)
+        if n >= 4 * parts:
+            assert sizes.max() <= 1.5 * n / parts + 8   # balanced
