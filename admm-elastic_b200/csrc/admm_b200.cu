@@ -134,7 +134,8 @@ struct admm_b200_solver {
 	DevBuf<PartDesc> res_parts;
 	DevBuf<uint16_t> res_col;
 	DevBuf<char> res_val;
-	DevBuf<int> res_gid, res_slice_row, res_color_slice;
+	DevBuf<int> res_gid, res_slice_row, res_color_slice, res_nbr;
+	DevBuf<unsigned int> res_sync; // part_epoch [8 * n_sms] | sweep_flag [iters] | sweep_arrive [iters]
 	DevBuf<short> res_slice_node;
 	std::vector<double> h_x0; // rest positions (partitioning)
 	std::string gs_info;
@@ -301,7 +302,9 @@ void launch_mcgs_resident(S *s)
 	McgsResParams R;
 	fill_mcgs_params(s, R.base);
 	R.parts = s->res_parts.p; R.col = s->res_col.p; R.val = s->res_val.p; R.gid = s->res_gid.p;
-	R.slice_row = s->res_slice_row.p; R.color_slice = s->res_color_slice.p; R.slice_node = s->res_slice_node.p;
+	R.slice_row = s->res_slice_row.p; R.color_slice = s->res_color_slice.p; R.slice_node = s->res_slice_node.p; R.nbr = s->res_nbr.p;
+	R.part_epoch = s->res_sync.p; R.sweep_flag = s->res_sync.p + 8 * (size_t)s->n_sms; R.sweep_arrive = R.sweep_flag + s->gs_iters;
+	CK(cudaMemsetAsync(s->res_sync.p, 0, s->res_sync.n * sizeof(unsigned int), s->stream));
 	void *args[] = {&R};
 	if (s->precision == ADMM_B200_FP64)
 		CK(cudaLaunchCooperativeKernel((void *)mcgs_resident_kernel<double>, dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
@@ -497,6 +500,9 @@ void build_mcgs_resident(S *s)
 	s->res_slice_row.upload(R.slice_row, s->stream);
 	s->res_color_slice.upload(R.color_slice, s->stream);
 	s->res_slice_node.upload(R.slice_node, s->stream);
+	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);
+	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
+	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
 	if (val_bytes == 8) {
 		s->res_val.alloc(std::max<size_t>(R.val.size(), 1) * 8);
 		if (!R.val.empty()) CK(cudaMemcpyAsync(s->res_val.p, R.val.data(), R.val.size() * 8, cudaMemcpyHostToDevice, s->stream));

@@ -315,17 +315,27 @@ struct McgsParams {
 	int *iters_done;            // return value of solve()
 };
 
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+	unsigned int v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Grid-wide barrier of a cooperative (co-resident) launch.  Polling uses relaxed loads (an acquire load
+// would invalidate L1 on every poll); one acq_rel fence on each side gives the ordering.
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &target, unsigned int n_blocks)
 {
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		target += n_blocks;
-		__threadfence();
+		fence_acq_rel_gpu();
 		atomicAdd(counter, 1u);
-		unsigned int seen;
-		do {
-			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-		} while (seen < target);
+		while (ld_relaxed_u32(counter) < target) { }
+		fence_acq_rel_gpu();
 	}
 	__syncthreads();
 }

@@ -25,9 +25,31 @@ struct McgsResParams {
 	const PartDesc *parts;      // [gridDim.x]
 	const uint16_t *col;        // all parts, 32-entry rows
 	const void *val;            // float or double, same indexing as col
-	const int *gid, *slice_row, *color_slice;
+	const int *gid, *slice_row, *color_slice, *nbr;
 	const short *slice_node;
+	unsigned int *part_epoch;   // [gridDim.x * 8] one flag per part (32-byte stride), zeroed before launch
+	unsigned int *sweep_flag;   // [iters] set to 1 by any part that proves "not converged yet" for that sweep
+	unsigned int *sweep_arrive; // [iters] parts that have finished that sweep
 };
+
+// Point-to-point ordering between neighbouring parts, replacing a grid barrier per colour pass.
+// publish: this part has finished pass `epoch` (all its reads of neighbours' values and all its writes).
+// wait:    every neighbour has finished pass `epoch`, so (a) their values of that pass are visible and
+//          (b) they no longer read the values this part is about to overwrite.
+__device__ __forceinline__ void part_publish(unsigned int *part_epoch, unsigned int epoch)
+{
+	__syncthreads();
+	if (threadIdx.x == 0) { fence_acq_rel_gpu(); st_release_u32(part_epoch + 8 * blockIdx.x, epoch); }
+}
+__device__ __forceinline__ void part_wait(const unsigned int *part_epoch, const int *s_nbr, int n_nbr, unsigned int epoch)
+{
+	if ((int)threadIdx.x < n_nbr) {
+		const unsigned int *f = part_epoch + 8 * s_nbr[threadIdx.x];
+		while (ld_relaxed_u32(f) < epoch) { }
+		fence_acq_rel_gpu();
+	}
+	__syncthreads();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -82,6 +104,8 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ double red[32];
 	__shared__ __align__(8) uint64_t tma_bar;
+	__shared__ int s_nbr[192];
+	__shared__ int s_decision;
 	const McgsParams &P = R.base;
 	const PartDesc d = R.parts[blockIdx.x];
 	const int tid = threadIdx.x, lane = tid & 31, sub = lane % T, grp = lane / T, warp = tid >> 5, n_warps = blockDim.x >> 5;
@@ -113,6 +137,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	for (int i = tid; i <= d.n_slices; i += blockDim.x) s_srow[i] = R.slice_row[d.slice_off + i];
 	for (int i = tid; i < G * d.n_slices; i += blockDim.x) s_snode[i] = R.slice_node[d.snode_off + i];
 	for (int i = tid; i <= P.n_colors; i += blockDim.x) s_cslice[i] = R.color_slice[d.cslice_off + i];
+	for (int i = tid; i < d.n_nbr; i += blockDim.x) s_nbr[i] = R.nbr[d.nbr_off + i];
 	for (int l = tid; l < d.n_own; l += blockDim.x) {
 		double4 xv = P.x[R.gid[d.gid_off + l]];
 		s_x[3 * l] = xv.x; s_x[3 * l + 1] = xv.y; s_x[3 * l + 2] = xv.z;
@@ -132,14 +157,18 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 		}
 		double s = block_sum(acc, red);
 		if (tid == 0) atomicAdd(&P.resid[0], s);
+		grid_barrier(P.barrier, bar_target, gridDim.x); // the only grid-wide barrier of a solve
 	}
+	const double thresh = check ? 4.0 * P.tol2 * __ldcg(&P.resid[0]) : 0.0;
 
 	int it = 0;
+	unsigned int epoch = 0;
 	for (; it < P.iters; ++it) {
 		double lb = 0;
 		for (int color = 0; color < P.n_colors; ++color) {
 			const int s0 = s_cslice[color], s1 = s_cslice[color + 1];
 			const bool last = check && (color == P.n_colors - 1);
+			if (epoch > 0) part_wait(R.part_epoch, s_nbr, d.n_nbr, epoch);
 			for (int sl = s0 + warp; sl < s1; sl += n_warps) {
 				const int l = s_snode[sl * G + grp];
 				const bool owner = (sub == 0 && l >= 0);
@@ -173,16 +202,36 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 					st_node(&P.x[node], nx[0], nx[1], nx[2]);
 				}
 			}
-			if (last) {
-				double s = block_sum(lb, red);
-				if (tid == 0 && s > 0.0) atomicAdd(&P.resid_lb[it], s);
-			}
-			grid_barrier(P.barrier, bar_target, gridDim.x);
+			part_publish(R.part_epoch, ++epoch);
 		}
 		if (check) {
-			const double b2 = __ldcg(&P.resid[0]);
-			const double bound = __ldcg(&P.resid_lb[it]);
-			if (!(bound >= 4.0 * P.tol2 * b2)) {
+			// Decide "converged?" without a grid barrier in the common case: any part whose own rows
+			// already prove |b - A x|^2 >= 4 tol^2 |b|^2 raises sweep_flag; a part continues as soon as it
+			// sees the flag.  Only if nobody can prove it do all parts meet (sweep_arrive == grid) and look
+			// at the summed bound, then at the exact residual.
+			double s = block_sum(lb, red);
+			if (tid == 0) {
+				if (s >= thresh) R.sweep_flag[it] = 1u;
+				else if (s > 0.0) atomicAdd(&P.resid_lb[it], s);
+				__threadfence();
+				atomicAdd(&R.sweep_arrive[it], 1u);
+				int decision = -1;
+				while (decision < 0) {
+					if (ld_relaxed_u32(&R.sweep_flag[it]) != 0u) decision = 1;
+					else if (ld_relaxed_u32(&R.sweep_arrive[it]) == gridDim.x) {
+						fence_acq_rel_gpu();
+						decision = (ld_relaxed_u32(&R.sweep_flag[it]) != 0u || __ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
+					}
+				}
+				s_decision = decision;
+			}
+			__syncthreads();
+			const bool proven_unconverged = s_decision == 1;
+			__syncthreads();
+			if (!proven_unconverged) {
+				const double b2 = __ldcg(&P.resid[0]);
+				// every part is here (sweep_arrive == grid) and all pass-`epoch` values are published
+				grid_barrier(P.barrier, bar_target, gridDim.x);
 				// exact residual b - A x (src/NodalMultiColorGS.hpp:136-139)
 				double acc = 0;
 				for (int sl = warp; sl < d.n_slices; sl += n_warps) {

@@ -26,6 +26,7 @@ struct PartDesc {
 	int slice_off;                       // into slice_row[] (n_slices + 1 entries, relative row numbers)
 	int snode_off;                       // into slice_node[] (n_slices * G local ids, -1 = padding)
 	int cslice_off;                      // into color_slice[] (n_colors + 1 entries)
+	int nbr_off, n_nbr;                  // into nbr[]: parts this part exchanges halo values with
 	int pad_;
 };
 
@@ -34,9 +35,10 @@ struct ResidentPlan {
 	std::vector<PartDesc> parts;
 	std::vector<uint16_t> col;     // local index: < n_own -> shared-memory x, else halo (gid[col])
 	std::vector<double> val;       // converted to the storage precision at upload
-	std::vector<int> gid, slice_row, color_slice;
+	std::vector<int> gid, slice_row, color_slice, nbr;
 	std::vector<short> slice_node;
 	std::vector<int> part_of;      // node -> part (for tests / diagnostics)
+	size_t max_nbr = 0;
 	size_t max_rows = 0, max_own = 0, max_halo = 0, max_slices = 0, entries = 0, nnz = 0;
 	// dynamic shared memory one CTA needs with `val_bytes`-wide matrix values
 	size_t smem_bytes(int n_colors, int val_bytes) const {
@@ -188,6 +190,24 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 		R.max_own = std::max(R.max_own, (size_t)d.n_own);
 		R.max_halo = std::max(R.max_halo, (size_t)d.n_halo);
 		R.max_slices = std::max(R.max_slices, (size_t)slices);
+	}
+	// neighbour parts (symmetric): q is a neighbour of p when either reads halo values of the other
+	std::vector<std::vector<int>> nb(n_parts);
+	for (int p = 0; p < n_parts; ++p) {
+		const PartDesc &d = R.parts[p];
+		for (int h = 0; h < d.n_halo; ++h) {
+			int q = R.part_of[R.gid[d.gid_off + d.n_own + h]];
+			nb[p].push_back(q);
+			nb[q].push_back(p);
+		}
+	}
+	for (int p = 0; p < n_parts; ++p) {
+		std::sort(nb[p].begin(), nb[p].end());
+		nb[p].erase(std::unique(nb[p].begin(), nb[p].end()), nb[p].end());
+		R.parts[p].nbr_off = (int)R.nbr.size();
+		R.parts[p].n_nbr = (int)nb[p].size();
+		R.nbr.insert(R.nbr.end(), nb[p].begin(), nb[p].end());
+		R.max_nbr = std::max(R.max_nbr, nb[p].size());
 	}
 	R.entries = R.col.size();
 	return R;
