@@ -130,11 +130,13 @@ struct admm_b200_solver {
 	size_t gs_nnz = 0, gs_ell_entries = 0;
 	// mcgs, shared-memory-resident variant (mcgs_resident.cuh)
 	bool gs_resident = false;
+	int gs_res_lanes = 1;
 	size_t gs_res_smem = 0;
 	DevBuf<PartDesc> res_parts;
 	DevBuf<uint16_t> res_col;
 	DevBuf<char> res_val;
 	DevBuf<int> res_gid, res_slice_row, res_color_slice, res_nbr;
+	DevBuf<unsigned long long> res_prof; // ADMM_B200_GS_PROF=1: per-part cycle counters of the last solve
 	DevBuf<unsigned int> res_sync; // part_epoch [8 * n_sms] | sweep_flag [iters] | sweep_arrive [iters]
 	DevBuf<short> res_slice_node;
 	std::vector<double> h_x0; // rest positions (partitioning)
@@ -297,6 +299,18 @@ template <int T> int mcgs_occupancy()
 
 void fill_mcgs_params(S *s, McgsParams &P);
 
+const void *resident_kernel_ptr(bool fp64, int lanes)
+{
+	if (fp64) {
+		if (lanes == 1) return (const void *)mcgs_resident_kernel<double, 1>;
+		if (lanes == 2) return (const void *)mcgs_resident_kernel<double, 2>;
+		return (const void *)mcgs_resident_kernel<double, 4>;
+	}
+	if (lanes == 1) return (const void *)mcgs_resident_kernel<float, 1>;
+	if (lanes == 2) return (const void *)mcgs_resident_kernel<float, 2>;
+	return (const void *)mcgs_resident_kernel<float, 4>;
+}
+
 void launch_mcgs_resident(S *s)
 {
 	McgsResParams R;
@@ -305,11 +319,9 @@ void launch_mcgs_resident(S *s)
 	R.slice_row = s->res_slice_row.p; R.color_slice = s->res_color_slice.p; R.slice_node = s->res_slice_node.p; R.nbr = s->res_nbr.p;
 	R.part_epoch = s->res_sync.p; R.sweep_flag = s->res_sync.p + 8 * (size_t)s->n_sms; R.sweep_arrive = R.sweep_flag + s->gs_iters;
 	CK(cudaMemsetAsync(s->res_sync.p, 0, s->res_sync.n * sizeof(unsigned int), s->stream));
+	R.prof = s->res_prof.p;
 	void *args[] = {&R};
-	if (s->precision == ADMM_B200_FP64)
-		CK(cudaLaunchCooperativeKernel((void *)mcgs_resident_kernel<double>, dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
-	else
-		CK(cudaLaunchCooperativeKernel((void *)mcgs_resident_kernel<float>, dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
+	CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(s->precision == ADMM_B200_FP64, s->gs_res_lanes), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
 	s->launches++;
 }
 
@@ -474,12 +486,17 @@ void build_mcgs_resident(S *s)
 	const int val_bytes = s->precision == ADMM_B200_FP64 ? 8 : 4;
 	int max_optin = 0;
 	CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+	const char *envl = getenv("ADMM_B200_GS_RES_LANES");
+	int lanes = envl ? atoi(envl) : 1;
+	if (lanes != 1 && lanes != 2 && lanes != 4) lanes = 1;
+	s->gs_res_lanes = lanes;
+	const void *kern = resident_kernel_ptr(val_bytes == 8, lanes);
 	cudaFuncAttributes fa;
-	if (val_bytes == 8) CK(cudaFuncGetAttributes(&fa, mcgs_resident_kernel<double>)); else CK(cudaFuncGetAttributes(&fa, mcgs_resident_kernel<float>));
+	CK(cudaFuncGetAttributes(&fa, kern));
 	const size_t budget = (size_t)max_optin - fa.sharedSizeBytes;
 	ResidentPlan R;
 	try {
-		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->n_sms);
+		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->n_sms, lanes);
 	} catch (std::exception &e) {
 		if (want == "resident") throw;
 		s->gs_info = std::string("stream (") + e.what() + ")";
@@ -487,8 +504,8 @@ void build_mcgs_resident(S *s)
 	}
 	const size_t need = R.smem_bytes(s->n_colors, val_bytes);
 	char buf[256];
-	snprintf(buf, sizeof(buf), "%zu B shared memory per part needed (max own %zu, halo %zu, rows %zu; ELL fill %.3f), budget %zu B", need, R.max_own, R.max_halo, R.max_rows,
-		R.entries ? (double)R.nnz / (double)R.entries : 1.0, budget);
+	snprintf(buf, sizeof(buf), "%d lane(s)/node, %zu B shared memory per part needed (max own %zu, halo %zu, rows %zu, neighbours %zu; ELL fill %.3f), budget %zu B", lanes, need, R.max_own, R.max_halo, R.max_rows,
+		R.max_nbr, R.entries ? (double)R.nnz / (double)R.entries : 1.0, budget);
 	if (need > budget) {
 		if (want == "resident") throw std::runtime_error(std::string("resident MCGS does not fit: ") + buf);
 		s->gs_info = std::string("stream: ") + buf;
@@ -503,18 +520,18 @@ void build_mcgs_resident(S *s)
 	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);
 	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
 	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
+	if (getenv("ADMM_B200_GS_PROF")) { s->res_prof.alloc(4 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
 	if (val_bytes == 8) {
 		s->res_val.alloc(std::max<size_t>(R.val.size(), 1) * 8);
 		if (!R.val.empty()) CK(cudaMemcpyAsync(s->res_val.p, R.val.data(), R.val.size() * 8, cudaMemcpyHostToDevice, s->stream));
-		CK(cudaFuncSetAttribute(mcgs_resident_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
 		CK(cudaStreamSynchronize(s->stream));
 	} else {
 		std::vector<float> v32(R.val.begin(), R.val.end());
 		s->res_val.alloc(std::max<size_t>(v32.size(), 1) * 4);
 		if (!v32.empty()) CK(cudaMemcpyAsync(s->res_val.p, v32.data(), v32.size() * 4, cudaMemcpyHostToDevice, s->stream));
-		CK(cudaFuncSetAttribute(mcgs_resident_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
 		CK(cudaStreamSynchronize(s->stream));
 	}
+	CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
 	CK(cudaStreamSynchronize(s->stream));
 	s->gs_res_smem = need;
 	s->gs_resident = true;
@@ -1142,6 +1159,14 @@ int admm_b200_debug_get(admm_b200_solver *s, const char *name, double *out, long
 			if (s->precision == ADMM_B200_FP64) gather_rows<double>(s, nm == "z", out, n_out); else gather_rows<float>(s, nm == "z", out, n_out);
 			return;
 		}
+		if (nm == "gs_prof") {
+			require(s->res_prof.p != nullptr, "debug_get gs_prof: set ADMM_B200_GS_PROF=1 before finalize");
+			require(n_out >= (long long)s->res_prof.n, "debug_get: output too small");
+			std::vector<unsigned long long> tmp(s->res_prof.n);
+			CK(cudaMemcpy(tmp.data(), s->res_prof.p, tmp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+			for (size_t i = 0; i < tmp.size(); ++i) out[i] = (double)tmp[i];
+			return;
+		}
 		const double4 *src = nullptr;
 		if (nm == "b") src = s->b.p; else if (nm == "x") src = s->cx.p; else if (nm == "v") src = s->v.p; else if (nm == "x0") src = s->x.p;
 		else throw std::runtime_error("debug_get: unknown array name");
@@ -1183,11 +1208,12 @@ long long admm_b200_launch_count(const admm_b200_solver *s) { return s ? s->laun
 // mcgs_resident_kernel's gather and returns max |(L_offdiag x)_plan - (L_offdiag x)_csr| over all nodes
 // for the given x (n values); stats = {shared bytes needed, max own, max halo, entries, nnz, parts used}.
 int admm_b200_plan_check(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
-	const double *pos3, int n_parts, int val_bytes, const double *x, double *max_err, long long *stats, int *part_of)
+	const double *pos3, int n_parts, int val_bytes, int lanes, const double *x, double *max_err, long long *stats, int *part_of)
 {
 	try {
-		ResidentPlan R = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts);
-		const int G = 8;
+		if (lanes != 1 && lanes != 2 && lanes != 4) throw std::runtime_error("plan_check: lanes must be 1, 2 or 4");
+		ResidentPlan R = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts, lanes);
+		const int T = lanes, G = 32 / T;
 		double worst = 0;
 		std::vector<char> seen(n, 0);
 		long long used = 0;
@@ -1197,16 +1223,18 @@ int admm_b200_plan_check(int n, const int *rowptr, const int *cols, const double
 			const int *srow = R.slice_row.data() + d.slice_off;
 			const short *snode = R.slice_node.data() + d.snode_off;
 			const int *cs = R.color_slice.data() + d.cslice_off;
-			if (cs[n_colors] != d.n_slices) throw std::runtime_error("plan: colour table does not cover all slices");
-			for (int c = 0; c < n_colors; ++c) for (int sl = cs[c]; sl < cs[c + 1]; ++sl) for (int g = 0; g < G; ++g) {
+			if (cs[2 * n_colors] != d.n_slices) throw std::runtime_error("plan: colour table does not cover all slices");
+			for (int c = 0; c < 2 * n_colors; ++c) for (int sl = cs[c]; sl < cs[c + 1]; ++sl) for (int g = 0; g < G; ++g) {
 				int l = snode[sl * G + g];
 				if (l < 0) continue;
 				int node = gid[l];
 				if (seen[node]) throw std::runtime_error("plan: node updated twice");
 				seen[node] = 1;
 				double acc = 0;
-				for (int r = srow[sl]; r < srow[sl + 1]; ++r) for (int t = 0; t < 4; ++t) {
-					size_t e = (size_t)d.ent_off + (size_t)r * 32 + g * 4 + t;
+				if ((c % 2 == 0) != (R.part_of[node] == R.part_of[node] && [&]() { for (int q = rowptr[node]; q < rowptr[node + 1]; ++q) if (cols[q] != node && vals[q] != 0.0 && R.part_of[cols[q]] != R.part_of[node]) return false; return true; }()))
+					throw std::runtime_error("plan: interior/boundary classification is wrong");
+				for (int r = srow[sl]; r < srow[sl + 1]; ++r) for (int t = 0; t < T; ++t) {
+					size_t e = (size_t)d.ent_off + (size_t)r * 32 + g * T + t;
 					int cl = R.col[e];
 					if (cl >= d.n_own + d.n_halo) throw std::runtime_error("plan: column out of range");
 					double v = val_bytes == 4 ? (double)(float)R.val[e] : R.val[e];

@@ -323,6 +323,9 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
 	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) {
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // Grid-wide barrier of a cooperative (co-resident) launch.  Polling uses relaxed loads (an acquire load

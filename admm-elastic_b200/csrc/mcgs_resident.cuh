@@ -30,6 +30,7 @@ struct McgsResParams {
 	unsigned int *part_epoch;   // [gridDim.x * 8] one flag per part (32-byte stride), zeroed before launch
 	unsigned int *sweep_flag;   // [iters] set to 1 by any part that proves "not converged yet" for that sweep
 	unsigned int *sweep_arrive; // [iters] parts that have finished that sweep
+	unsigned long long *prof;   // NULL, or [gridDim.x * 4] clock cycles of thread 0: waiting, computing, publishing, total
 };
 
 // Point-to-point ordering between neighbouring parts, replacing a grid barrier per colour pass.
@@ -39,7 +40,7 @@ struct McgsResParams {
 __device__ __forceinline__ void part_publish(unsigned int *part_epoch, unsigned int epoch)
 {
 	__syncthreads();
-	if (threadIdx.x == 0) { fence_acq_rel_gpu(); st_release_u32(part_epoch + 8 * blockIdx.x, epoch); }
+	if (threadIdx.x == 0) { fence_acq_rel_gpu(); st_relaxed_u32(part_epoch + 8 * blockIdx.x, epoch); }
 }
 __device__ __forceinline__ void part_wait(const unsigned int *part_epoch, const int *s_nbr, int n_nbr, unsigned int epoch)
 {
@@ -75,7 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-template <typename V>
+template <typename V, int T>
 __device__ __forceinline__ void res_gather(const V *s_val, const uint16_t *s_col, const double *s_x, const int *s_gid, const double4 *x,
 	int n_own, int r0, int r1, int lane, double &sx, double &sy, double &sz)
 {
@@ -90,17 +91,19 @@ __device__ __forceinline__ void res_gather(const V *s_val, const uint16_t *s_col
 		sx += a * x0; sy += a * x1; sz += a * x2;
 	}
 #pragma unroll
-	for (int o = 1; o < 4; o <<= 1) {
+	for (int o = 1; o < T; o <<= 1) {
 		sx += __shfl_xor_sync(0xffffffffu, sx, o);
 		sy += __shfl_xor_sync(0xffffffffu, sy, o);
 		sz += __shfl_xor_sync(0xffffffffu, sz, o);
 	}
 }
 
-template <typename V>
+// T lanes cooperate on one node (T = 1: one node per lane, no shuffles, every lane does an update;
+// T = 4: shorter per-lane chains but only a quarter of the lanes own a node).
+template <typename V, int T>
 __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(McgsResParams R)
 {
-	constexpr int T = 4, G = 8;
+	constexpr int G = 32 / T;
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ double red[32];
 	__shared__ __align__(8) uint64_t tma_bar;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	int *s_gid = (int *)(smem + take(sizeof(int) * ((size_t)d.n_own + d.n_halo)));
 	int *s_srow = (int *)(smem + take(sizeof(int) * ((size_t)d.n_slices + 1)));
 	short *s_snode = (short *)(smem + take(sizeof(short) * (size_t)G * d.n_slices));
-	int *s_cslice = (int *)(smem + take(sizeof(int) * ((size_t)P.n_colors + 1)));
+	int *s_cslice = (int *)(smem + take(sizeof(int) * (2 * (size_t)P.n_colors + 1)));
 
 	// ---- stage the part: matrix by TMA bulk copy, the small index arrays and x by plain loads ----
 	const uint32_t val_bytes = (uint32_t)(sizeof(V) * 32 * (size_t)d.n_rows), col_bytes = (uint32_t)(sizeof(uint16_t) * 32 * (size_t)d.n_rows);
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	for (int i = tid; i < d.n_own + d.n_halo; i += blockDim.x) s_gid[i] = R.gid[d.gid_off + i];
 	for (int i = tid; i <= d.n_slices; i += blockDim.x) s_srow[i] = R.slice_row[d.slice_off + i];
 	for (int i = tid; i < G * d.n_slices; i += blockDim.x) s_snode[i] = R.slice_node[d.snode_off + i];
-	for (int i = tid; i <= P.n_colors; i += blockDim.x) s_cslice[i] = R.color_slice[d.cslice_off + i];
+	for (int i = tid; i <= 2 * P.n_colors; i += blockDim.x) s_cslice[i] = R.color_slice[d.cslice_off + i];
 	for (int i = tid; i < d.n_nbr; i += blockDim.x) s_nbr[i] = R.nbr[d.nbr_off + i];
 	for (int l = tid; l < d.n_own; l += blockDim.x) {
 		double4 xv = P.x[R.gid[d.gid_off + l]];
@@ -161,48 +164,64 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	}
 	const double thresh = check ? 4.0 * P.tol2 * __ldcg(&P.resid[0]) : 0.0;
 
-	int it = 0;
-	unsigned int epoch = 0;
-	for (; it < P.iters; ++it) {
-		double lb = 0;
-		for (int color = 0; color < P.n_colors; ++color) {
-			const int s0 = s_cslice[color], s1 = s_cslice[color + 1];
-			const bool last = check && (color == P.n_colors - 1);
-			if (epoch > 0) part_wait(R.part_epoch, s_nbr, d.n_nbr, epoch);
-			for (int sl = s0 + warp; sl < s1; sl += n_warps) {
-				const int l = s_snode[sl * G + grp];
-				const bool owner = (sub == 0 && l >= 0);
-				double4 bi = make_double4(0, 0, 0, 0);
-				double a0 = 1, a1 = 1, a2 = 1;
-				int ps = -1, node = 0;
-				if (owner) {
-					node = s_gid[l];
-					bi = ld_node(&P.b[node]);
-					a0 = __ldg(&P.diag[3 * node]); a1 = __ldg(&P.diag[3 * node + 1]); a2 = __ldg(&P.diag[3 * node + 2]);
-					if (P.has_pins) ps = __ldg(&P.pin_slot[node]);
-				}
-				double sx, sy, sz;
-				res_gather<V>(s_val, s_col, s_x, s_gid, P.x, d.n_own, s_srow[sl], s_srow[sl + 1], lane, sx, sy, sz);
-				if (owner) {
-					double nx[3];
-					if (ps >= 0) { nx[0] = P.pin_pos[3 * ps]; nx[1] = P.pin_pos[3 * ps + 1]; nx[2] = P.pin_pos[3 * ps + 2]; }
-					else {
-						const double xo[3] = {s_x[3 * l], s_x[3 * l + 1], s_x[3 * l + 2]};
-						// segment_update (src/NodalMultiColorGS.hpp:180-215)
-						double gs[3] = {(bi.x - sx) / a0, (bi.y - sy) / a1, (bi.z - sz) / a2};
-						nx[0] = one_m_omega * xo[0] + omega * gs[0]; nx[1] = one_m_omega * xo[1] + omega * gs[1]; nx[2] = one_m_omega * xo[2] + omega * gs[2];
-						bool hit = false;
-						if (P.n_obstacles > 0) hit = mcgs_collide(P.obs, P.n_obstacles, gs, nx);
-						if (last && !hit) {
-							double rx = a0 * lb_scale * (nx[0] - xo[0]), ry = a1 * lb_scale * (nx[1] - xo[1]), rz = a2 * lb_scale * (nx[2] - xo[2]);
-							lb += rx * rx + ry * ry + rz * rz;
-						}
-					}
-					s_x[3 * l] = nx[0]; s_x[3 * l + 1] = nx[1]; s_x[3 * l + 2] = nx[2];
-					st_node(&P.x[node], nx[0], nx[1], nx[2]);
+	// One slice = G nodes of one colour: gather, SOR update, write back.  `to_global`: boundary nodes are
+	// read by other parts and go to global memory at once; interior ones only at the end of the solve.
+	double lb = 0;
+	auto do_slice = [&](int sl, bool to_global, bool last) {
+		const int l = s_snode[sl * G + grp];
+		const bool owner = (sub == 0 && l >= 0);
+		double4 bi = make_double4(0, 0, 0, 0);
+		double a0 = 1, a1 = 1, a2 = 1;
+		int ps = -1, node = 0;
+		if (owner) {
+			node = s_gid[l];
+			bi = ld_node(&P.b[node]);
+			a0 = __ldg(&P.diag[3 * node]); a1 = __ldg(&P.diag[3 * node + 1]); a2 = __ldg(&P.diag[3 * node + 2]);
+			if (P.has_pins) ps = __ldg(&P.pin_slot[node]);
+		}
+		double sx, sy, sz;
+		res_gather<V, T>(s_val, s_col, s_x, s_gid, P.x, d.n_own, s_srow[sl], s_srow[sl + 1], lane, sx, sy, sz);
+		if (owner) {
+			double nx[3];
+			if (ps >= 0) { nx[0] = P.pin_pos[3 * ps]; nx[1] = P.pin_pos[3 * ps + 1]; nx[2] = P.pin_pos[3 * ps + 2]; }
+			else {
+				const double xo[3] = {s_x[3 * l], s_x[3 * l + 1], s_x[3 * l + 2]};
+				// segment_update (src/NodalMultiColorGS.hpp:180-215)
+				double gs[3] = {(bi.x - sx) / a0, (bi.y - sy) / a1, (bi.z - sz) / a2};
+				nx[0] = one_m_omega * xo[0] + omega * gs[0]; nx[1] = one_m_omega * xo[1] + omega * gs[1]; nx[2] = one_m_omega * xo[2] + omega * gs[2];
+				bool hit = false;
+				if (P.n_obstacles > 0) hit = mcgs_collide(P.obs, P.n_obstacles, gs, nx);
+				if (last && !hit) {
+					double rx = a0 * lb_scale * (nx[0] - xo[0]), ry = a1 * lb_scale * (nx[1] - xo[1]), rz = a2 * lb_scale * (nx[2] - xo[2]);
+					lb += rx * rx + ry * ry + rz * rz;
 				}
 			}
+			s_x[3 * l] = nx[0]; s_x[3 * l + 1] = nx[1]; s_x[3 * l + 2] = nx[2];
+			if (to_global) st_node(&P.x[node], nx[0], nx[1], nx[2]);
+		}
+	};
+
+	int it = 0;
+	unsigned int epoch = 0;
+	long long pw = 0, pc = 0, pp = 0;
+	const long long t_begin = R.prof ? clock64() : 0;
+	for (; it < P.iters; ++it) {
+		lb = 0;
+		for (int color = 0; color < P.n_colors; ++color) {
+			const int s0 = s_cslice[2 * color], s1 = s_cslice[2 * color + 1], s2 = s_cslice[2 * color + 2];
+			const bool last = check && (color == P.n_colors - 1);
+			long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+			if (R.prof) t0 = clock64();
+			// interior nodes: nobody else reads or writes them and they read only this part's values, which
+			// the __syncthreads of the previous publish made visible -> no need to wait for the neighbours
+			for (int sl = s0 + warp; sl < s1; sl += n_warps) do_slice(sl, false, last);
+			if (R.prof) t1 = clock64();
+			if (epoch > 0) part_wait(R.part_epoch, s_nbr, d.n_nbr, epoch);
+			if (R.prof) t2 = clock64();
+			for (int sl = s1 + warp; sl < s2; sl += n_warps) do_slice(sl, true, last);
+			if (R.prof) { __syncthreads(); t3 = clock64(); }
 			part_publish(R.part_epoch, ++epoch);
+			if (R.prof && tid == 0) { long long t4 = clock64(); pw += t2 - t1; pc += (t1 - t0) + (t3 - t2); pp += t4 - t3; }
 		}
 		if (check) {
 			// Decide "converged?" without a grid barrier in the common case: any part whose own rows
@@ -230,14 +249,14 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 			__syncthreads();
 			if (!proven_unconverged) {
 				const double b2 = __ldcg(&P.resid[0]);
-				// every part is here (sweep_arrive == grid) and all pass-`epoch` values are published
+				// every part is here (sweep_arrive == grid) and all boundary values of this sweep are published
 				grid_barrier(P.barrier, bar_target, gridDim.x);
 				// exact residual b - A x (src/NodalMultiColorGS.hpp:136-139)
 				double acc = 0;
 				for (int sl = warp; sl < d.n_slices; sl += n_warps) {
 					const int l = s_snode[sl * G + grp];
 					double sx, sy, sz;
-					res_gather<V>(s_val, s_col, s_x, s_gid, P.x, d.n_own, s_srow[sl], s_srow[sl + 1], lane, sx, sy, sz);
+					res_gather<V, T>(s_val, s_col, s_x, s_gid, P.x, d.n_own, s_srow[sl], s_srow[sl + 1], lane, sx, sy, sz);
 					if (sub == 0 && l >= 0) {
 						const int node = s_gid[l];
 						double4 bi = ld_node(&P.b[node]);
@@ -247,15 +266,22 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 						acc += rx * rx + ry * ry + rz * rz;
 					}
 				}
-				double s = block_sum(acc, red);
-				if (tid == 0) atomicAdd(&P.resid[1 + it], s);
+				double sres = block_sum(acc, red);
+				if (tid == 0) atomicAdd(&P.resid[1 + it], sres);
 				grid_barrier(P.barrier, bar_target, gridDim.x);
 				double r2 = __ldcg(&P.resid[1 + it]);
 				if (r2 / b2 < P.tol2) break;
 			}
 		}
 	}
+	// the interior nodes have only been updated in shared memory: hand the whole part back
+	__syncthreads();
+	for (int l = tid; l < d.n_own; l += blockDim.x) st_node(&P.x[s_gid[l]], s_x[3 * l], s_x[3 * l + 1], s_x[3 * l + 2]);
 	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
+	if (R.prof && tid == 0) {
+		R.prof[4 * blockIdx.x] = (unsigned long long)pw; R.prof[4 * blockIdx.x + 1] = (unsigned long long)pc;
+		R.prof[4 * blockIdx.x + 2] = (unsigned long long)pp; R.prof[4 * blockIdx.x + 3] = (unsigned long long)(clock64() - t_begin);
+	}
 }
 
 } // namespace admmb200

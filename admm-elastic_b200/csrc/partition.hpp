@@ -25,7 +25,8 @@ struct PartDesc {
 	int gid_off;                         // into gid[]: n_own owned ids (local order) then n_halo halo ids
 	int slice_off;                       // into slice_row[] (n_slices + 1 entries, relative row numbers)
 	int snode_off;                       // into slice_node[] (n_slices * G local ids, -1 = padding)
-	int cslice_off;                      // into color_slice[] (n_colors + 1 entries)
+	int cslice_off;                      // into color_slice[] (2 n_colors + 1 entries: per colour first interior
+	                                     // slice, first boundary slice; then the end)
 	int nbr_off, n_nbr;                  // into nbr[]: parts this part exchanges halo values with
 	int pad_;
 };
@@ -43,12 +44,12 @@ struct ResidentPlan {
 	// dynamic shared memory one CTA needs with `val_bytes`-wide matrix values
 	size_t smem_bytes(int n_colors, int val_bytes) const {
 		size_t worst = 0;
-		for (const PartDesc &d : parts) worst = std::max(worst, layout(d, n_colors, val_bytes, nullptr));
+		for (const PartDesc &d : parts) worst = std::max(worst, layout(d, n_colors, val_bytes, lanes, nullptr));
 		return worst;
 	}
 	// byte offsets of the shared-memory arrays of one part (the kernel computes the same)
-	static size_t layout(const PartDesc &d, int n_colors, int val_bytes, size_t *off /* [7] or null */) {
-		const int G = 8; // nodes per slice at 4 lanes per node
+	static size_t layout(const PartDesc &d, int n_colors, int val_bytes, int lanes, size_t *off /* [7] or null */) {
+		const int G = 32 / lanes; // nodes per slice
 		size_t o = 0, tmp[7];
 		auto take = [&](int i, size_t bytes) { tmp[i] = o; o += (bytes + 15) & ~(size_t)15; };
 		take(0, sizeof(double) * 3 * (size_t)d.n_own);         // xs
@@ -57,7 +58,7 @@ struct ResidentPlan {
 		take(3, sizeof(int) * ((size_t)d.n_own + d.n_halo));   // gid
 		take(4, sizeof(int) * ((size_t)d.n_slices + 1));       // slice_row
 		take(5, sizeof(short) * (size_t)G * d.n_slices);       // slice_node
-		take(6, sizeof(int) * ((size_t)n_colors + 1));         // color_slice
+		take(6, sizeof(int) * (2 * (size_t)n_colors + 1));     // color_slice
 		if (off) std::memcpy(off, tmp, sizeof(tmp));
 		return o;
 	}
@@ -115,13 +116,22 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 
 	std::vector<std::vector<int>> own(n_parts);
 	for (int i = 0; i < n; ++i) own[R.part_of[i]].push_back(i);
+	// boundary node = has a neighbour owned by another part (the pattern is symmetric, so it is also
+	// exactly the set of nodes other parts read as halo)
+	std::vector<char> boundary(n, 0);
+	for (int i = 0; i < n; ++i)
+		for (int q = rowptr[i]; q < rowptr[i + 1]; ++q)
+			if (cols[q] != i && vals[q] != 0.0 && R.part_of[cols[q]] != R.part_of[i]) { boundary[i] = 1; boundary[cols[q]] = 1; }
 	std::vector<int> local_of(n, -1);
 	R.parts.resize(n_parts);
 	for (int p = 0; p < n_parts; ++p) {
 		std::vector<int> &nodes = own[p];
 		// colour-major, long rows first inside a colour (uniform slices -> little ELL padding), ids last
+		// and inside a colour the interior nodes first: they are updated while the neighbours' flags of
+		// the previous pass are still in flight
 		std::sort(nodes.begin(), nodes.end(), [&](int a, int b) {
 			if (color_of[a] != color_of[b]) return color_of[a] < color_of[b];
+			if (boundary[a] != boundary[b]) return boundary[a] < boundary[b];
 			if (rowlen[a] != rowlen[b]) return rowlen[a] > rowlen[b];
 			return a < b;
 		});
@@ -144,10 +154,11 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 		int rows = 0, slices = 0;
 		R.slice_row.push_back(0);
 		int k = 0;
-		for (int c = 0; c < n_colors; ++c) {
+		for (int cc = 0; cc < 2 * n_colors; ++cc) {
+			const int c = cc / 2, bnd = cc % 2;
 			R.color_slice.push_back(slices);
 			int k1 = k;
-			while (k1 < d.n_own && color_of[nodes[k1]] == c) ++k1;
+			while (k1 < d.n_own && color_of[nodes[k1]] == c && boundary[nodes[k1]] == bnd) ++k1;
 			for (; k < k1; k += G) {
 				int width = 0;
 				for (int g = 0; g < G && k + g < k1; ++g) width = std::max(width, (rowlen[nodes[k + g]] + T - 1) / T);

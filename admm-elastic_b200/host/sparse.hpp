@@ -47,10 +47,17 @@ inline Csr from_entries(int n, std::vector<Entry> &e)
 // Output: colour -> ascending node list, like graphcolor::make_map.
 inline void color_greedy(const Csr &A, std::vector<std::vector<int>> &colors)
 {
+	// Largest-degree-first greedy (Welsh-Powell), ties by node id: deterministic, and on tet meshes it
+	// gives few, evenly filled colours (4 on the block beams where index order gives 9, five of them
+	// nearly empty) -- every colour costs one synchronisation per sweep on the GPU.
 	const int n = A.n;
+	std::vector<int> deg(n, 0), order(n);
+	for (int i = 0; i < n; ++i) for (int q = A.rowptr[i]; q < A.rowptr[i + 1]; ++q) if (A.cols[q] != i && A.vals[q] != 0.0) ++deg[i];
+	std::iota(order.begin(), order.end(), 0);
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
 	std::vector<int> color(n, -1), mark;
 	int n_colors = 0;
-	for (int i = 0; i < n; ++i) {
+	for (int i : order) {
 		mark.assign(n_colors + 1, 0);
 		for (int q = A.rowptr[i]; q < A.rowptr[i + 1]; ++q) {
 			int j = A.cols[q];

@@ -183,7 +183,7 @@ long long admm_b200_launch_count( const admm_b200_solver *s );
  * csrc/partition.hpp.  Returns 0 when the plan covers every node exactly once and reproduces
  * L_offdiag * x; the message of a failure is available from admm_b200_last_error(NULL). */
 int admm_b200_plan_check( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
-	const double *pos3, int n_parts, int val_bytes, const double *x, double *max_err, long long *stats, int *part_of );
+	const double *pos3, int n_parts, int val_bytes, int lanes, const double *x, double *max_err, long long *stats, int *part_of );
 
 /* One line describing which global-solve kernel finalize chose and why (diagnostics). */
 const char *admm_b200_solver_info( const admm_b200_solver *s );

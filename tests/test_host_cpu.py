@@ -137,9 +137,9 @@ def test_resident_gauss_seidel_plan(pkg, dims, parts):
     rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
     ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-    for val_bytes, tol in ((8, 1e-12), (4, 1e-12)):
+    for val_bytes, lanes, tol in ((8, 1, 1e-12), (4, 1, 1e-12), (8, 2, 1e-12), (4, 4, 1e-12)):
         err, stats, part = ctypes.c_double(0), (ctypes.c_longlong * 6)(), np.zeros(n, np.int32)
-        rc = pkg.cuda_lib.admm_b200_plan_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), parts, val_bytes,
+        rc = pkg.cuda_lib.admm_b200_plan_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), parts, val_bytes, lanes,
                                                dp(x), ctypes.byref(err), stats, ip(part))
         assert rc == 0, pkg.cuda_lib.admm_b200_last_error(None)
         assert err.value < tol
