@@ -30,28 +30,33 @@ struct McgsResParams {
 	unsigned int *part_epoch;   // [gridDim.x * 8] one flag per part (32-byte stride), zeroed before launch
 	unsigned int *sweep_flag;   // [iters] set to 1 by any part that proves "not converged yet" for that sweep
 	unsigned int *sweep_arrive; // [iters] parts that have finished that sweep
-	unsigned long long *prof;   // NULL, or [gridDim.x * 4] clock cycles of thread 0: waiting, computing, publishing, total
+	unsigned long long *prof;   // NULL, or [gridDim.x * 5] clock cycles of thread 0: waiting, boundary compute, publishing, total, interior compute
 };
 
 // Point-to-point ordering between neighbouring parts, replacing a grid barrier per colour pass.
 // publish: this part has finished pass `epoch` (all its reads of neighbours' values and all its writes).
 // wait:    every neighbour has finished pass `epoch`, so (a) their values of that pass are visible and
 //          (b) they no longer read the values this part is about to overwrite.
+// Only the boundary warps (warps [0, n_bwarps)) wait: they synchronise among themselves with named
+// barrier 1, so the interior warps keep computing while the flags are in flight.
+__device__ __forceinline__ void named_sync(int id, int n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
+
 __device__ __forceinline__ void part_publish(unsigned int *part_epoch, unsigned int epoch)
 {
-	__syncthreads();
+	// caller has just passed a __syncthreads(): every warp's writes of this pass are done
 	if (threadIdx.x == 0) { fence_acq_rel_gpu(); st_relaxed_u32(part_epoch + 8 * blockIdx.x, epoch); }
 }
-__device__ __forceinline__ void part_wait(const unsigned int *part_epoch, const int *s_nbr, int n_nbr, unsigned int epoch)
+__device__ __forceinline__ void part_wait(const unsigned int *part_epoch, const int *s_nbr, int n_nbr, unsigned int epoch, int n_bthreads)
 {
-	if ((int)threadIdx.x < n_nbr) {
-		const unsigned int *f = part_epoch + 8 * s_nbr[threadIdx.x];
+	for (int i = threadIdx.x; i < n_nbr; i += n_bthreads) {
+		const unsigned int *f = part_epoch + 8 * s_nbr[i];
 		while (ld_relaxed_u32(f) < epoch) { }
-		fence_acq_rel_gpu();
 	}
-	__syncthreads();
+	fence_acq_rel_gpu();
+	named_sync(1, n_bthreads);
 }
 
+// ---- TMA bulk copy (cp.async.bulk) + mbarrier, used once per launch to stage the matrix ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -201,9 +206,14 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 		}
 	};
 
+	// Warp roles: warps [0, n_bwarps) own the boundary slices -- the chain "wait for the neighbours ->
+	// update -> publish" that limits the pass rate -- the others update the interior concurrently.  Both
+	// meet at one __syncthreads per pass: pass c+1 reads what both groups wrote in pass c.
+	const int n_bwarps = n_warps / 2, n_iwarps = n_warps - n_bwarps;
+	const bool bwarp = warp < n_bwarps;
 	int it = 0;
 	unsigned int epoch = 0;
-	long long pw = 0, pc = 0, pp = 0;
+	long long pw = 0, pc = 0, pp = 0, pi = 0;
 	const long long t_begin = R.prof ? clock64() : 0;
 	for (; it < P.iters; ++it) {
 		lb = 0;
@@ -212,16 +222,21 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 			const bool last = check && (color == P.n_colors - 1);
 			long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 			if (R.prof) t0 = clock64();
-			// interior nodes: nobody else reads or writes them and they read only this part's values, which
-			// the __syncthreads of the previous publish made visible -> no need to wait for the neighbours
-			for (int sl = s0 + warp; sl < s1; sl += n_warps) do_slice(sl, false, last);
-			if (R.prof) t1 = clock64();
-			if (epoch > 0) part_wait(R.part_epoch, s_nbr, d.n_nbr, epoch);
-			if (R.prof) t2 = clock64();
-			for (int sl = s1 + warp; sl < s2; sl += n_warps) do_slice(sl, true, last);
-			if (R.prof) { __syncthreads(); t3 = clock64(); }
+			if (bwarp) {
+				if (epoch > 0) part_wait(R.part_epoch, s_nbr, d.n_nbr, epoch, 32 * n_bwarps);
+				if (R.prof) t1 = clock64();
+				for (int sl = s1 + warp; sl < s2; sl += n_bwarps) do_slice(sl, true, last);
+				if (R.prof) t2 = clock64();
+			} else {
+				// interior nodes: nobody else reads or writes them and they read only this part's values
+				for (int sl = s0 + (warp - n_bwarps); sl < s1; sl += n_iwarps) do_slice(sl, false, last);
+				if (R.prof) t1 = clock64();
+			}
+			__syncthreads();
+			if (R.prof) t3 = clock64();
 			part_publish(R.part_epoch, ++epoch);
-			if (R.prof && tid == 0) { long long t4 = clock64(); pw += t2 - t1; pc += (t1 - t0) + (t3 - t2); pp += t4 - t3; }
+			if (R.prof && tid == 0) { long long t4 = clock64(); pw += t1 - t0; pc += t2 - t1; pp += t4 - t3; }
+			if (R.prof && tid == 32 * n_bwarps) pi += t1 - t0;
 		}
 		if (check) {
 			// Decide "converged?" without a grid barrier in the common case: any part whose own rows
@@ -279,9 +294,10 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	for (int l = tid; l < d.n_own; l += blockDim.x) st_node(&P.x[s_gid[l]], s_x[3 * l], s_x[3 * l + 1], s_x[3 * l + 2]);
 	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
 	if (R.prof && tid == 0) {
-		R.prof[4 * blockIdx.x] = (unsigned long long)pw; R.prof[4 * blockIdx.x + 1] = (unsigned long long)pc;
-		R.prof[4 * blockIdx.x + 2] = (unsigned long long)pp; R.prof[4 * blockIdx.x + 3] = (unsigned long long)(clock64() - t_begin);
+		R.prof[5 * blockIdx.x] = (unsigned long long)pw; R.prof[5 * blockIdx.x + 1] = (unsigned long long)pc;
+		R.prof[5 * blockIdx.x + 2] = (unsigned long long)pp; R.prof[5 * blockIdx.x + 3] = (unsigned long long)(clock64() - t_begin);
 	}
+	if (R.prof && tid == 32 * n_bwarps) R.prof[5 * blockIdx.x + 4] = (unsigned long long)pi;
 }
 
 } // namespace admmb200

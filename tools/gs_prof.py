@@ -12,7 +12,8 @@ assert sol.initialize(dt=1/24,admm_iters=20,gravity=-9.8,linsolver=1)
 sol.set_x(scene['x0'].ravel()); sol.upload_state()
 for _ in range(3): sol.step_device()
 print(sol.runtime_data())
-p=sol.device().debug_get('gs_prof',4*148).reshape(148,4)
-print('cycles per solve: wait mean/max %.0f %.0f | compute mean/max %.0f %.0f | publish mean/max %.0f %.0f | total %.0f'%(p[:,0].mean(),p[:,0].max(),p[:,1].mean(),p[:,1].max(),p[:,2].mean(),p[:,2].max(),p[:,3].mean()))
-print('per pass (270): wait %.0f compute %.0f publish %.0f total %.0f cycles'%tuple(p.mean(0)/270))
+ncol=len(sol.colors()); passes=30*ncol
+p=sol.device().debug_get('gs_prof',5*148).reshape(148,5)
+names=['wait','boundary','publish','total','interior']
+print('colours',ncol,'passes',passes,' cycles per pass (mean over parts | max):', {n:(int(p[:,i].mean()/passes), int(p[:,i].max()/passes)) for i,n in enumerate(names)})
 print(sol.device().info())
