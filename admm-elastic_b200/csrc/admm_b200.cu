@@ -520,7 +520,7 @@ void build_mcgs_resident(S *s)
 	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);
 	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
 	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
-	if (getenv("ADMM_B200_GS_PROF")) { s->res_prof.alloc(5 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
+	if (getenv("ADMM_B200_GS_PROF")) { s->res_prof.alloc(16 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
 	if (val_bytes == 8) {
 		s->res_val.alloc(std::max<size_t>(R.val.size(), 1) * 8);
 		if (!R.val.empty()) CK(cudaMemcpyAsync(s->res_val.p, R.val.data(), R.val.size() * 8, cudaMemcpyHostToDevice, s->stream));

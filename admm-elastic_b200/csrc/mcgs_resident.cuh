@@ -30,7 +30,7 @@ struct McgsResParams {
 	unsigned int *part_epoch;   // [gridDim.x * 8] one flag per part (32-byte stride), zeroed before launch
 	unsigned int *sweep_flag;   // [iters] set to 1 by any part that proves "not converged yet" for that sweep
 	unsigned int *sweep_arrive; // [iters] parts that have finished that sweep
-	unsigned long long *prof;   // NULL, or [gridDim.x * 5] clock cycles of thread 0: waiting, boundary compute, publishing, total, interior compute
+	unsigned long long *prof;   // NULL, or [gridDim.x * 16] clock cycles of thread 0: waiting, boundary compute, publishing, total, interior compute
 };
 
 // Point-to-point ordering between neighbouring parts, replacing a grid barrier per colour pass.
@@ -48,11 +48,13 @@ __device__ __forceinline__ void part_publish(unsigned int *part_epoch, unsigned 
 }
 __device__ __forceinline__ void part_wait(const unsigned int *part_epoch, const int *s_nbr, int n_nbr, unsigned int epoch, int n_bthreads)
 {
-	for (int i = threadIdx.x; i < n_nbr; i += n_bthreads) {
-		const unsigned int *f = part_epoch + 8 * s_nbr[i];
-		while (ld_relaxed_u32(f) < epoch) { }
+	if ((int)threadIdx.x < n_nbr) {
+		for (int i = threadIdx.x; i < n_nbr; i += n_bthreads) {
+			const unsigned int *f = part_epoch + 8 * s_nbr[i];
+			while (ld_relaxed_u32(f) < epoch) { }
+		}
+		fence_acq_rel_gpu();
 	}
-	fence_acq_rel_gpu();
 	named_sync(1, n_bthreads);
 }
 
@@ -172,7 +174,10 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	// One slice = G nodes of one colour: gather, SOR update, write back.  `to_global`: boundary nodes are
 	// read by other parts and go to global memory at once; interior ones only at the end of the solve.
 	double lb = 0;
+	long long ps_meta = 0, ps_gather = 0, ps_tail = 0, ps_n = 0;
 	auto do_slice = [&](int sl, bool to_global, bool last) {
+		long long q0 = 0, q1 = 0, q2 = 0;
+		if (R.prof) q0 = clock64();
 		const int l = s_snode[sl * G + grp];
 		const bool owner = (sub == 0 && l >= 0);
 		double4 bi = make_double4(0, 0, 0, 0);
@@ -185,7 +190,9 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 			if (P.has_pins) ps = __ldg(&P.pin_slot[node]);
 		}
 		double sx, sy, sz;
+		if (R.prof) q1 = clock64();
 		res_gather<V, T>(s_val, s_col, s_x, s_gid, P.x, d.n_own, s_srow[sl], s_srow[sl + 1], lane, sx, sy, sz);
+		if (R.prof) q2 = clock64();
 		if (owner) {
 			double nx[3];
 			if (ps >= 0) { nx[0] = P.pin_pos[3 * ps]; nx[1] = P.pin_pos[3 * ps + 1]; nx[2] = P.pin_pos[3 * ps + 2]; }
@@ -204,6 +211,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 			s_x[3 * l] = nx[0]; s_x[3 * l + 1] = nx[1]; s_x[3 * l + 2] = nx[2];
 			if (to_global) st_node(&P.x[node], nx[0], nx[1], nx[2]);
 		}
+		if (R.prof) { long long q3 = clock64(); ps_meta += q1 - q0; ps_gather += q2 - q1; ps_tail += q3 - q2; ps_n += 1; }
 	};
 
 	// Warp roles: warps [0, n_bwarps) own the boundary slices -- the chain "wait for the neighbours ->
@@ -294,10 +302,15 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_kernel(
 	for (int l = tid; l < d.n_own; l += blockDim.x) st_node(&P.x[s_gid[l]], s_x[3 * l], s_x[3 * l + 1], s_x[3 * l + 2]);
 	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
 	if (R.prof && tid == 0) {
-		R.prof[5 * blockIdx.x] = (unsigned long long)pw; R.prof[5 * blockIdx.x + 1] = (unsigned long long)pc;
-		R.prof[5 * blockIdx.x + 2] = (unsigned long long)pp; R.prof[5 * blockIdx.x + 3] = (unsigned long long)(clock64() - t_begin);
+		unsigned long long *q = R.prof + 16 * blockIdx.x;
+		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pp; q[3] = (unsigned long long)(clock64() - t_begin);
+		q[5] = (unsigned long long)ps_meta; q[6] = (unsigned long long)ps_gather; q[7] = (unsigned long long)ps_tail; q[8] = (unsigned long long)ps_n;
 	}
-	if (R.prof && tid == 32 * n_bwarps) R.prof[5 * blockIdx.x + 4] = (unsigned long long)pi;
+	if (R.prof && tid == 32 * n_bwarps) {
+		unsigned long long *q = R.prof + 16 * blockIdx.x;
+		q[4] = (unsigned long long)pi;
+		q[9] = (unsigned long long)ps_meta; q[10] = (unsigned long long)ps_gather; q[11] = (unsigned long long)ps_tail; q[12] = (unsigned long long)ps_n;
+	}
 }
 
 } // namespace admmb200
