@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "sptrsv.cuh"
 #include "mcgs_resident.cuh"
+#include "mcgs_resident_f32.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -135,7 +136,8 @@ struct admm_b200_solver {
 	DevBuf<PartDesc> res_parts;
 	DevBuf<uint16_t> res_col;
 	DevBuf<char> res_val;
-	DevBuf<int> res_gid, res_slice_row, res_color_slice, res_nbr;
+	DevBuf<int> res_gid, res_slice_row, res_color_slice, res_nbr, res_halo_color;
+	DevBuf<float4> res_dglob, res_nodebuf;
 	DevBuf<unsigned long long> res_prof; // ADMM_B200_GS_PROF=1: per-part cycle counters of the last solve
 	DevBuf<unsigned int> res_sync; // part_epoch [8 * n_sms] | sweep_flag [iters] | sweep_arrive [iters]
 	DevBuf<short> res_slice_node;
@@ -299,6 +301,8 @@ template <int T> int mcgs_occupancy()
 
 void fill_mcgs_params(S *s, McgsParams &P);
 
+// precision FP64: positions in shared memory as doubles (mcgs_resident_kernel<double>);
+// precision FP32: fp32 sweeps on the increment around the fp64 anchor (mcgs_resident_f32_kernel)
 const void *resident_kernel_ptr(bool fp64, int lanes)
 {
 	if (fp64) {
@@ -306,22 +310,35 @@ const void *resident_kernel_ptr(bool fp64, int lanes)
 		if (lanes == 2) return (const void *)mcgs_resident_kernel<double, 2>;
 		return (const void *)mcgs_resident_kernel<double, 4>;
 	}
-	if (lanes == 1) return (const void *)mcgs_resident_kernel<float, 1>;
-	if (lanes == 2) return (const void *)mcgs_resident_kernel<float, 2>;
-	return (const void *)mcgs_resident_kernel<float, 4>;
+	if (lanes == 1) return (const void *)mcgs_resident_f32_kernel<1>;
+	if (lanes == 2) return (const void *)mcgs_resident_f32_kernel<2>;
+	return (const void *)mcgs_resident_f32_kernel<4>;
 }
 
 void launch_mcgs_resident(S *s)
 {
+	const bool fp64 = s->precision == ADMM_B200_FP64;
 	McgsResParams R;
-	fill_mcgs_params(s, R.base);
-	R.parts = s->res_parts.p; R.col = s->res_col.p; R.val = s->res_val.p; R.gid = s->res_gid.p;
-	R.slice_row = s->res_slice_row.p; R.color_slice = s->res_color_slice.p; R.slice_node = s->res_slice_node.p; R.nbr = s->res_nbr.p;
-	R.part_epoch = s->res_sync.p; R.sweep_flag = s->res_sync.p + 8 * (size_t)s->n_sms; R.sweep_arrive = R.sweep_flag + s->gs_iters;
+	McgsRes32Params R32;
+	McgsParams &B = fp64 ? R.base : R32.base;
+	fill_mcgs_params(s, B);
+	unsigned int *part_epoch = s->res_sync.p, *sweep_flag = s->res_sync.p + 8 * (size_t)s->n_sms, *sweep_arrive = sweep_flag + s->gs_iters;
 	CK(cudaMemsetAsync(s->res_sync.p, 0, s->res_sync.n * sizeof(unsigned int), s->stream));
-	R.prof = s->res_prof.p;
-	void *args[] = {&R};
-	CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(s->precision == ADMM_B200_FP64, s->gs_res_lanes), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
+	void *args[1];
+	if (fp64) {
+		R.parts = s->res_parts.p; R.col = s->res_col.p; R.val = s->res_val.p; R.gid = s->res_gid.p;
+		R.slice_row = s->res_slice_row.p; R.color_slice = s->res_color_slice.p; R.slice_node = s->res_slice_node.p; R.nbr = s->res_nbr.p;
+		R.part_epoch = part_epoch; R.sweep_flag = sweep_flag; R.sweep_arrive = sweep_arrive; R.prof = s->res_prof.p;
+		args[0] = &R;
+	} else {
+		R32.parts = s->res_parts.p; R32.col = s->res_col.p; R32.val = (const float *)s->res_val.p; R32.gid = s->res_gid.p;
+		R32.slice_row = s->res_slice_row.p; R32.color_slice = s->res_color_slice.p; R32.slice_node = s->res_slice_node.p; R32.nbr = s->res_nbr.p;
+		R32.halo_color = s->res_halo_color.p;
+		R32.part_epoch = part_epoch; R32.sweep_flag = sweep_flag; R32.sweep_arrive = sweep_arrive; R32.prof = s->res_prof.p;
+		R32.dglob = s->res_dglob.p; R32.nodebuf = s->res_nodebuf.p;
+		args[0] = &R32;
+	}
+	CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
 	s->launches++;
 }
 
@@ -502,7 +519,7 @@ void build_mcgs_resident(S *s)
 		s->gs_info = std::string("stream (") + e.what() + ")";
 		return;
 	}
-	const size_t need = R.smem_bytes(s->n_colors, val_bytes);
+	const size_t need = R.smem_bytes(s->n_colors, val_bytes, val_bytes == 8 ? 0 : 1);
 	char buf[256];
 	snprintf(buf, sizeof(buf), "%d lane(s)/node, %zu B shared memory per part needed (max own %zu, halo %zu, rows %zu, neighbours %zu; ELL fill %.3f), budget %zu B", lanes, need, R.max_own, R.max_halo, R.max_rows,
 		R.max_nbr, R.entries ? (double)R.nnz / (double)R.entries : 1.0, budget);
@@ -518,6 +535,8 @@ void build_mcgs_resident(S *s)
 	s->res_color_slice.upload(R.color_slice, s->stream);
 	s->res_slice_node.upload(R.slice_node, s->stream);
 	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);
+	s->res_halo_color.upload(R.halo_color, s->stream);
+	if (val_bytes == 4) { s->res_dglob.alloc(s->n_nodes); s->res_dglob.zero(s->stream); s->res_nodebuf.alloc(2 * (size_t)s->n_nodes); s->res_nodebuf.zero(s->stream); }
 	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
 	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
 	if (getenv("ADMM_B200_GS_PROF")) { s->res_prof.alloc(16 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }

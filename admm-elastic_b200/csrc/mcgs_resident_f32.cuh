@@ -1,0 +1,292 @@
+// mcgs_resident_f32.cuh -- NodalMultiColorGS::solve (src/NodalMultiColorGS.hpp:60-146) on the INCREMENT,
+// resident in shared memory, single precision sweeps around a double precision anchor.
+//
+// SOR on A x = b started at x_ref is, in exact arithmetic, the same iteration as SOR on
+//     A d = r0,   r0 = b - A x_ref,   x = x_ref + d,   d = 0 at the start
+// (substitute x = x_ref + d in segment_update, src/NodalMultiColorGS.hpp:180-215).  x_ref -- the previous
+// ADMM iterate, metres -- stays in fp64 in HBM and is touched twice per solve (r0 at the start, x = x_ref
+// + d at the end); the increment d -- millimetres within one solve -- is swept in fp32.  An fp32 ulp of d is
+// 1e-10 m, i.e. better than 1e-10 relative to x: far below the 1e-6 the reference's own prox defines x
+// to, while every neighbour read is one 16-byte float4 from shared memory instead of three
+// doubles and all arithmetic is FFMA.  This is the production (ADMM_B200_FP32) global solve; the fp64
+// variant (mcgs_resident_kernel) stays the validation path.
+//
+// Layout per part (one CTA per SM, partition.hpp mode 1): float4 d[own + halo], float val / u16 col sliced
+// ELL, id tables.  Halo increments are cached in shared memory and refreshed once per pass -- only the
+// halo nodes of the colour the neighbours have just updated (contiguous: halo is sorted by colour) --
+// so the gather itself never leaves the SM.  Synchronisation, warp roles and the lazy convergence test
+// are those of mcgs_resident.cuh.
+#pragma once
+#include "mcgs_resident.cuh"
+
+namespace admmb200 {
+
+struct McgsRes32Params {
+	McgsParams base;
+	const PartDesc *parts;
+	const uint16_t *col;
+	const float *val;
+	const int *gid, *slice_row, *color_slice, *nbr, *halo_color;
+	const short *slice_node;
+	unsigned int *part_epoch, *sweep_flag, *sweep_arrive;
+	unsigned long long *prof;
+	float4 *dglob;   // [n_nodes]: increments of boundary nodes, published every pass
+	float4 *nodebuf; // [2 * n_nodes] by (own_off + local id): {r0.xyz, pin slot + 1}, {1/a.xyz, -}
+};
+
+__device__ __forceinline__ float4 ldcg_f4(const float4 *p) { return __ldcg(p); }
+
+template <int T>
+__device__ __forceinline__ void res32_gather(const float *s_val, const uint16_t *s_col, const float4 *s_d, int r0, int r1, int lane,
+	float &sx, float &sy, float &sz)
+{
+	sx = 0.f; sy = 0.f; sz = 0.f;
+#pragma unroll 4
+	for (int r = r0; r < r1; ++r) {
+		const int c = s_col[r * 32 + lane];
+		const float a = s_val[r * 32 + lane];
+		const float4 dv = s_d[c];
+		sx = fmaf(a, dv.x, sx); sy = fmaf(a, dv.y, sy); sz = fmaf(a, dv.z, sz);
+	}
+#pragma unroll
+	for (int o = 1; o < T; o <<= 1) {
+		sx += __shfl_xor_sync(0xffffffffu, sx, o);
+		sy += __shfl_xor_sync(0xffffffffu, sy, o);
+		sz += __shfl_xor_sync(0xffffffffu, sz, o);
+	}
+}
+
+template <int T>
+__global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_kernel(McgsRes32Params R)
+{
+	constexpr int G = 32 / T;
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ double red[32];
+	__shared__ __align__(8) uint64_t tma_bar;
+	__shared__ int s_nbr[192];
+	__shared__ int s_decision;
+	const McgsParams &P = R.base;
+	const PartDesc d = R.parts[blockIdx.x];
+	const int tid = threadIdx.x, lane = tid & 31, sub = lane % T, grp = lane / T, warp = tid >> 5, n_warps = blockDim.x >> 5;
+	const int n_loc = d.n_own + d.n_halo, C = P.n_colors;
+
+	// shared-memory layout: must match ResidentPlan::layout(mode 1)
+	size_t o = 0;
+	auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+	float4 *s_d = (float4 *)(smem + take(16 * (size_t)n_loc));
+	float *s_val = (float *)(smem + take(sizeof(float) * 32 * (size_t)d.n_rows));
+	uint16_t *s_col = (uint16_t *)(smem + take(sizeof(uint16_t) * 32 * (size_t)d.n_rows));
+	int *s_gid = (int *)(smem + take(sizeof(int) * (size_t)n_loc));
+	int *s_srow = (int *)(smem + take(sizeof(int) * ((size_t)d.n_slices + 1)));
+	short *s_snode = (short *)(smem + take(sizeof(short) * (size_t)G * d.n_slices));
+	int *s_cslice = (int *)(smem + take(sizeof(int) * (2 * (size_t)C + 1)));
+	int *s_hcol = (int *)(smem + take(sizeof(int) * ((size_t)C + 1)));
+
+	// ---- stage the part: matrix by TMA bulk copy, index tables by plain loads, d = 0 ----
+	const uint32_t val_bytes = (uint32_t)(sizeof(float) * 32 * (size_t)d.n_rows), col_bytes = (uint32_t)(sizeof(uint16_t) * 32 * (size_t)d.n_rows);
+	if (tid == 0) mbar_init(&tma_bar, 1);
+	__syncthreads();
+	if (tid == 0 && d.n_rows > 0) {
+		mbar_expect_tx(&tma_bar, val_bytes + col_bytes);
+		const unsigned char *gv = (const unsigned char *)(R.val + d.ent_off);
+		const unsigned char *gc = (const unsigned char *)(R.col + d.ent_off);
+		const uint32_t chunk = 32768;
+		for (uint32_t at = 0; at < val_bytes; at += chunk) bulk_g2s((unsigned char *)s_val + at, gv + at, min(chunk, val_bytes - at), &tma_bar);
+		for (uint32_t at = 0; at < col_bytes; at += chunk) bulk_g2s((unsigned char *)s_col + at, gc + at, min(chunk, col_bytes - at), &tma_bar);
+	}
+	for (int i = tid; i < n_loc; i += blockDim.x) { s_gid[i] = R.gid[d.gid_off + i]; s_d[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+	for (int i = tid; i <= d.n_slices; i += blockDim.x) s_srow[i] = R.slice_row[d.slice_off + i];
+	for (int i = tid; i < G * d.n_slices; i += blockDim.x) s_snode[i] = R.slice_node[d.snode_off + i];
+	for (int i = tid; i <= 2 * C; i += blockDim.x) s_cslice[i] = R.color_slice[d.cslice_off + i];
+	for (int i = tid; i <= C; i += blockDim.x) s_hcol[i] = R.halo_color[d.hcolor_off + i];
+	for (int i = tid; i < d.n_nbr; i += blockDim.x) s_nbr[i] = R.nbr[d.nbr_off + i];
+	if (d.n_rows > 0) mbar_wait(&tma_bar, 0);
+	__syncthreads();
+
+	unsigned int bar_target = 0;
+	const bool check = P.tol2 > 0.0;
+	const float omega = (float)P.omega, one_m_omega = (float)(1.0 - P.omega), lb_scale = (float)(1.0 / P.omega - 1.0);
+	float4 *nb = R.nodebuf + 2 * (size_t)d.own_off;
+
+	// ---- r0 = b - A x_ref in fp64 (x_ref = P.x, read-only until the very end), and |b|^2 ----
+	{
+		double b2 = 0;
+		for (int sl = warp; sl < d.n_slices; sl += n_warps) {
+			const int l = s_snode[sl * G + grp];
+			double sx = 0, sy = 0, sz = 0;
+			for (int r = s_srow[sl]; r < s_srow[sl + 1]; ++r) {
+				const int c = s_col[r * 32 + lane];
+				const double a = (double)s_val[r * 32 + lane];
+				const double4 xc = ld_node(&P.x[s_gid[c]]);
+				sx += a * xc.x; sy += a * xc.y; sz += a * xc.z;
+			}
+#pragma unroll
+			for (int o2 = 1; o2 < T; o2 <<= 1) {
+				sx += __shfl_xor_sync(0xffffffffu, sx, o2);
+				sy += __shfl_xor_sync(0xffffffffu, sy, o2);
+				sz += __shfl_xor_sync(0xffffffffu, sz, o2);
+			}
+			if (sub == 0 && l >= 0) {
+				const int node = s_gid[l];
+				const double4 bi = ld_node(&P.b[node]), xi = ld_node(&P.x[node]);
+				const double a0 = __ldg(&P.diag[3 * node]), a1 = __ldg(&P.diag[3 * node + 1]), a2 = __ldg(&P.diag[3 * node + 2]);
+				const int ps = P.has_pins ? __ldg(&P.pin_slot[node]) : -1;
+				nb[2 * l] = make_float4((float)(bi.x - sx - a0 * xi.x), (float)(bi.y - sy - a1 * xi.y), (float)(bi.z - sz - a2 * xi.z), __int_as_float(ps + 1));
+				nb[2 * l + 1] = make_float4((float)(1.0 / a0), (float)(1.0 / a1), (float)(1.0 / a2), 0.f);
+				b2 += bi.x * bi.x + bi.y * bi.y + bi.z * bi.z;
+			}
+		}
+		if (check) {
+			double s = block_sum(b2, red); // b_norm = |b|^2 (src/NodalMultiColorGS.hpp:92)
+			if (tid == 0) atomicAdd(&P.resid[0], s);
+			grid_barrier(P.barrier, bar_target, gridDim.x); // the only grid-wide barrier of a solve
+		} else __syncthreads();
+	}
+	const double thresh = check ? 4.0 * P.tol2 * __ldcg(&P.resid[0]) : 0.0;
+
+	double lb = 0;
+	auto do_slice = [&](int sl, bool to_global, bool last) {
+		const int l = s_snode[sl * G + grp];
+		const bool owner = (sub == 0 && l >= 0);
+		float4 rb = make_float4(0.f, 0.f, 0.f, 0.f), ia = rb;
+		if (owner) { rb = nb[2 * l]; ia = nb[2 * l + 1]; }
+		float sx, sy, sz;
+		res32_gather<T>(s_val, s_col, s_d, s_srow[sl], s_srow[sl + 1], lane, sx, sy, sz);
+		if (owner) {
+			const float4 dold = s_d[l];
+			float4 dn;
+			const int ps = __float_as_int(rb.w) - 1;
+			if (ps >= 0) {
+				// pinned node (src/NodalMultiColorGS.hpp:111-117): x = pin, i.e. d = pin - x_ref
+				const double4 xr = ld_node(&P.x[s_gid[l]]);
+				dn = make_float4((float)(P.pin_pos[3 * ps] - xr.x), (float)(P.pin_pos[3 * ps + 1] - xr.y), (float)(P.pin_pos[3 * ps + 2] - xr.z), 0.f);
+			} else {
+				// segment_update (src/NodalMultiColorGS.hpp:180-215) on the increment
+				const float g0 = (rb.x - sx) * ia.x, g1 = (rb.y - sy) * ia.y, g2 = (rb.z - sz) * ia.z;
+				dn = make_float4(fmaf(omega, g0, one_m_omega * dold.x), fmaf(omega, g1, one_m_omega * dold.y), fmaf(omega, g2, one_m_omega * dold.z), 0.f);
+				bool hit = false;
+				if (P.n_obstacles > 0) {
+					// the obstacle test needs absolute positions
+					const double4 xr = ld_node(&P.x[s_gid[l]]);
+					double gs[3] = {xr.x + (double)g0, xr.y + (double)g1, xr.z + (double)g2};
+					double nx[3] = {xr.x + (double)dn.x, xr.y + (double)dn.y, xr.z + (double)dn.z};
+					hit = mcgs_collide(P.obs, P.n_obstacles, gs, nx);
+					if (hit) dn = make_float4((float)(nx[0] - xr.x), (float)(nx[1] - xr.y), (float)(nx[2] - xr.z), 0.f);
+				}
+				if (last && !hit) {
+					const float rx = lb_scale * (dn.x - dold.x) / ia.x, ry = lb_scale * (dn.y - dold.y) / ia.y, rz = lb_scale * (dn.z - dold.z) / ia.z;
+					lb += (double)rx * rx + (double)ry * ry + (double)rz * rz;
+				}
+			}
+			s_d[l] = dn;
+			if (to_global) R.dglob[s_gid[l]] = dn;
+		}
+	};
+
+	const int n_bwarps = n_warps / 2, n_iwarps = n_warps - n_bwarps, n_bthreads = 32 * n_bwarps;
+	const bool bwarp = warp < n_bwarps;
+	int it = 0;
+	unsigned int epoch = 0;
+	long long pw = 0, pc = 0, pp = 0, pi = 0;
+	const long long t_begin = R.prof ? clock64() : 0;
+	for (; it < P.iters; ++it) {
+		lb = 0;
+		for (int color = 0; color < C; ++color) {
+			const int s0 = s_cslice[2 * color], s1 = s_cslice[2 * color + 1], s2 = s_cslice[2 * color + 2];
+			const bool last = check && (color == C - 1);
+			long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+			if (R.prof) t0 = clock64();
+			if (bwarp) {
+				if (epoch > 0) {
+					// wait for the neighbours' previous pass, then pull in what they changed: the halo nodes of
+					// that pass's colour
+					if (tid < d.n_nbr) {
+						for (int i = tid; i < d.n_nbr; i += n_bthreads) {
+							const unsigned int *f = R.part_epoch + 8 * s_nbr[i];
+							while (ld_relaxed_u32(f) < epoch) { }
+						}
+						fence_acq_rel_gpu();
+					}
+					named_sync(1, n_bthreads);
+					const int cp = (color + C - 1) % C;
+					for (int h = s_hcol[cp] + tid; h < s_hcol[cp + 1]; h += n_bthreads) s_d[d.n_own + h] = ldcg_f4(&R.dglob[s_gid[d.n_own + h]]);
+					named_sync(1, n_bthreads);
+				}
+				if (R.prof) t1 = clock64();
+				for (int sl = s1 + warp; sl < s2; sl += n_bwarps) do_slice(sl, true, last);
+				if (R.prof) t2 = clock64();
+			} else {
+				for (int sl = s0 + (warp - n_bwarps); sl < s1; sl += n_iwarps) do_slice(sl, false, last);
+				if (R.prof) t1 = clock64();
+			}
+			__syncthreads();
+			if (R.prof) t3 = clock64();
+			part_publish(R.part_epoch, ++epoch);
+			if (R.prof && tid == 0) { long long t4 = clock64(); pw += t1 - t0; pc += t2 - t1; pp += t4 - t3; }
+			if (R.prof && tid == n_bthreads) pi += t1 - t0;
+		}
+		if (check) {
+			// see mcgs_resident.cuh: "converged?" decided without a grid barrier in the common case
+			double s = block_sum(lb, red);
+			if (tid == 0) {
+				if (s >= thresh) R.sweep_flag[it] = 1u;
+				else if (s > 0.0) atomicAdd(&P.resid_lb[it], s);
+				__threadfence();
+				atomicAdd(&R.sweep_arrive[it], 1u);
+				int decision = -1;
+				while (decision < 0) {
+					if (ld_relaxed_u32(&R.sweep_flag[it]) != 0u) decision = 1;
+					else if (ld_relaxed_u32(&R.sweep_arrive[it]) == gridDim.x) {
+						fence_acq_rel_gpu();
+						decision = (ld_relaxed_u32(&R.sweep_flag[it]) != 0u || __ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
+					}
+				}
+				s_decision = decision;
+			}
+			__syncthreads();
+			const bool proven_unconverged = s_decision == 1;
+			__syncthreads();
+			if (!proven_unconverged) {
+				const double b2 = __ldcg(&P.resid[0]);
+				grid_barrier(P.barrier, bar_target, gridDim.x);
+				// exact residual b - A x = r0 - A d (src/NodalMultiColorGS.hpp:136-139): all halo values first
+				for (int h = tid; h < d.n_halo; h += blockDim.x) s_d[d.n_own + h] = ldcg_f4(&R.dglob[s_gid[d.n_own + h]]);
+				__syncthreads();
+				double acc = 0;
+				for (int sl = warp; sl < d.n_slices; sl += n_warps) {
+					const int l = s_snode[sl * G + grp];
+					float sx, sy, sz;
+					res32_gather<T>(s_val, s_col, s_d, s_srow[sl], s_srow[sl + 1], lane, sx, sy, sz);
+					if (sub == 0 && l >= 0) {
+						const float4 rb = nb[2 * l], ia = nb[2 * l + 1], dv = s_d[l];
+						double rx = (double)rb.x - (double)sx - (double)dv.x / (double)ia.x;
+						double ry = (double)rb.y - (double)sy - (double)dv.y / (double)ia.y;
+						double rz = (double)rb.z - (double)sz - (double)dv.z / (double)ia.z;
+						acc += rx * rx + ry * ry + rz * rz;
+					}
+				}
+				double sres = block_sum(acc, red);
+				if (tid == 0) atomicAdd(&P.resid[1 + it], sres);
+				grid_barrier(P.barrier, bar_target, gridDim.x);
+				double r2 = __ldcg(&P.resid[1 + it]);
+				if (r2 / b2 < P.tol2) break;
+			}
+		}
+	}
+	// x = x_ref + d: the only write to the positions
+	__syncthreads();
+	for (int l = tid; l < d.n_own; l += blockDim.x) {
+		const int node = s_gid[l];
+		const double4 xr = P.x[node];
+		const float4 dv = s_d[l];
+		st_node(&P.x[node], xr.x + (double)dv.x, xr.y + (double)dv.y, xr.z + (double)dv.z);
+	}
+	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
+	if (R.prof && tid == 0) {
+		unsigned long long *q = R.prof + 16 * blockIdx.x;
+		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pp; q[3] = (unsigned long long)(clock64() - t_begin);
+	}
+	if (R.prof && tid == n_bthreads) R.prof[16 * blockIdx.x + 4] = (unsigned long long)pi;
+}
+
+} // namespace admmb200

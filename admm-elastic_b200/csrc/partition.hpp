@@ -28,7 +28,9 @@ struct PartDesc {
 	int cslice_off;                      // into color_slice[] (2 n_colors + 1 entries: per colour first interior
 	                                     // slice, first boundary slice; then the end)
 	int nbr_off, n_nbr;                  // into nbr[]: parts this part exchanges halo values with
-	int pad_;
+	int own_off;                         // number of nodes owned by the parts before this one
+	int hcolor_off;                      // into halo_color[] (n_colors + 1 entries): halo nodes are sorted by colour
+	int pad_[2];
 };
 
 struct ResidentPlan {
@@ -36,29 +38,34 @@ struct ResidentPlan {
 	std::vector<PartDesc> parts;
 	std::vector<uint16_t> col;     // local index: < n_own -> shared-memory x, else halo (gid[col])
 	std::vector<double> val;       // converted to the storage precision at upload
-	std::vector<int> gid, slice_row, color_slice, nbr;
+	std::vector<int> gid, slice_row, color_slice, nbr, halo_color;
 	std::vector<short> slice_node;
 	std::vector<int> part_of;      // node -> part (for tests / diagnostics)
 	size_t max_nbr = 0;
 	size_t max_rows = 0, max_own = 0, max_halo = 0, max_slices = 0, entries = 0, nnz = 0;
 	// dynamic shared memory one CTA needs with `val_bytes`-wide matrix values
-	size_t smem_bytes(int n_colors, int val_bytes) const {
+	// dynamic shared memory one CTA needs.  mode 0: positions of the owned nodes as 3 doubles, matrix
+	// values `val_bytes` wide (mcgs_resident_kernel); mode 1: float4 increments of owned AND halo nodes,
+	// float values (mcgs_resident_f32_kernel).
+	size_t smem_bytes(int n_colors, int val_bytes, int mode = 0) const {
 		size_t worst = 0;
-		for (const PartDesc &d : parts) worst = std::max(worst, layout(d, n_colors, val_bytes, lanes, nullptr));
+		for (const PartDesc &d : parts) worst = std::max(worst, layout(d, n_colors, val_bytes, lanes, mode, nullptr));
 		return worst;
 	}
-	// byte offsets of the shared-memory arrays of one part (the kernel computes the same)
-	static size_t layout(const PartDesc &d, int n_colors, int val_bytes, int lanes, size_t *off /* [7] or null */) {
+	// byte offsets of the shared-memory arrays of one part (the kernels compute the same)
+	static size_t layout(const PartDesc &d, int n_colors, int val_bytes, int lanes, int mode, size_t *off /* [8] or null */) {
 		const int G = 32 / lanes; // nodes per slice
-		size_t o = 0, tmp[7];
+		size_t o = 0, tmp[8];
 		auto take = [&](int i, size_t bytes) { tmp[i] = o; o += (bytes + 15) & ~(size_t)15; };
-		take(0, sizeof(double) * 3 * (size_t)d.n_own);         // xs
-		take(1, (size_t)val_bytes * 32 * (size_t)d.n_rows);    // val
-		take(2, sizeof(uint16_t) * 32 * (size_t)d.n_rows);     // col
-		take(3, sizeof(int) * ((size_t)d.n_own + d.n_halo));   // gid
-		take(4, sizeof(int) * ((size_t)d.n_slices + 1));       // slice_row
-		take(5, sizeof(short) * (size_t)G * d.n_slices);       // slice_node
-		take(6, sizeof(int) * (2 * (size_t)n_colors + 1));     // color_slice
+		if (mode == 0) take(0, sizeof(double) * 3 * (size_t)d.n_own);               // x of owned nodes
+		else take(0, 16 * ((size_t)d.n_own + d.n_halo));                             // float4 increments, owned + halo
+		take(1, (size_t)(mode == 0 ? val_bytes : 4) * 32 * (size_t)d.n_rows);        // val
+		take(2, sizeof(uint16_t) * 32 * (size_t)d.n_rows);                           // col
+		take(3, sizeof(int) * ((size_t)d.n_own + d.n_halo));                         // gid
+		take(4, sizeof(int) * ((size_t)d.n_slices + 1));                             // slice_row
+		take(5, sizeof(short) * (size_t)G * d.n_slices);                             // slice_node
+		take(6, sizeof(int) * (2 * (size_t)n_colors + 1));                           // color_slice
+		take(7, mode == 0 ? 0 : sizeof(int) * ((size_t)n_colors + 1));               // halo_color
 		if (off) std::memcpy(off, tmp, sizeof(tmp));
 		return o;
 	}
@@ -124,6 +131,7 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 			if (cols[q] != i && vals[q] != 0.0 && R.part_of[cols[q]] != R.part_of[i]) { boundary[i] = 1; boundary[cols[q]] = 1; }
 	std::vector<int> local_of(n, -1);
 	R.parts.resize(n_parts);
+	int own_running = 0;
 	for (int p = 0; p < n_parts; ++p) {
 		std::vector<int> &nodes = own[p];
 		// colour-major, long rows first inside a colour (uniform slices -> little ELL padding), ids last
@@ -138,19 +146,35 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 		PartDesc d;
 		std::memset(&d, 0, sizeof(d));
 		d.n_own = (int)nodes.size();
+		d.own_off = own_running;
+		own_running += d.n_own;
 		d.gid_off = (int)R.gid.size();
 		d.slice_off = (int)R.slice_row.size();
 		d.snode_off = (int)R.slice_node.size();
 		d.cslice_off = (int)R.color_slice.size();
 		d.ent_off = (long long)R.col.size();
 		for (int l = 0; l < d.n_own; ++l) { local_of[nodes[l]] = l; R.gid.push_back(nodes[l]); }
-		// halo numbering in order of first use
+		// halo nodes, sorted by colour (then id): after a pass only the halo nodes of that pass's colour
+		// have new values, and they are contiguous
 		std::vector<int> halo;
-		auto local_index = [&](int g) -> int {
-			if (R.part_of[g] == p) return local_of[g];
-			if (local_of[g] < 0) { local_of[g] = d.n_own + (int)halo.size(); halo.push_back(g); }
-			return local_of[g];
-		};
+		for (int l = 0; l < d.n_own; ++l) {
+			const int node = nodes[l];
+			for (int q = rowptr[node]; q < rowptr[node + 1]; ++q) {
+				const int g = cols[q];
+				if (g == node || vals[q] == 0.0 || R.part_of[g] == p || local_of[g] == -2) continue;
+				local_of[g] = -2;
+				halo.push_back(g);
+			}
+		}
+		std::sort(halo.begin(), halo.end(), [&](int a, int b) { return color_of[a] != color_of[b] ? color_of[a] < color_of[b] : a < b; });
+		d.hcolor_off = (int)R.halo_color.size();
+		{
+			size_t h = 0;
+			for (int c = 0; c < n_colors; ++c) { R.halo_color.push_back((int)h); while (h < halo.size() && color_of[halo[h]] == c) ++h; }
+			R.halo_color.push_back((int)halo.size());
+		}
+		for (size_t h = 0; h < halo.size(); ++h) local_of[halo[h]] = d.n_own + (int)h;
+		auto local_index = [&](int g) -> int { return local_of[g]; };
 		int rows = 0, slices = 0;
 		R.slice_row.push_back(0);
 		int k = 0;
