@@ -137,7 +137,10 @@ struct admm_b200_solver {
 	DevBuf<uint16_t> res_col;
 	DevBuf<char> res_val;
 	DevBuf<int> res_gid, res_slice_row, res_color_slice, res_nbr, res_halo_color;
-	DevBuf<float4> res_dglob, res_nodebuf;
+	DevBuf<float4> res_nodebuf;
+	DevBuf<uint2> res_dglob;
+	unsigned int gs_solve_seq = 0;
+	DevBuf<double> res_val64;
 	DevBuf<unsigned long long> res_prof; // ADMM_B200_GS_PROF=1: per-part cycle counters of the last solve
 	DevBuf<unsigned int> res_sync; // part_epoch [8 * n_sms] | sweep_flag [iters] | sweep_arrive [iters]
 	DevBuf<short> res_slice_node;
@@ -335,7 +338,11 @@ void launch_mcgs_resident(S *s)
 		R32.slice_row = s->res_slice_row.p; R32.color_slice = s->res_color_slice.p; R32.slice_node = s->res_slice_node.p; R32.nbr = s->res_nbr.p;
 		R32.halo_color = s->res_halo_color.p;
 		R32.part_epoch = part_epoch; R32.sweep_flag = sweep_flag; R32.sweep_arrive = sweep_arrive; R32.prof = s->res_prof.p;
-		R32.dglob = s->res_dglob.p; R32.nodebuf = s->res_nodebuf.p;
+		R32.dglob = s->res_dglob.p; R32.nodebuf = s->res_nodebuf.p; R32.val64 = s->res_val64.p;
+		s->gs_solve_seq = (s->gs_solve_seq + 1) & 0xFFFFFu;
+		if (s->gs_solve_seq == 0) s->gs_solve_seq = 1;
+		R32.tag_base = s->gs_solve_seq << 12;
+		R32.n_nodes_total = s->n_nodes;
 		args[0] = &R32;
 	}
 	CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
@@ -536,7 +543,11 @@ void build_mcgs_resident(S *s)
 	s->res_slice_node.upload(R.slice_node, s->stream);
 	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);
 	s->res_halo_color.upload(R.halo_color, s->stream);
-	if (val_bytes == 4) { s->res_dglob.alloc(s->n_nodes); s->res_dglob.zero(s->stream); s->res_nodebuf.alloc(2 * (size_t)s->n_nodes); s->res_nodebuf.zero(s->stream); }
+	if (val_bytes == 4) {
+		require((long long)s->gs_iters * s->n_colors < 4094, "resident fp32 MCGS: sweeps x colours must stay below 4094 (12-bit pass tags)");
+		s->res_dglob.alloc(6 * (size_t)s->n_nodes); s->res_dglob.zero(s->stream);
+		s->res_nodebuf.alloc(2 * (size_t)s->n_nodes); s->res_nodebuf.zero(s->stream);
+	}
 	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
 	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
 	if (getenv("ADMM_B200_GS_PROF")) { s->res_prof.alloc(16 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
@@ -545,6 +556,7 @@ void build_mcgs_resident(S *s)
 		if (!R.val.empty()) CK(cudaMemcpyAsync(s->res_val.p, R.val.data(), R.val.size() * 8, cudaMemcpyHostToDevice, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
 	} else {
+		s->res_val64.upload(R.val.empty() ? std::vector<double>(1, 0.0) : R.val, s->stream);
 		std::vector<float> v32(R.val.begin(), R.val.end());
 		s->res_val.alloc(std::max<size_t>(v32.size(), 1) * 4);
 		if (!v32.empty()) CK(cudaMemcpyAsync(s->res_val.p, v32.data(), v32.size() * 4, cudaMemcpyHostToDevice, s->stream));

@@ -25,14 +25,33 @@ struct McgsRes32Params {
 	McgsParams base;
 	const PartDesc *parts;
 	const uint16_t *col;
-	const float *val;
+	const float *val;     // swept in shared memory
+	const double *val64;  // same entries in full precision, streamed once per solve for r0 = b - A x_ref
 	const int *gid, *slice_row, *color_slice, *nbr, *halo_color;
 	const short *slice_node;
 	unsigned int *part_epoch, *sweep_flag, *sweep_arrive;
 	unsigned long long *prof;
-	float4 *dglob;   // [n_nodes]: increments of boundary nodes, published every pass
+	uint2 *dglob;    // [2][n_nodes][3]: published increments of boundary nodes, each component one 64-bit word
+	                 // {float bits, tag}; double-buffered by sweep parity
 	float4 *nodebuf; // [2 * n_nodes] by (own_off + local id): {r0.xyz, pin slot + 1}, {1/a.xyz, -}
+	unsigned int tag_base; // (solve sequence number << 12): tags never repeat across solves
+	int n_nodes_total;
 };
+
+// Halo exchange without flags or fences ("flag in data", as in NCCL's LL protocol): every published
+// component is ONE aligned 64-bit word {value, tag}, tag = tag_base | (pass + 1).  A 64-bit store is
+// single-copy atomic, so a reader that sees the expected tag has the value of exactly that pass; it
+// simply re-reads until then.  There is no back-pressure, so the buffer is double-buffered by sweep
+// parity: a part can only overwrite a word two sweeps later, and to get there it must have received --
+// from every neighbour -- values those neighbours computed after they consumed the word.
+__device__ __forceinline__ void ll_store(uint2 *p, float v, unsigned int tag) {
+	asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ll_load(const uint2 *p) {
+	uint2 v;
+	asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+	return v;
+}
 
 __device__ __forceinline__ float4 ldcg_f4(const float4 *p) { return __ldcg(p); }
 
@@ -109,14 +128,18 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	float4 *nb = R.nodebuf + 2 * (size_t)d.own_off;
 
 	// ---- r0 = b - A x_ref in fp64 (x_ref = P.x, read-only until the very end), and |b|^2 ----
+	// With the EXACT matrix: the rows of L sum to zero (translation invariance), rounding its entries to
+	// fp32 breaks that by 6e-8 |a_ii| per row, which multiplied by |x_ref| ~ metres would be a visible
+	// force; multiplied by the millimetre increment in the sweeps it is not.
 	{
 		double b2 = 0;
+		const double *g_val64 = R.val64 + d.ent_off;
 		for (int sl = warp; sl < d.n_slices; sl += n_warps) {
 			const int l = s_snode[sl * G + grp];
 			double sx = 0, sy = 0, sz = 0;
 			for (int r = s_srow[sl]; r < s_srow[sl + 1]; ++r) {
 				const int c = s_col[r * 32 + lane];
-				const double a = (double)s_val[r * 32 + lane];
+				const double a = __ldg(&g_val64[(size_t)r * 32 + lane]);
 				const double4 xc = ld_node(&P.x[s_gid[c]]);
 				sx += a * xc.x; sy += a * xc.y; sz += a * xc.z;
 			}
@@ -145,6 +168,8 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	const double thresh = check ? 4.0 * P.tol2 * __ldcg(&P.resid[0]) : 0.0;
 
 	double lb = 0;
+	unsigned int pass_tag = 0;   // tag of the pass being computed
+	uint2 *pub = R.dglob;         // buffer of the current sweep parity
 	auto do_slice = [&](int sl, bool to_global, bool last) {
 		const int l = s_snode[sl * G + grp];
 		const bool owner = (sub == 0 && l >= 0);
@@ -179,14 +204,37 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 				}
 			}
 			s_d[l] = dn;
-			if (to_global) R.dglob[s_gid[l]] = dn;
+			if (to_global) {
+				uint2 *w = pub + 3 * (size_t)s_gid[l];
+				ll_store(w, dn.x, pass_tag); ll_store(w + 1, dn.y, pass_tag); ll_store(w + 2, dn.z, pass_tag);
+			}
 		}
 	};
 
-	const int n_bwarps = n_warps / 2, n_iwarps = n_warps - n_bwarps, n_bthreads = 32 * n_bwarps;
+	// Warp roles (see mcgs_resident.cuh), split in proportion to the boundary / interior work of this part.
+	int n_bwarps;
+	{
+		int mb = 0, mi = 0;
+		for (int c = 0; c < C; ++c) { mi = max(mi, s_cslice[2 * c + 1] - s_cslice[2 * c]); mb = max(mb, s_cslice[2 * c + 2] - s_cslice[2 * c + 1]); }
+		n_bwarps = (mb + mi) > 0 ? (n_warps * mb + (mb + mi) / 2) / (mb + mi) : n_warps / 2;
+		n_bwarps = min(max(n_bwarps, 1), n_warps - 1);
+	}
+	const int n_iwarps = n_warps - n_bwarps, n_bthreads = 32 * n_bwarps;
 	const bool bwarp = warp < n_bwarps;
+	const size_t buf_stride = 3 * (size_t)R.n_nodes_total;
+
+	// pulls the halo values of colour `cp` published with tag `tag` in buffer `buf` into shared memory
+	auto refresh = [&](int cp, const uint2 *buf, unsigned int tag, int t0, int nt) {
+		for (int h = s_hcol[cp] + t0; h < s_hcol[cp + 1]; h += nt) {
+			const uint2 *w = buf + 3 * (size_t)s_gid[d.n_own + h];
+			uint2 a, b, c;
+			do { a = ll_load(w); b = ll_load(w + 1); c = ll_load(w + 2); } while (a.y != tag || b.y != tag || c.y != tag);
+			s_d[d.n_own + h] = make_float4(__uint_as_float(a.x), __uint_as_float(b.x), __uint_as_float(c.x), 0.f);
+		}
+	};
+
 	int it = 0;
-	unsigned int epoch = 0;
+	unsigned int pass = 0; // passes done so far
 	long long pw = 0, pc = 0, pp = 0, pi = 0;
 	const long long t_begin = R.prof ? clock64() : 0;
 	for (; it < P.iters; ++it) {
@@ -194,22 +242,16 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 		for (int color = 0; color < C; ++color) {
 			const int s0 = s_cslice[2 * color], s1 = s_cslice[2 * color + 1], s2 = s_cslice[2 * color + 2];
 			const bool last = check && (color == C - 1);
-			long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+			pass_tag = R.tag_base | (pass + 1);
+			pub = R.dglob + (size_t)(it & 1) * buf_stride;
+			long long t0 = 0, t1 = 0, t2 = 0;
 			if (R.prof) t0 = clock64();
 			if (bwarp) {
-				if (epoch > 0) {
-					// wait for the neighbours' previous pass, then pull in what they changed: the halo nodes of
-					// that pass's colour
-					if (tid < d.n_nbr) {
-						for (int i = tid; i < d.n_nbr; i += n_bthreads) {
-							const unsigned int *f = R.part_epoch + 8 * s_nbr[i];
-							while (ld_relaxed_u32(f) < epoch) { }
-						}
-						fence_acq_rel_gpu();
-					}
-					named_sync(1, n_bthreads);
+				if (pass > 0) {
+					// what the neighbours changed in the previous pass: the halo nodes of that pass's colour
 					const int cp = (color + C - 1) % C;
-					for (int h = s_hcol[cp] + tid; h < s_hcol[cp + 1]; h += n_bthreads) s_d[d.n_own + h] = ldcg_f4(&R.dglob[s_gid[d.n_own + h]]);
+					const int it_prev = color > 0 ? it : it - 1;
+					refresh(cp, R.dglob + (size_t)(it_prev & 1) * buf_stride, R.tag_base | pass, tid, n_bthreads);
 					named_sync(1, n_bthreads);
 				}
 				if (R.prof) t1 = clock64();
@@ -220,25 +262,27 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 				if (R.prof) t1 = clock64();
 			}
 			__syncthreads();
-			if (R.prof) t3 = clock64();
-			part_publish(R.part_epoch, ++epoch);
-			if (R.prof && tid == 0) { long long t4 = clock64(); pw += t1 - t0; pc += t2 - t1; pp += t4 - t3; }
+			++pass;
+			if (R.prof && tid == 0) { long long t3 = clock64(); pw += t1 - t0; pc += t2 - t1; pp += t3 - t2; }
 			if (R.prof && tid == n_bthreads) pi += t1 - t0;
 		}
 		if (check) {
-			// see mcgs_resident.cuh: "converged?" decided without a grid barrier in the common case
+			// "converged?" (see mcgs_resident.cuh).  A part whose own rows prove |b - A x|^2 >= 4 tol^2 |b|^2
+			// knows the answer without talking to anyone; it only leaves a note for parts that cannot.
 			double s = block_sum(lb, red);
 			if (tid == 0) {
-				if (s >= thresh) R.sweep_flag[it] = 1u;
-				else if (s > 0.0) atomicAdd(&P.resid_lb[it], s);
-				__threadfence();
-				atomicAdd(&R.sweep_arrive[it], 1u);
 				int decision = -1;
-				while (decision < 0) {
-					if (ld_relaxed_u32(&R.sweep_flag[it]) != 0u) decision = 1;
-					else if (ld_relaxed_u32(&R.sweep_arrive[it]) == gridDim.x) {
-						fence_acq_rel_gpu();
-						decision = (ld_relaxed_u32(&R.sweep_flag[it]) != 0u || __ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
+				if (s >= thresh) { st_relaxed_u32(&R.sweep_flag[it], 1u); atomicAdd(&R.sweep_arrive[it], 1u); decision = 1; }
+				else {
+					if (s > 0.0) atomicAdd(&P.resid_lb[it], s);
+					__threadfence();
+					atomicAdd(&R.sweep_arrive[it], 1u);
+					while (decision < 0) {
+						if (ld_relaxed_u32(&R.sweep_flag[it]) != 0u) decision = 1;
+						else if (ld_relaxed_u32(&R.sweep_arrive[it]) == gridDim.x) {
+							fence_acq_rel_gpu();
+							decision = (ld_relaxed_u32(&R.sweep_flag[it]) != 0u || __ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
+						}
 					}
 				}
 				s_decision = decision;
@@ -248,9 +292,9 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 			__syncthreads();
 			if (!proven_unconverged) {
 				const double b2 = __ldcg(&P.resid[0]);
-				grid_barrier(P.barrier, bar_target, gridDim.x);
-				// exact residual b - A x = r0 - A d (src/NodalMultiColorGS.hpp:136-139): all halo values first
-				for (int h = tid; h < d.n_halo; h += blockDim.x) s_d[d.n_own + h] = ldcg_f4(&R.dglob[s_gid[d.n_own + h]]);
+				// exact residual b - A x = r0 - A d (src/NodalMultiColorGS.hpp:136-139).  Every part takes this
+				// branch; the last colour's halo values are the only ones not pulled in yet.
+				refresh(C - 1, R.dglob + (size_t)(it & 1) * buf_stride, R.tag_base | pass, tid, (int)blockDim.x);
 				__syncthreads();
 				double acc = 0;
 				for (int sl = warp; sl < d.n_slices; sl += n_warps) {
@@ -287,6 +331,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pp; q[3] = (unsigned long long)(clock64() - t_begin);
 	}
 	if (R.prof && tid == n_bthreads) R.prof[16 * blockIdx.x + 4] = (unsigned long long)pi;
+	(void)pw; (void)pc; (void)pp; (void)pi;
 }
 
 } // namespace admmb200

@@ -18,5 +18,5 @@ names=['wait','boundary','publish','total','interior']
 print('colours',ncol,'passes',passes,' cycles per pass (mean over parts | max):', {n:(int(p[:,i].mean()/passes), int(p[:,i].max()/passes)) for i,n in enumerate(names)})
 for nm,o in (('boundary warp0',5),('interior warp0',9)):
     n=p[:,o+3].sum()
-    print(nm,'slices/pass %.2f'%(p[:,o+3].mean()/passes),'cycles per slice: meta %.0f gather %.0f tail %.0f'%(p[:,o].sum()/n,p[:,o+1].sum()/n,p[:,o+2].sum()/n))
+    if n > 0: print(nm,'slices/pass %.2f'%(p[:,o+3].mean()/passes),'cycles per slice: meta %.0f gather %.0f tail %.0f'%(p[:,o].sum()/n,p[:,o+1].sum()/n,p[:,o+2].sum()/n))
 print(sol.device().info())
