@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	__shared__ int s_nbr[192];
 	__shared__ int s_decision;
 	const McgsParams &P = R.base;
+	const long long t_kernel = R.prof ? clock64() : 0;
 	const PartDesc d = R.parts[blockIdx.x];
 	const int tid = threadIdx.x, lane = tid & 31, sub = lane % T, grp = lane / T, warp = tid >> 5, n_warps = blockDim.x >> 5;
 	const int n_loc = d.n_own + d.n_halo, C = P.n_colors;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	if (d.n_rows > 0) mbar_wait(&tma_bar, 0);
 	__syncthreads();
 
+	const long long t_staged = R.prof ? clock64() : 0;
 	unsigned int bar_target = 0;
 	const bool check = P.tol2 > 0.0;
 	const float omega = (float)P.omega, one_m_omega = (float)(1.0 - P.omega), lb_scale = (float)(1.0 / P.omega - 1.0);
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 		}
 	}
 	// x = x_ref + d: the only write to the positions
+	const long long t_loop_end = R.prof ? clock64() : 0;
 	__syncthreads();
 	for (int l = tid; l < d.n_own; l += blockDim.x) {
 		const int node = s_gid[l];
@@ -328,7 +331,8 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
 	if (R.prof && tid == 0) {
 		unsigned long long *q = R.prof + 16 * blockIdx.x;
-		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pp; q[3] = (unsigned long long)(clock64() - t_begin);
+		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pp; q[3] = (unsigned long long)(clock64() - t_kernel);
+		q[13] = (unsigned long long)(t_staged - t_kernel); q[14] = (unsigned long long)(t_begin - t_staged); q[15] = (unsigned long long)(t_loop_end - t_begin);
 	}
 	if (R.prof && tid == n_bthreads) R.prof[16 * blockIdx.x + 4] = (unsigned long long)pi;
 	(void)pw; (void)pc; (void)pp; (void)pi;

@@ -19,4 +19,5 @@ print('colours',ncol,'passes',passes,' cycles per pass (mean over parts | max):'
 for nm,o in (('boundary warp0',5),('interior warp0',9)):
     n=p[:,o+3].sum()
     if n > 0: print(nm,'slices/pass %.2f'%(p[:,o+3].mean()/passes),'cycles per slice: meta %.0f gather %.0f tail %.0f'%(p[:,o].sum()/n,p[:,o+1].sum()/n,p[:,o+2].sum()/n))
+print('kernel phases (cycles, mean over parts): staging %.0f  r0+|b|^2 %.0f  sweeps %.0f  total %.0f'%(p[:,13].mean(),p[:,14].mean(),p[:,15].mean(),p[:,3].mean()))
 print(sol.device().info())
