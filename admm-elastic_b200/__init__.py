@@ -25,6 +25,7 @@ TET_LINEAR, TET_NEOHOOKEAN, TET_STVK, TET_SPLINE_NH, TET_SPLINE_STVK, TET_SPLINE
 LDLT, MCGS, UZAWA = 0, 1, 2
 FP32, FP64 = 0, 1
 COLOR_GREEDY, COLOR_RANDOM, COLOR_USER = 0, 1, 2
+IPC_BYTES = 256
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int_p = ctypes.POINTER(ctypes.c_int)
@@ -265,6 +266,28 @@ class Solver(object):
             if k not in self._opts:
                 raise KeyError(k)
         self._opts.update(kw)
+
+    # --- multi-GPU (one process per GPU) -----------------------------------------------------------
+    def set_rank(self, rank, world):
+        """Call before initialize(): this process is `rank` of `world` (<= 8) on one NVLink box."""
+        _host.admmhost_set_rank(self.h, int(rank), int(world))
+        self._rank, self._world = int(rank), int(world)
+
+    def mgpu_connect(self, all_gather_bytes):
+        """After initialize() on every rank: swaps the CUDA-IPC blobs.  `all_gather_bytes(b) -> [b_0..b_{w-1}]`
+        is the caller's collective (e.g. built on torch.distributed.all_gather_object)."""
+        blob = ctypes.create_string_buffer(IPC_BYTES)
+        self._ck(_host.admmhost_mgpu_export(self.h, blob))
+        blobs = all_gather_bytes(bytes(blob.raw))
+        for r, b in enumerate(blobs):
+            if r != self._rank:
+                self._ck(_host.admmhost_mgpu_import(self.h, r, ctypes.create_string_buffer(b, IPC_BYTES)))
+        self._ck(_host.admmhost_mgpu_ready(self.h))
+
+    def node_owner(self):
+        out = np.zeros(self.dof // 3, dtype=np.int32)
+        n = _host.admmhost_get_node_owner(self.h, _ip(out))
+        return out[:n]
 
     def set_colors(self, colors):
         """colors: list of node lists (colour -> nodes), e.g. read from the reference."""

@@ -146,6 +146,15 @@ struct admm_b200_solver {
 	DevBuf<short> res_slice_node;
 	std::vector<double> h_x0; // rest positions (partitioning)
 	std::string gs_info;
+	// multi-GPU: one handle per rank, peers' buffers mapped through CUDA IPC
+	int rank = 0, world = 1;
+	DevBuf<unsigned int> mg_dest_mask, mg_flags; // flags: [ADMMB200_MAX_RANKS * 8], slot 8*q = epoch of rank q's last barrier
+	uint2 *peer_dglob[ADMMB200_MAX_RANKS] = {nullptr};
+	double4 *peer_x[ADMMB200_MAX_RANKS] = {nullptr};
+	unsigned int *peer_flags[ADMMB200_MAX_RANKS] = {nullptr};
+	std::vector<void *> ipc_opened;
+	bool mg_ready = false;
+	unsigned int mg_epoch = 0;
 
 	// ldlt
 	bool have_ldlt = false;
@@ -168,6 +177,7 @@ struct admm_b200_solver {
 	std::vector<cudaEvent_t> events;
 
 	~admm_b200_solver() {
+		for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
 		for (auto t : tets) delete t;
 		for (auto t : tris) delete t;
 		for (auto e : events) cudaEventDestroy(e);
@@ -343,6 +353,10 @@ void launch_mcgs_resident(S *s)
 		if (s->gs_solve_seq == 0) s->gs_solve_seq = 1;
 		R32.tag_base = s->gs_solve_seq << 12;
 		R32.n_nodes_total = s->n_nodes;
+		R32.part0 = s->rank * s->n_sms; R32.world = s->world; R32.rank = s->rank;
+		R32.dest_mask = s->world > 1 ? s->mg_dest_mask.p : nullptr;
+		for (int q = 0; q < ADMMB200_MAX_RANKS; ++q) { R32.peer_dglob[q] = s->peer_dglob[q]; R32.peer_x[q] = s->peer_x[q]; }
+		if (s->world > 1) { require(s->mg_ready, "multi-GPU solver used before admm_b200_mgpu_ready"); R32.base.tol2 = 0.0; }
 		args[0] = &R32;
 	}
 	CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
@@ -401,10 +415,37 @@ void launch_ldlt(S *s)
 	s->launches++;
 }
 
+// Cross-GPU barrier (one tiny kernel): every rank stores its epoch into every peer's flag array and
+// waits until all peers' epochs have arrived in its own.  Runs after the solve so that the ghost
+// positions the peers pushed at the end of their solve are complete before the next local step.
+struct MgBarrierParams { int world, rank; unsigned int epoch; unsigned int *mine; unsigned int *peer[ADMMB200_MAX_RANKS]; };
+__global__ void mgpu_barrier_kernel(MgBarrierParams B)
+{
+	const int q = threadIdx.x;
+	if (q >= B.world || q == B.rank) return;
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(B.peer[q] + 8 * B.rank), "r"(B.epoch) : "memory");
+	unsigned int seen;
+	do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(B.mine + 8 * q) : "memory"); } while (seen < B.epoch);
+}
+
+void launch_mgpu_barrier(S *s)
+{
+	if (s->world <= 1) return;
+	require(s->mg_ready, "multi-GPU solver used before admm_b200_mgpu_ready");
+	MgBarrierParams B;
+	B.world = s->world; B.rank = s->rank; B.epoch = ++s->mg_epoch; B.mine = s->mg_flags.p;
+	for (int q = 0; q < ADMMB200_MAX_RANKS; ++q) B.peer[q] = s->peer_flags[q];
+	mgpu_barrier_kernel<<<1, 32, 0, s->stream>>>(B);
+	CK(cudaGetLastError());
+	s->launches++;
+}
+
 void launch_global(S *s)
 {
 	if (s->linsolver == ADMM_B200_MCGS) launch_mcgs(s);
 	else launch_ldlt(s); // LDLT, and UzawaCG with an empty constraint matrix (src/UzawaCG.hpp:78-81)
+	launch_mgpu_barrier(s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -498,6 +539,14 @@ void upload_gs_pins(S *s)
 	CK(cudaStreamSynchronize(s->stream));
 }
 
+int plan_default_lanes()
+{
+	const char *envl = getenv("ADMM_B200_GS_RES_LANES");
+	int lanes = envl ? atoi(envl) : 1;
+	if (lanes != 1 && lanes != 2 && lanes != 4) lanes = 1;
+	return lanes;
+}
+
 // Plans the shared-memory-resident variant and uses it when every part fits one SM's shared memory
 // with the chosen value precision; otherwise the streaming kernel (any size) stays in charge.
 // ADMM_B200_GS_KERNEL=stream|resident overrides the choice (resident fails loudly if it does not fit).
@@ -506,13 +555,12 @@ void build_mcgs_resident(S *s)
 	const char *env = getenv("ADMM_B200_GS_KERNEL");
 	const std::string want = env ? env : "auto";
 	s->gs_resident = false;
+	if (s->world > 1) require(s->precision == ADMM_B200_FP32 && want != "stream", "multi-GPU needs the resident fp32 Gauss-Seidel (precision FP32)");
 	if (want == "stream") { s->gs_info = "stream (forced)"; return; }
 	const int val_bytes = s->precision == ADMM_B200_FP64 ? 8 : 4;
 	int max_optin = 0;
 	CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-	const char *envl = getenv("ADMM_B200_GS_RES_LANES");
-	int lanes = envl ? atoi(envl) : 1;
-	if (lanes != 1 && lanes != 2 && lanes != 4) lanes = 1;
+	const int lanes = plan_default_lanes();
 	s->gs_res_lanes = lanes;
 	const void *kern = resident_kernel_ptr(val_bytes == 8, lanes);
 	cudaFuncAttributes fa;
@@ -520,9 +568,9 @@ void build_mcgs_resident(S *s)
 	const size_t budget = (size_t)max_optin - fa.sharedSizeBytes;
 	ResidentPlan R;
 	try {
-		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->n_sms, lanes);
+		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->n_sms * s->world, lanes);
 	} catch (std::exception &e) {
-		if (want == "resident") throw;
+		if (want == "resident" || s->world > 1) throw;
 		s->gs_info = std::string("stream (") + e.what() + ")";
 		return;
 	}
@@ -531,7 +579,7 @@ void build_mcgs_resident(S *s)
 	snprintf(buf, sizeof(buf), "%d lane(s)/node, %zu B shared memory per part needed (max own %zu, halo %zu, rows %zu, neighbours %zu; ELL fill %.3f), budget %zu B", lanes, need, R.max_own, R.max_halo, R.max_rows,
 		R.max_nbr, R.entries ? (double)R.nnz / (double)R.entries : 1.0, budget);
 	if (need > budget) {
-		if (want == "resident") throw std::runtime_error(std::string("resident MCGS does not fit: ") + buf);
+		if (want == "resident" || s->world > 1) throw std::runtime_error(std::string("resident MCGS does not fit: ") + buf);
 		s->gs_info = std::string("stream: ") + buf;
 		return;
 	}
@@ -543,6 +591,10 @@ void build_mcgs_resident(S *s)
 	s->res_slice_node.upload(R.slice_node, s->stream);
 	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);
 	s->res_halo_color.upload(R.halo_color, s->stream);
+	if (s->world > 1) {
+		s->mg_dest_mask.upload(dest_masks(R, s->n_nodes, s->n_sms, s->rank), s->stream);
+		s->mg_flags.alloc(8 * ADMMB200_MAX_RANKS); s->mg_flags.zero(s->stream);
+	}
 	if (val_bytes == 4) {
 		require((long long)s->gs_iters * s->n_colors < 4094, "resident fp32 MCGS: sweeps x colours must stay below 4094 (12-bit pass tags)");
 		s->res_dglob.alloc(6 * (size_t)s->n_nodes); s->res_dglob.zero(s->stream);
@@ -1073,6 +1125,94 @@ int admm_b200_set_ldlt(admm_b200_solver *s, int n, const int *perm, const int *L
 		for (int i = 0; i < n; ++i) require(D[i] != 0.0, "set_ldlt: zero pivot");
 		s->have_ldlt = true;
 	});
+}
+
+int admm_b200_set_rank(admm_b200_solver *s, int rank, int world)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_rank after finalize");
+		require(world >= 1 && world <= ADMMB200_MAX_RANKS && rank >= 0 && rank < world, "set_rank: rank/world out of range (at most 8 ranks)");
+		s->rank = rank; s->world = world;
+	});
+}
+
+int admm_b200_device_sms(const admm_b200_solver *s) { return s ? s->n_sms : 0; }
+
+namespace {
+struct IpcBlob { cudaIpcMemHandle_t x, dglob, flags; int rank, n_nodes; };
+static_assert(sizeof(IpcBlob) <= ADMM_B200_IPC_BYTES, "IPC blob too large");
+}
+
+int admm_b200_mgpu_export(admm_b200_solver *s, void *blob)
+{
+	return guard(s, [&]() {
+		require(s->finalized && s->world > 1 && blob, "mgpu_export: needs a finalized multi-rank solver");
+		require(s->gs_resident && s->res_dglob.p && s->mg_flags.p, "mgpu_export: the resident fp32 Gauss-Seidel is not active");
+		IpcBlob b;
+		std::memset(&b, 0, sizeof(b));
+		CK(cudaIpcGetMemHandle(&b.x, s->cx.p));
+		CK(cudaIpcGetMemHandle(&b.dglob, s->res_dglob.p));
+		CK(cudaIpcGetMemHandle(&b.flags, s->mg_flags.p));
+		b.rank = s->rank; b.n_nodes = s->n_nodes;
+		std::memset(blob, 0, ADMM_B200_IPC_BYTES);
+		std::memcpy(blob, &b, sizeof(b));
+	});
+}
+
+int admm_b200_mgpu_import(admm_b200_solver *s, int peer_rank, const void *blob)
+{
+	return guard(s, [&]() {
+		require(s->finalized && s->world > 1 && blob, "mgpu_import: needs a finalized multi-rank solver");
+		require(peer_rank >= 0 && peer_rank < s->world, "mgpu_import: peer rank out of range");
+		if (peer_rank == s->rank) return;
+		IpcBlob b;
+		std::memcpy(&b, blob, sizeof(b));
+		require(b.rank == peer_rank && b.n_nodes == s->n_nodes, "mgpu_import: blob does not belong to that rank / mesh");
+		void *px = nullptr, *pd = nullptr, *pf = nullptr;
+		CK(cudaIpcOpenMemHandle(&px, b.x, cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(px);
+		CK(cudaIpcOpenMemHandle(&pd, b.dglob, cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pd);
+		CK(cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pf);
+		s->peer_x[peer_rank] = (double4 *)px; s->peer_dglob[peer_rank] = (uint2 *)pd; s->peer_flags[peer_rank] = (unsigned int *)pf;
+	});
+}
+
+int admm_b200_mgpu_ready(admm_b200_solver *s)
+{
+	return guard(s, [&]() {
+		require(s->finalized && s->world > 1, "mgpu_ready: needs a finalized multi-rank solver");
+		for (int q = 0; q < s->world; ++q) if (q != s->rank) require(s->peer_x[q] && s->peer_dglob[q] && s->peer_flags[q], "mgpu_ready: a peer has not been imported");
+		s->mg_ready = true;
+	});
+}
+
+// Host-only: node -> part of the resident plan (csrc/partition.hpp) for n_parts parts.  With n_parts =
+// world * admm_b200_device_sms(), part / sms is the rank that owns the node.
+int admm_b200_plan_parts(int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, int n_parts, int *part_of)
+{
+	try {
+		if (n <= 0 || !rowptr || !cols || !vals || !pos3 || !part_of || n_parts <= 0) throw std::runtime_error("plan_parts: bad arguments");
+		// EXACTLY the partition plan_resident computes at finalize: same code, same lane count
+		std::vector<int> part = plan_partition(n, rowptr, cols, vals, pos3, n_parts, plan_default_lanes());
+		std::copy(part.begin(), part.end(), part_of);
+		return 0;
+	} catch (std::exception &e) { g_create_error = e.what(); return 1; }
+}
+
+// Host-only: what rank `rank` of `world` would exchange.  mask_out[g] = ranks (bit q) that read node g, for
+// nodes this rank owns; ghost_out[g] = 1 for nodes this rank reads from another rank; owner_out[g] = rank.
+int admm_b200_mgpu_plan_check(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int sms, int world, int rank, unsigned int *mask_out, int *ghost_out, int *owner_out)
+{
+	try {
+		ResidentPlan R = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, sms * world, plan_default_lanes());
+		std::vector<unsigned int> m = dest_masks(R, n, sms, rank);
+		for (int i = 0; i < n; ++i) { mask_out[i] = m[i]; ghost_out[i] = 0; owner_out[i] = R.part_of[i] / sms; }
+		for (int p = rank * sms; p < (rank + 1) * sms; ++p) {
+			const PartDesc &d = R.parts[p];
+			for (int h = 0; h < d.n_halo; ++h) { int g = R.gid[d.gid_off + d.n_own + h]; if (R.part_of[g] / sms != rank) ghost_out[g] = 1; }
+		}
+		return 0;
+	} catch (std::exception &e) { g_create_error = e.what(); return 1; }
 }
 
 int admm_b200_set_debug(admm_b200_solver *s, int store_z)

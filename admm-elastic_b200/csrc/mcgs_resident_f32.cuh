@@ -21,6 +21,8 @@
 
 namespace admmb200 {
 
+#define ADMMB200_MAX_RANKS 8
+
 struct McgsRes32Params {
 	McgsParams base;
 	const PartDesc *parts;
@@ -36,6 +38,13 @@ struct McgsRes32Params {
 	float4 *nodebuf; // [2 * n_nodes] by (own_off + local id): {r0.xyz, pin slot + 1}, {1/a.xyz, -}
 	unsigned int tag_base; // (solve sequence number << 12): tags never repeat across solves
 	int n_nodes_total;
+	// multi-GPU (world > 1): this rank runs parts [part0, part0 + gridDim.x) of a plan that spans all ranks.
+	// Boundary values are also pushed into the peers that read them (stores over NVLink into their dglob /
+	// x arrays, mapped through CUDA IPC); nothing is ever READ from a peer, so spinning stays local.
+	int part0, world, rank;
+	const unsigned int *dest_mask; // [n_nodes] ranks (bit q) that read this node as halo; NULL when world == 1
+	uint2 *peer_dglob[ADMMB200_MAX_RANKS];
+	double4 *peer_x[ADMMB200_MAX_RANKS];
 };
 
 // Halo exchange without flags or fences ("flag in data", as in NCCL's LL protocol): every published
@@ -46,6 +55,9 @@ struct McgsRes32Params {
 // from every neighbour -- values those neighbours computed after they consumed the word.
 __device__ __forceinline__ void ll_store(uint2 *p, float v, unsigned int tag) {
 	asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ll_store_sys(uint2 *p, float v, unsigned int tag) { // into a peer GPU's memory
+	asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
 __device__ __forceinline__ uint2 ll_load(const uint2 *p) {
 	uint2 v;
@@ -86,7 +98,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	__shared__ int s_decision;
 	const McgsParams &P = R.base;
 	const long long t_kernel = R.prof ? clock64() : 0;
-	const PartDesc d = R.parts[blockIdx.x];
+	const PartDesc d = R.parts[R.part0 + blockIdx.x];
 	const int tid = threadIdx.x, lane = tid & 31, sub = lane % T, grp = lane / T, warp = tid >> 5, n_warps = blockDim.x >> 5;
 	const int n_loc = d.n_own + d.n_halo, C = P.n_colors;
 
@@ -157,7 +169,8 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 				const double a0 = __ldg(&P.diag[3 * node]), a1 = __ldg(&P.diag[3 * node + 1]), a2 = __ldg(&P.diag[3 * node + 2]);
 				const int ps = P.has_pins ? __ldg(&P.pin_slot[node]) : -1;
 				nb[2 * l] = make_float4((float)(bi.x - sx - a0 * xi.x), (float)(bi.y - sy - a1 * xi.y), (float)(bi.z - sz - a2 * xi.z), __int_as_float(ps + 1));
-				nb[2 * l + 1] = make_float4((float)(1.0 / a0), (float)(1.0 / a1), (float)(1.0 / a2), 0.f);
+				const unsigned int dm = R.dest_mask ? __ldg(&R.dest_mask[node]) : 0u;
+				nb[2 * l + 1] = make_float4((float)(1.0 / a0), (float)(1.0 / a1), (float)(1.0 / a2), __uint_as_float(dm));
 				b2 += bi.x * bi.x + bi.y * bi.y + bi.z * bi.z;
 			}
 		}
@@ -171,7 +184,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 
 	double lb = 0;
 	unsigned int pass_tag = 0;   // tag of the pass being computed
-	uint2 *pub = R.dglob;         // buffer of the current sweep parity
+	size_t pub_off = 0;           // offset of the current sweep parity's buffer in dglob
 	auto do_slice = [&](int sl, bool to_global, bool last) {
 		const int l = s_snode[sl * G + grp];
 		const bool owner = (sub == 0 && l >= 0);
@@ -207,8 +220,15 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 			}
 			s_d[l] = dn;
 			if (to_global) {
-				uint2 *w = pub + 3 * (size_t)s_gid[l];
+				const size_t at = pub_off + 3 * (size_t)s_gid[l];
+				uint2 *w = R.dglob + at;
 				ll_store(w, dn.x, pass_tag); ll_store(w + 1, dn.y, pass_tag); ll_store(w + 2, dn.z, pass_tag);
+				unsigned int dm = __float_as_uint(ia.w);
+				while (dm) { // peers that read this node
+					const int q = __ffs(dm) - 1; dm &= dm - 1;
+					uint2 *wq = R.peer_dglob[q] + at;
+					ll_store_sys(wq, dn.x, pass_tag); ll_store_sys(wq + 1, dn.y, pass_tag); ll_store_sys(wq + 2, dn.z, pass_tag);
+				}
 			}
 		}
 	};
@@ -245,7 +265,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 			const int s0 = s_cslice[2 * color], s1 = s_cslice[2 * color + 1], s2 = s_cslice[2 * color + 2];
 			const bool last = check && (color == C - 1);
 			pass_tag = R.tag_base | (pass + 1);
-			pub = R.dglob + (size_t)(it & 1) * buf_stride;
+			pub_off = (size_t)(it & 1) * buf_stride;
 			long long t0 = 0, t1 = 0, t2 = 0;
 			if (R.prof) t0 = clock64();
 			if (bwarp) {
@@ -326,7 +346,12 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 		const int node = s_gid[l];
 		const double4 xr = P.x[node];
 		const float4 dv = s_d[l];
-		st_node(&P.x[node], xr.x + (double)dv.x, xr.y + (double)dv.y, xr.z + (double)dv.z);
+		const double nx0 = xr.x + (double)dv.x, nx1 = xr.y + (double)dv.y, nx2 = xr.z + (double)dv.z;
+		st_node(&P.x[node], nx0, nx1, nx2);
+		if (R.world > 1) { // ghost copies on the peers (their next local step and r0 read them)
+			unsigned int dm = __float_as_uint(nb[2 * l + 1].w);
+			while (dm) { const int q = __ffs(dm) - 1; dm &= dm - 1; st_node(&R.peer_x[q][node], nx0, nx1, nx2); }
+		}
 	}
 	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
 	if (R.prof && tid == 0) {

@@ -99,6 +99,22 @@ inline void rcb(std::vector<int> &ids, int lo, int hi, int k, int part0, const d
 }
 } // namespace detail
 
+// node -> part: recursive coordinate bisection balanced by padded row length (+ the node's own update)
+inline std::vector<int> plan_partition(int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, int n_parts, int lanes)
+{
+	const int T = lanes;
+	std::vector<double> w(n);
+	for (int i = 0; i < n; ++i) {
+		int len = 0;
+		for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) if (cols[q] != i && vals[q] != 0.0) ++len;
+		w[i] = (double)((len + T - 1) / T * T) + 2.0;
+	}
+	std::vector<int> part_of(n, 0), ids(n);
+	std::iota(ids.begin(), ids.end(), 0);
+	detail::rcb(ids, 0, n, n_parts, 0, pos3, w, part_of);
+	return part_of;
+}
+
 // rowptr/cols/vals: scalar matrix L (both triangles); color_of_list: colour -> node lists (offsets, nodes)
 inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off,
 	const int *color_nodes, const double *pos3, int n_parts, int lanes = 4)
@@ -109,17 +125,12 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 	std::vector<int> color_of(n, -1);
 	for (int c = 0; c < n_colors; ++c) for (int k = color_off[c]; k < color_off[c + 1]; ++k) color_of[color_nodes[k]] = c;
 	std::vector<int> rowlen(n, 0);
-	std::vector<double> w(n);
 	for (int i = 0; i < n; ++i) {
 		int len = 0;
 		for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) if (cols[q] != i && vals[q] != 0.0) ++len;
 		rowlen[i] = len;
-		w[i] = (double)((len + T - 1) / T * T) + 2.0; // padded row + the node's own update
 	}
-	R.part_of.assign(n, 0);
-	std::vector<int> ids(n);
-	std::iota(ids.begin(), ids.end(), 0);
-	detail::rcb(ids, 0, n, n_parts, 0, pos3, w, R.part_of);
+	R.part_of = plan_partition(n, rowptr, cols, vals, pos3, n_parts, lanes);
 
 	std::vector<std::vector<int>> own(n_parts);
 	for (int i = 0; i < n; ++i) own[R.part_of[i]].push_back(i);
@@ -246,6 +257,24 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 	}
 	R.entries = R.col.size();
 	return R;
+}
+
+// Multi-GPU: parts [r * parts_per_rank, (r+1) * parts_per_rank) live on rank r.  For every node owned by
+// `rank`, the set of OTHER ranks that read it as halo (bit q = rank q).  The pattern is symmetric, so this
+// is also the set of ranks whose values this rank reads next to that node.
+inline std::vector<unsigned int> dest_masks(const ResidentPlan &R, int n_nodes, int parts_per_rank, int rank)
+{
+	std::vector<unsigned int> mask((size_t)n_nodes, 0u);
+	for (int p = 0; p < R.n_parts; ++p) {
+		const int q = p / parts_per_rank;
+		if (q == rank) continue;
+		const PartDesc &d = R.parts[p];
+		for (int h = 0; h < d.n_halo; ++h) {
+			const int g = R.gid[d.gid_off + d.n_own + h];
+			if (R.part_of[g] / parts_per_rank == rank) mask[g] |= 1u << q;
+		}
+	}
+	return mask;
 }
 
 } // namespace admmb200

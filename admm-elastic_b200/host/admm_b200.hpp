@@ -317,6 +317,10 @@ public:
 		bool keep_z = false;             // keep z on the device for debugging
 		bool timers = true;              // fill RuntimeData from CUDA events (synchronises every step)
 		void *stream = nullptr;          // cudaStream_t to run on (NULL: the solver's own)
+		// multi-GPU: this process is rank `rank` of `world` (one process per GPU, <= 8).  Every rank builds the
+		// SAME scene; initialize() keeps the elements that touch a node this rank owns.  After initialize()
+		// the ranks swap mgpu_export() blobs and feed them to mgpu_import() (see include/admm_b200.h).
+		int rank = 0, world = 1;
 	} device_options;
 
 	Solver() : initialized(false), handle(nullptr) {}
@@ -349,6 +353,11 @@ public:
 	void sync_state();
 	void upload_state();
 	admm_b200_solver *device_handle() { return handle; }
+	// multi-GPU plumbing (device_options.world > 1)
+	void mgpu_export(void *blob) { check(admm_b200_mgpu_export(handle, blob), "mgpu_export"); }
+	void mgpu_import(int peer_rank, const void *blob) { check(admm_b200_mgpu_import(handle, peer_rank, blob), "mgpu_import"); }
+	void mgpu_ready() { check(admm_b200_mgpu_ready(handle), "mgpu_ready"); }
+	const std::vector<int> &node_owner() const { return m_node_owner; } // rank owning each node (empty when world == 1)
 	const sparse::Csr &system_matrix() const { return scalarL; }
 	const std::vector<std::vector<int>> &colors() const { return m_colors; }
 	int n_reduction_rows() const { return n_D_rows; }
@@ -366,6 +375,7 @@ protected:
 	std::vector<std::vector<int>> m_colors;
 	int n_D_rows = 0;
 	bool state_on_device_newer = false;
+	std::vector<int> m_node_owner;
 
 	bool host_pinned = false;
 	void release_device() {
@@ -520,11 +530,41 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 		}
 	}
 	for (int i = 0; i < n_nodes; ++i) entries.push_back({i, i, 0.0}); // every node gets a diagonal entry
-	for (auto &g : tgroups) check(admm_b200_add_tets(handle, (int)g.w.size(), g.idx.data(), g.dminv.data(), g.w.data(), g.model, g.mu, g.lambda, g.kappa, g.row.data()), "add_tets");
-	for (auto &g : rgroups) check(admm_b200_add_tris(handle, (int)g.w.size(), g.idx.data(), g.rest.data(), g.w.data(), g.lmin, g.lmax, g.row.data()), "add_tris");
-	if (!p_idx.empty()) check(admm_b200_add_pins(handle, (int)p_idx.size(), p_idx.data(), p_pos.data(), p_w.data(), p_row.data()), "add_pins");
 	scalarL = sparse::from_entries(n_nodes, entries);
 	entries.clear(); entries.shrink_to_fit();
+
+	// Multi-GPU: colour and partition the GLOBAL matrix (identically on every rank), then keep only the
+	// elements that touch a node this rank owns; elements on a cut are computed by both sides.
+	m_node_owner.clear();
+	const int world = device_options.world, rank = device_options.rank;
+	if (world > 1) {
+		if (m_settings.linsolver != 1) throw std::runtime_error("**admm_b200::Solver Error: multi-GPU needs the NodalMultiColorGS solver (-ls 1)");
+		if (!rgroups.empty() || !p_idx.empty()) throw std::runtime_error("**admm_b200::Solver Error: multi-GPU supports tet meshes only");
+		check(admm_b200_set_rank(handle, rank, world), "set_rank");
+		const int sms = admm_b200_device_sms(handle);
+		std::vector<int> part(n_nodes);
+		if (admm_b200_plan_parts(n_nodes, scalarL.rowptr.data(), scalarL.cols.data(), scalarL.vals.data(), m_x.data(), world * sms, part.data()))
+			throw std::runtime_error(std::string("**admm_b200 plan_parts: ") + admm_b200_last_error(nullptr));
+		m_node_owner.resize(n_nodes);
+		for (int i = 0; i < n_nodes; ++i) m_node_owner[i] = part[i] / sms;
+		for (auto &g : tgroups) {
+			size_t keep = 0;
+			const size_t n_e = g.w.size();
+			for (size_t e = 0; e < n_e; ++e) {
+				bool mine = false;
+				for (int c = 0; c < 4; ++c) mine = mine || m_node_owner[g.idx[4 * e + c]] == rank;
+				if (!mine) continue;
+				for (int c = 0; c < 4; ++c) g.idx[4 * keep + c] = g.idx[4 * e + c];
+				for (int k = 0; k < 9; ++k) g.dminv[9 * keep + k] = g.dminv[9 * e + k];
+				g.w[keep] = g.w[e]; g.row[keep] = g.row[e];
+				++keep;
+			}
+			g.idx.resize(4 * keep); g.dminv.resize(9 * keep); g.w.resize(keep); g.row.resize(keep);
+		}
+	}
+	for (auto &g : tgroups) if (!g.w.empty()) check(admm_b200_add_tets(handle, (int)g.w.size(), g.idx.data(), g.dminv.data(), g.w.data(), g.model, g.mu, g.lambda, g.kappa, g.row.data()), "add_tets");
+	for (auto &g : rgroups) check(admm_b200_add_tris(handle, (int)g.w.size(), g.idx.data(), g.rest.data(), g.w.data(), g.lmin, g.lmax, g.row.data()), "add_tris");
+	if (!p_idx.empty()) check(admm_b200_add_pins(handle, (int)p_idx.size(), p_idx.data(), p_pos.data(), p_w.data(), p_row.data()), "add_pins");
 
 	for (auto &o : passive_objs) { double p[4]; o->params(p); check(admm_b200_add_obstacle(handle, o->kind(), p), "add_obstacle"); }
 

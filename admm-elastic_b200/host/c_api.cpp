@@ -83,6 +83,20 @@ int admmhost_set_options(void *h_, int device, int precision, int gs_max_iters, 
 	return 0;
 }
 
+int admmhost_set_rank(void *h_, int rank, int world) {
+	Host *h = (Host *)h_;
+	h->solver.device_options.rank = rank; h->solver.device_options.world = world;
+	return 0;
+}
+int admmhost_mgpu_export(void *h_, void *blob) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.mgpu_export(blob); }); }
+int admmhost_mgpu_import(void *h_, int peer, const void *blob) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.mgpu_import(peer, blob); }); }
+int admmhost_mgpu_ready(void *h_) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.mgpu_ready(); }); }
+int admmhost_get_node_owner(void *h_, int *out) {
+	const std::vector<int> &o = ((Host *)h_)->solver.node_owner();
+	for (size_t i = 0; i < o.size(); ++i) out[i] = o[i];
+	return (int)o.size();
+}
+
 int admmhost_set_colors(void *h_, int n_colors, const int *offsets, const int *nodes) {
 	Host *h = (Host *)h_;
 	h->solver.user_colors.clear();

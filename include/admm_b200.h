@@ -179,6 +179,27 @@ int admm_b200_time_kernels( admm_b200_solver *s, int reps, double *out_ms );
 /* Counts of kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long admm_b200_launch_count( const admm_b200_solver *s );
 
+/* ---- multi-GPU: one handle per rank (process), at most 8 ranks on one NVLink box ----------------
+ * Every rank is handed the SAME nodes, system matrix, colours and pins, but only the elements that touch
+ * a node it owns (node -> part from admm_b200_plan_parts with n_parts = world * admm_b200_device_sms();
+ * owner rank = part / sms).  Elements on a cut are therefore computed by both neighbours (a few per
+ * cent), which makes the right-hand side assembly local.  The one exchange of the path -- neighbour
+ * values inside the Gauss-Seidel sweeps and the solved positions of cut nodes -- is done by the solve
+ * kernel itself with stores into the peers' memory (CUDA IPC mappings of their buffers); the 256-byte
+ * blobs are moved between the processes by the caller (e.g. torch.distributed.all_gather).
+ * Restrictions: NodalMultiColorGS, precision FP32, the reference's convergence test is off. */
+#define ADMM_B200_IPC_BYTES 256
+int admm_b200_set_rank( admm_b200_solver *s, int rank, int world );                /* before finalize */
+int admm_b200_device_sms( const admm_b200_solver *s );
+int admm_b200_plan_parts( int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, int n_parts, int *part_of );
+int admm_b200_mgpu_export( admm_b200_solver *s, void *blob );                      /* after finalize */
+int admm_b200_mgpu_import( admm_b200_solver *s, int peer_rank, const void *blob );
+int admm_b200_mgpu_ready( admm_b200_solver *s );
+/* Host-only (tests): what rank `rank` would exchange -- per node the ranks that read it (owned nodes), a
+ * ghost flag (nodes read from another rank) and the owning rank. */
+int admm_b200_mgpu_plan_check( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int sms, int world, int rank, unsigned int *mask_out, int *ghost_out, int *owner_out );
+
 /* Host-only self check of the shared-memory-resident Gauss-Seidel plan (no device needed): see
  * csrc/partition.hpp.  Returns 0 when the plan covers every node exactly once and reproduces
  * L_offdiag * x; the message of a failure is available from admm_b200_last_error(NULL). */
