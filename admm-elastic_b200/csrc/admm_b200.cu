@@ -60,6 +60,7 @@ struct TetBatchH {
 	size_t slot_base = 0;
 	DevBuf<int4> d_idx;
 	DevBuf<char> d_dminv, d_wdt2, d_u, d_z; // element precision, raw bytes
+	DevBuf<int> d_defer;                    // [1 + n]: counter, then the queue of degenerate elements
 };
 struct TriBatchH {
 	int n = 0, n_pad = 0;
@@ -228,12 +229,23 @@ template <typename E, int MODEL> void launch_tet_model(S *s, TetBatchH *t)
 	tb.z = (E *)t->d_z.p;
 	tb.f = (typename Vec4<E>::type *)s->f.p + t->slot_base;
 	tb.mat = Material<E>::make(t->mu, t->lambda, t->kappa);
+	tb.defer_count = t->d_defer.p; tb.defer_list = t->d_defer.p + 1;
 	const int threads = 128;
 	int blocks = (t->n + threads - 1) / threads;
-	if (s->store_z && t->d_z.p) tet_local_kernel<E, MODEL, true><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	const bool sz = s->store_z && t->d_z.p;
+	if (MODEL != TET_LINEAR) CK(cudaMemsetAsync(t->d_defer.p, 0, sizeof(int), s->stream));
+	if (sz) tet_local_kernel<E, MODEL, true><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else tet_local_kernel<E, MODEL, false><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	CK(cudaGetLastError());
 	s->launches++;
+	if (MODEL != TET_LINEAR) {
+		// degenerate elements queued by the kernel above (usually none)
+		const int dblocks = std::min(blocks, 2 * s->n_sms);
+		if (sz) tet_local_deferred_kernel<E, MODEL, true><<<dblocks, threads, 0, s->stream>>>(tb, s->cx.p);
+		else tet_local_deferred_kernel<E, MODEL, false><<<dblocks, threads, 0, s->stream>>>(tb, s->cx.p);
+		CK(cudaGetLastError());
+		s->launches++;
+	}
 }
 
 template <typename E> void launch_tet(S *s, TetBatchH *t)
@@ -490,6 +502,7 @@ template <typename E> void upload_elements(S *s)
 		upload_soa<E>(t->d_wdt2, w2, t->n, t->n_pad, 1, s->stream);
 		t->d_u.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_u.zero(s->stream);
 		if (s->store_z) { t->d_z.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_z.zero(s->stream); }
+		t->d_defer.alloc((size_t)t->n + 1); t->d_defer.zero(s->stream);
 	}
 	for (auto t : s->tris) {
 		t->n_pad = pad32(t->n);
@@ -859,17 +872,22 @@ template <typename E> void prox_tets_impl(S *s, int model, double mu, double lam
 	DevBuf<E> d; d.upload(tmp, s->stream);
 	Material<E> mat = Material<E>::make(mu, lambda, kappa);
 	int threads = 128, blocks = (n + threads - 1) / threads;
+	DevBuf<int> defer; defer.alloc((size_t)n + 1); defer.zero(s->stream);
+#define ADMMB200_PROX_ONLY(M) \
+	tet_prox_only_kernel<E, M><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat, defer.p, defer.p + 1); \
+	if (M != TET_LINEAR) tet_prox_only_deferred_kernel<E, M><<<std::min(blocks, 2 * s->n_sms), threads, 0, s->stream>>>(n_pad, d.p, mat, defer.p, defer.p + 1);
 	switch (model) {
-	case TET_LINEAR: tet_prox_only_kernel<E, TET_LINEAR><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
-	case TET_NEOHOOKEAN: tet_prox_only_kernel<E, TET_NEOHOOKEAN><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
-	case TET_STVK: tet_prox_only_kernel<E, TET_STVK><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
-	case TET_SPLINE_NH: tet_prox_only_kernel<E, TET_SPLINE_NH><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
-	case TET_SPLINE_STVK: tet_prox_only_kernel<E, TET_SPLINE_STVK><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
-	case TET_SPLINE_COROT: tet_prox_only_kernel<E, TET_SPLINE_COROT><<<blocks, threads, 0, s->stream>>>(n, n_pad, d.p, mat); break;
+	case TET_LINEAR: ADMMB200_PROX_ONLY(TET_LINEAR) break;
+	case TET_NEOHOOKEAN: ADMMB200_PROX_ONLY(TET_NEOHOOKEAN) break;
+	case TET_STVK: ADMMB200_PROX_ONLY(TET_STVK) break;
+	case TET_SPLINE_NH: ADMMB200_PROX_ONLY(TET_SPLINE_NH) break;
+	case TET_SPLINE_STVK: ADMMB200_PROX_ONLY(TET_SPLINE_STVK) break;
+	case TET_SPLINE_COROT: ADMMB200_PROX_ONLY(TET_SPLINE_COROT) break;
 	default: throw std::runtime_error("unknown tet model");
 	}
+#undef ADMMB200_PROX_ONLY
 	CK(cudaGetLastError());
-	s->launches++;
+	s->launches += 2;
 	CK(cudaMemcpyAsync(tmp.data(), d.p, tmp.size() * sizeof(E), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	for (int e = 0; e < n; ++e) for (int k = 0; k < 9; ++k) z_out[(size_t)9 * e + k] = double(tmp[(size_t)k * n_pad + e]);

@@ -84,13 +84,15 @@ struct TetBatch {
 	E *z;                     // [9][n_pad] or NULL
 	typename Vec4<E>::type *f; // [4n]
 	Material<E> mat;
+	int *defer_count;         // queue of degenerate elements (see prox.cuh, PROX_FAST / PROX_REFERENCE)
+	int *defer_list;          // [n]
 };
 
-template <typename E, int MODEL, bool STORE_Z>
-__global__ void __launch_bounds__(128, 4) tet_local_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
+// One element of the local step.  MODE = PROX_FAST: the hot kernel; a degenerate element is queued and
+// left untouched.  MODE = PROX_REFERENCE: the queue's consumer redoes such an element from scratch.
+template <typename E, int MODEL, bool STORE_Z, int MODE>
+__device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4 *__restrict__ cx, int e)
 {
-	int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= tb.n) return;
 	const int np = tb.n_pad;
 	int4 id = __ldg(&tb.idx[e]);
 	double4 p0 = ld_node(&cx[id.x]), p1 = ld_node(&cx[id.y]), p2 = ld_node(&cx[id.z]), p3 = ld_node(&cx[id.w]);
@@ -110,7 +112,10 @@ __global__ void __launch_bounds__(128, 4) tet_local_kernel(TetBatch<E> tb, const
 			F[3 * r + j] = ds[j] * bi[r] + ds[3 + j] * bi[3 + r] + ds[6 + j] * bi[6 + r];
 			z[3 * r + j] = F[3 * r + j] + u[3 * r + j];
 		}
-	prox_tet<E, MODEL>(tb.mat, z);
+	if (prox_tet_mode<E, MODEL, MODE>(tb.mat, z)) {
+		tb.defer_list[atomicAdd(tb.defer_count, 1)] = e; // MODE == PROX_FAST only
+		return;
+	}
 	// u += Dx - z ; y = z - u_new
 	E y[9];
 #pragma unroll
@@ -136,18 +141,49 @@ __global__ void __launch_bounds__(128, 4) tet_local_kernel(TetBatch<E> tb, const
 	f[3] = Vec4<E>::make(f3[0], f3[1], f3[2]);
 }
 
+template <typename E, int MODEL, bool STORE_Z>
+__global__ void __launch_bounds__(128) tet_local_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= tb.n) return;
+	tet_element<E, MODEL, STORE_Z, PROX_FAST>(tb, cx, e);
+}
+
+// Consumer of the queue of degenerate elements (usually empty: the launch costs a few microseconds).
+template <typename E, int MODEL, bool STORE_Z>
+__global__ void __launch_bounds__(128) tet_local_deferred_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
+{
+	const int count = *tb.defer_count;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
+		tet_element<E, MODEL, STORE_Z, PROX_REFERENCE>(tb, cx, tb.defer_list[k]);
+}
+
 // prox alone on raw deformation gradients (parity tests / micro-benchmarks): zio is [9][n_pad] SoA
 template <typename E, int MODEL>
-__global__ void __launch_bounds__(128) tet_prox_only_kernel(int n, int n_pad, E *zio, Material<E> mat)
+__global__ void __launch_bounds__(128) tet_prox_only_kernel(int n, int n_pad, E *zio, Material<E> mat, int *defer_count, int *defer_list)
 {
 	int e = blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= n) return;
 	E z[9];
 #pragma unroll
 	for (int k = 0; k < 9; ++k) z[k] = zio[(size_t)k * n_pad + e];
-	prox_tet<E, MODEL>(mat, z);
+	if (prox_tet_mode<E, MODEL, PROX_FAST>(mat, z)) { defer_list[atomicAdd(defer_count, 1)] = e; return; }
 #pragma unroll
 	for (int k = 0; k < 9; ++k) zio[(size_t)k * n_pad + e] = z[k];
+}
+template <typename E, int MODEL>
+__global__ void __launch_bounds__(128) tet_prox_only_deferred_kernel(int n_pad, E *zio, Material<E> mat, const int *defer_count, const int *defer_list)
+{
+	const int count = *defer_count;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+		const int e = defer_list[k];
+		E z[9];
+#pragma unroll
+		for (int j = 0; j < 9; ++j) z[j] = zio[(size_t)j * n_pad + e];
+		prox_tet_mode<E, MODEL, PROX_REFERENCE>(mat, z);
+#pragma unroll
+		for (int j = 0; j < 9; ++j) zio[(size_t)j * n_pad + e] = z[j];
+	}
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -41,8 +41,18 @@ template <> struct Num<float> {
 	static ADMMB200_FN float rsqrt(float x) { return ::rsqrtf(x); }
 	static ADMMB200_FN float sqrt(float x) { return ::sqrtf(x); }
 	static ADMMB200_FN float log(float x) { return ::logf(x); }
+	// approximate (<= 2 ulp) quotient / reciprocal for quantities that only steer an iteration (Jacobi
+	// angles, Newton directions): one MUFU.RCP instead of the IEEE sequence with its slow-path branch
+#if defined(__CUDA_ARCH__)
+	static ADMMB200_FN float fdiv(float a, float b) { return __fdividef(a, b); }
+	static ADMMB200_FN float frcp(float x) { return __fdividef(1.0f, x); }
+#else
+	static ADMMB200_FN float fdiv(float a, float b) { return a / b; }
+	static ADMMB200_FN float frcp(float x) { return 1.0f / x; }
+#endif
 	static constexpr int jacobi_sweeps = 5;
 	static constexpr int newton_iters = 24;
+	static ADMMB200_FN float newton_tol() { return 2e-4f; } // quadratic convergence: the step after a 2e-4 step is < 1e-7
 };
 template <> struct Num<double> {
 	static ADMMB200_FN double eps() { return 2.220446049250313e-16; }
@@ -50,8 +60,11 @@ template <> struct Num<double> {
 	static ADMMB200_FN double rsqrt(double x) { return 1.0 / ::sqrt(x); }
 	static ADMMB200_FN double sqrt(double x) { return ::sqrt(x); }
 	static ADMMB200_FN double log(double x) { return ::log(x); }
+	static ADMMB200_FN double fdiv(double a, double b) { return a / b; }
+	static ADMMB200_FN double frcp(double x) { return 1.0 / x; }
 	static constexpr int jacobi_sweeps = 8;
 	static constexpr int newton_iters = 48;
+	static ADMMB200_FN double newton_tol() { return 1e-7; }
 };
 
 // One Jacobi rotation in the (p,q) plane of a symmetric 3x3 matrix; r is the third index.
@@ -61,8 +74,8 @@ ADMMB200_FN void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &arq,
 	T &v0p, T &v0q, T &v1p, T &v1q, T &v2p, T &v2q)
 {
 	if (fabs(apq) <= Num<T>::eps() * T(0.125) * (fabs(app) + fabs(aqq)) || fabs(apq) < Num<T>::tiny()) { apq = (fabs(apq) < Num<T>::tiny()) ? T(0) : apq; return; }
-	T theta = (aqq - app) / (T(2) * apq);
-	T t = copysign(T(1), theta) / (fabs(theta) + Num<T>::sqrt(theta * theta + T(1)));
+	T theta = Num<T>::fdiv(aqq - app, T(2) * apq);
+	T t = Num<T>::fdiv(copysign(T(1), theta), fabs(theta) + Num<T>::sqrt(theta * theta + T(1)));
 	T c = Num<T>::rsqrt(t * t + T(1));
 	T s = t * c;
 	app -= t * apq;
@@ -95,6 +108,14 @@ ADMMB200_FN void svd3_signed(const T *F, T *S, T *U, T *V)
 		jacobi_rot(c00, c11, c01, c02, c12, v00, v01, v10, v11, v20, v21); // (0,1), r=2
 		jacobi_rot(c00, c22, c02, c01, c12, v00, v02, v10, v12, v20, v22); // (0,2), r=1
 		jacobi_rot(c11, c22, c12, c01, c02, v01, v02, v11, v12, v21, v22); // (1,2), r=0
+		// converged when every off-diagonal is below the rotation threshold; leave as a warp (all lanes agree)
+		const T tr = fabs(c00) + fabs(c11) + fabs(c22);
+		const bool done = (fabs(c01) + fabs(c02) + fabs(c12)) <= Num<T>::eps() * T(0.125) * tr;
+#if defined(__CUDA_ARCH__)
+		if (__all_sync(__activemask(), done)) break;
+#else
+		if (done) break;
+#endif
 	}
 	// sort eigenvalues descending; a swap of two columns with one negation keeps det V = +1
 #define ADMMB200_SWAPCOL(la, lb, a0, a1, a2, b0, b1, b2)                \
@@ -286,6 +307,8 @@ ADMMB200_FN bool prox_newton(const Material<T> &m, const T *x0, T *x)
 	bool converged = false;
 	typedef Energy<T, MODEL> En;
 	const T floor_x = NeedsPositive<MODEL>::value ? T(1e-12) : T(0);
+	T phi_x = T(0);          // phi at x, carried from the accepted trial point of the previous iteration
+	bool have_phi = false;
 #pragma unroll 1
 	for (int it = 0; it < Num<T>::newton_iters; ++it) {
 		T g[3], h[6];
@@ -302,28 +325,28 @@ ADMMB200_FN bool prox_newton(const Material<T> &m, const T *x0, T *x)
 			if (x[1] <= on_bound && g[1] > T(0)) { x[1] = T(0); g[1] = T(0); h[1] = T(1); h[3] = T(0); h[5] = T(0); }
 			if (x[2] <= on_bound && g[2] > T(0)) { x[2] = T(0); g[2] = T(0); h[2] = T(1); h[4] = T(0); h[5] = T(0); }
 		}
-		// Newton direction by LDL^T; if H is not positive definite fall back to a scaled gradient step
+		// Newton direction by LDL^T (reciprocals of the pivots are approximate: they only steer the
+		// iteration); if H is not positive definite fall back to a scaled gradient step
 		T d[3];
-		bool pd = true;
-		T d0 = h[0];
-		pd = pd && (d0 > T(0));
-		T l10 = h[3] / d0, l20 = h[4] / d0;
-		T d1 = h[1] - l10 * h[3];
-		pd = pd && (d1 > T(0));
-		T l21 = (h[5] - l20 * h[3]) / d1;
-		T d2 = h[2] - l20 * h[4] - l21 * l21 * d1;
-		pd = pd && (d2 > T(0));
+		const T d0 = h[0];
+		const T r0 = Num<T>::frcp(d0);
+		const T l10 = h[3] * r0, l20 = h[4] * r0;
+		const T d1 = h[1] - l10 * h[3];
+		const T r1 = Num<T>::frcp(d1);
+		const T l21 = (h[5] - l20 * h[3]) * r1;
+		const T d2 = h[2] - l20 * h[4] - l21 * l21 * d1;
+		const bool pd = (d0 > T(0)) && (d1 > T(0)) && (d2 > T(0));
 		if (pd) {
+			const T r2 = Num<T>::frcp(d2);
 			T y0 = -g[0], y1 = -g[1] - l10 * y0, y2 = -g[2] - l20 * y0 - l21 * y1;
-			T z2 = y2 / d2, z1 = y1 / d1 - l21 * z2, z0 = y0 / d0 - l10 * z1 - l20 * z2;
+			T z2 = y2 * r2, z1 = y1 * r1 - l21 * z2, z0 = y0 * r0 - l10 * z1 - l20 * z2;
 			d[0] = z0; d[1] = z1; d[2] = z2;
 		} else {
 			T bound = fmax(fmax(fabs(h[0]) + fabs(h[3]) + fabs(h[4]), fabs(h[1]) + fabs(h[3]) + fabs(h[5])), fabs(h[2]) + fabs(h[4]) + fabs(h[5]));
 			T sc = T(1) / fmax(bound, T(1));
 			d[0] = -g[0] * sc; d[1] = -g[1] * sc; d[2] = -g[2] * sc;
 		}
-		T gd = g[0] * d[0] + g[1] * d[1] + g[2] * d[2];
-		// keep the iterate inside the feasible set (value() is +inf for x<0, src/TetEnergyTerm.cpp:184-188)
+		// keep the iterate inside the feasible set
 		T t = T(1);
 #pragma unroll
 		for (int i = 0; i < 3; ++i) {
@@ -333,21 +356,37 @@ ADMMB200_FN bool prox_newton(const Material<T> &m, const T *x0, T *x)
 				t = fmin(t, ti);
 			}
 		}
-		T dx0 = x[0] - x0[0], dx1 = x[1] - x0[1], dx2 = x[2] - x0[2];
-		T phi0 = En::value(m, x) + T(0.5) * (dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
-		T slack = T(8) * Num<T>::eps() * (fabs(phi0) + T(1));
+		const T dmax = fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2]));
+		const T xmin = fmin(fmin(x[0], x[1]), x[2]);
 		T xn[3];
+		// A full Newton step that is small against the distance to the bound and taken with a positive
+		// definite Hessian needs no safeguard; everything else goes through the Armijo backtracking.
+		if (pd && t == T(1) && dmax < T(0.05) * xmin) {
+			xn[0] = x[0] + d[0]; xn[1] = x[1] + d[1]; xn[2] = x[2] + d[2];
+			have_phi = false;
+		} else {
+			T gd = g[0] * d[0] + g[1] * d[1] + g[2] * d[2];
+			if (!have_phi) {
+				T dx0 = x[0] - x0[0], dx1 = x[1] - x0[1], dx2 = x[2] - x0[2];
+				phi_x = En::value(m, x) + T(0.5) * (dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+			}
+			T slack = T(8) * Num<T>::eps() * (fabs(phi_x) + T(1));
+			T phi = phi_x;
 #pragma unroll 1
-		for (int ls = 0; ls < 16; ++ls) {
-			xn[0] = fmax(x[0] + t * d[0], floor_x); xn[1] = fmax(x[1] + t * d[1], floor_x); xn[2] = fmax(x[2] + t * d[2], floor_x);
-			T e0 = xn[0] - x0[0], e1 = xn[1] - x0[1], e2 = xn[2] - x0[2];
-			T phi = En::value(m, xn) + T(0.5) * (e0 * e0 + e1 * e1 + e2 * e2);
-			if (phi <= phi0 + T(1e-4) * t * gd + slack) break;
-			t *= T(0.5);
+			for (int ls = 0; ls < 16; ++ls) {
+				xn[0] = fmax(x[0] + t * d[0], floor_x); xn[1] = fmax(x[1] + t * d[1], floor_x); xn[2] = fmax(x[2] + t * d[2], floor_x);
+				T e0 = xn[0] - x0[0], e1 = xn[1] - x0[1], e2 = xn[2] - x0[2];
+				phi = En::value(m, xn) + T(0.5) * (e0 * e0 + e1 * e1 + e2 * e2);
+				if (phi <= phi_x + T(1e-4) * t * gd + slack) break;
+				t *= T(0.5);
+			}
+			phi_x = phi; have_phi = true;
 		}
-		T step = t * fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2]));
+		const T step = t * dmax;
 		x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
-		T scale = T(1) + fmax(fmax(fabs(x[0]), fabs(x[1])), fabs(x[2]));
+		const T scale = T(1) + fmax(fmax(fabs(x[0]), fabs(x[1])), fabs(x[2]));
+		// quadratic convergence: after a (safeguard-free or full) step of size s the error is O(s^2)
+		if (step <= Num<T>::newton_tol() * scale && t == T(1) && pd) { converged = true; break; }
 		if (step <= T(4) * Num<T>::eps() * scale) { converged = true; break; }
 	}
 	// "near the bound" is generous on purpose: the slow path IS the reference's algorithm
@@ -473,8 +512,14 @@ ADMMB200_SLOWPATH void prox_lbfgs_reference(double mu, double lambda, double kap
 }
 
 // HyperElasticTet::prox (src/TetEnergyTerm.cpp:114-136) on a column-major 3x3 z (in/out).
-template <typename T, int MODEL>
-ADMMB200_FN void prox_tet(const Material<T> &m, T *z)
+//   PROX_INLINE     Newton, and the reference-faithful path right here when the element is degenerate
+//   PROX_FAST       Newton only; returns true (z unspecified) for a degenerate element, so that the
+//                   caller can queue it -- the hot kernel then carries no call, no stack, fewer registers
+//   PROX_REFERENCE  the reference-faithful path only (the queue's consumer)
+enum ProxMode { PROX_INLINE = 0, PROX_FAST = 1, PROX_REFERENCE = 2 };
+
+template <typename T, int MODEL, int MODE>
+ADMMB200_FN bool prox_tet_mode(const Material<T> &m, T *z)
 {
 	T S[3], U[9], V[9];
 	svd3_signed(z, S, U, V);
@@ -485,7 +530,7 @@ ADMMB200_FN void prox_tet(const Material<T> &m, T *z)
 		usvt(U, one, V, P);
 #pragma unroll
 		for (int i = 0; i < 9; ++i) z[i] = T(0.5) * (P[i] + z[i]);
-		return;
+		return false;
 	}
 	T x0[3] = {S[0], S[1], S[2]};
 	const T eps = T(1e-6);
@@ -497,25 +542,32 @@ ADMMB200_FN void prox_tet(const Material<T> &m, T *z)
 		const T lo = T(1e-7);
 		S[0] = fmax(S[0], lo); S[1] = fmax(S[1], lo); S[2] = fmax(S[2], lo);
 	}
-	T start[3] = {S[0], S[1], S[2]};
 	// an element collapsed to a point starts 6 decades from its minimiser: where the reference's
 	// optimiser stops from there is path-dependent too (src/TetEnergyTerm.cpp:126-129)
 	bool degenerate = collapsed;
-	if (!collapsed) {
-	if (MODEL == TET_NEOHOOKEAN) degenerate = prox_newton<T, TET_NEOHOOKEAN>(m, x0, S);
-	if (MODEL == TET_STVK) degenerate = prox_newton<T, TET_STVK>(m, x0, S);
-	if (MODEL == TET_SPLINE_NH) degenerate = prox_newton<T, TET_SPLINE_NH>(m, x0, S);
-	if (MODEL == TET_SPLINE_STVK) degenerate = prox_newton<T, TET_SPLINE_STVK>(m, x0, S);
-	if (MODEL == TET_SPLINE_COROT) degenerate = prox_newton<T, TET_SPLINE_COROT>(m, x0, S);
+	if (MODE == PROX_REFERENCE) degenerate = true;
+	else if (!collapsed) {
+		T start[3] = {S[0], S[1], S[2]};
+		if (MODEL == TET_NEOHOOKEAN) degenerate = prox_newton<T, TET_NEOHOOKEAN>(m, x0, S);
+		if (MODEL == TET_STVK) degenerate = prox_newton<T, TET_STVK>(m, x0, S);
+		if (MODEL == TET_SPLINE_NH) degenerate = prox_newton<T, TET_SPLINE_NH>(m, x0, S);
+		if (MODEL == TET_SPLINE_STVK) degenerate = prox_newton<T, TET_SPLINE_STVK>(m, x0, S);
+		if (MODEL == TET_SPLINE_COROT) degenerate = prox_newton<T, TET_SPLINE_COROT>(m, x0, S);
+		if (degenerate) { S[0] = start[0]; S[1] = start[1]; S[2] = start[2]; }
 	}
 	if (degenerate) {
+		if (MODE == PROX_FAST) return true;
 		// minimiser on the bound (or no convergence): walk the reference optimiser's own path in fp64
-		double xs[3] = {double(start[0]), double(start[1]), double(start[2])}, xc[3] = {double(x0[0]), double(x0[1]), double(x0[2])};
+		double xs[3] = {double(S[0]), double(S[1]), double(S[2])}, xc[3] = {double(x0[0]), double(x0[1]), double(x0[2])};
 		if (MODEL != TET_LINEAR) prox_lbfgs_reference<MODEL == TET_LINEAR ? TET_STVK : MODEL>(m.mu, m.lambda, m.kappa, xc, xs);
 		S[0] = T(xs[0]); S[1] = T(xs[1]); S[2] = T(xs[2]);
 	}
 	usvt(U, S, V, z);
+	return false;
 }
+
+template <typename T, int MODEL>
+ADMMB200_FN void prox_tet(const Material<T> &m, T *z) { prox_tet_mode<T, MODEL, PROX_INLINE>(m, z); }
 
 // TriEnergyTerm::prox (src/TriEnergyTerm.cpp:73-101) on a column-major 3x2 z (in/out):
 // P = U[:, :2] V^T (nearest matrix with singular values 1,1), z = (P+z)/2, then the optional
