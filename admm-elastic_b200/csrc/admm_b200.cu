@@ -173,6 +173,7 @@ struct admm_b200_solver {
 	int linsolver = 0, gs_iters = 30, precision = 0;
 	double gs_omega = 1.9, gs_tol = 1e-10;
 	bool store_z = false;
+	int tet_minblocks = 6; // resident blocks/SM the fp32 tet kernel is compiled for (ADMM_B200_TET_MINBLOCKS = 5, 6, 8)
 
 	// events
 	std::vector<cudaEvent_t> events;
@@ -234,8 +235,11 @@ template <typename E, int MODEL> void launch_tet_model(S *s, TetBatchH *t)
 	int blocks = (t->n + threads - 1) / threads;
 	const bool sz = s->store_z && t->d_z.p;
 	if (MODEL != TET_LINEAR) CK(cudaMemsetAsync(t->d_defer.p, 0, sizeof(int), s->stream));
-	if (sz) tet_local_kernel<E, MODEL, true><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
-	else tet_local_kernel<E, MODEL, false><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	if (sz) tet_local_kernel<E, MODEL, true, 4><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	else if (sizeof(E) == 8) tet_local_kernel<E, MODEL, false, 4><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	else if (s->tet_minblocks >= 8) tet_local_kernel<E, MODEL, false, 8><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	else if (s->tet_minblocks >= 6) tet_local_kernel<E, MODEL, false, 6><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	else tet_local_kernel<E, MODEL, false, 5><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	CK(cudaGetLastError());
 	s->launches++;
 	if (MODEL != TET_LINEAR) {

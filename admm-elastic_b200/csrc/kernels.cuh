@@ -141,8 +141,9 @@ __device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4
 	f[3] = Vec4<E>::make(f3[0], f3[1], f3[2]);
 }
 
-template <typename E, int MODEL, bool STORE_Z>
-__global__ void __launch_bounds__(128) tet_local_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
+// MINB = resident blocks per SM asked of the compiler (register budget 65536 / (128 MINB))
+template <typename E, int MODEL, bool STORE_Z, int MINB>
+__global__ void __launch_bounds__(128, MINB) tet_local_kernel(TetBatch<E> tb, const double4 *__restrict__ cx)
 {
 	int e = blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= tb.n) return;

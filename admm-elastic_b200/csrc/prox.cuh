@@ -73,14 +73,18 @@ template <typename T>
 ADMMB200_FN void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &arq,
 	T &v0p, T &v0q, T &v1p, T &v1q, T &v2p, T &v2q)
 {
-	if (fabs(apq) <= Num<T>::eps() * T(0.125) * (fabs(app) + fabs(aqq)) || fabs(apq) < Num<T>::tiny()) { apq = (fabs(apq) < Num<T>::tiny()) ? T(0) : apq; return; }
-	T theta = Num<T>::fdiv(aqq - app, T(2) * apq);
+	// branch-free: a negligible off-diagonal gets the identity rotation (t = 0 -> c = 1, s = 0)
+	const bool skip = fabs(apq) <= Num<T>::eps() * T(0.125) * (fabs(app) + fabs(aqq)) || fabs(apq) < Num<T>::tiny();
+	const T den = skip ? T(1) : T(2) * apq;
+	T theta = Num<T>::fdiv(aqq - app, den);
 	T t = Num<T>::fdiv(copysign(T(1), theta), fabs(theta) + Num<T>::sqrt(theta * theta + T(1)));
+	t = skip ? T(0) : t;
+	if (fabs(apq) < Num<T>::tiny()) apq = T(0);
 	T c = Num<T>::rsqrt(t * t + T(1));
 	T s = t * c;
 	app -= t * apq;
 	aqq += t * apq;
-	apq = T(0);
+	apq = skip ? apq : T(0);
 	T nrp = c * arp - s * arq, nrq = s * arp + c * arq; arp = nrp; arq = nrq;
 	T a, b;
 	a = c * v0p - s * v0q; b = s * v0p + c * v0q; v0p = a; v0q = b;
