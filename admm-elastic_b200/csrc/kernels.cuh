@@ -94,15 +94,18 @@ template <typename E, int MODEL, bool STORE_Z, int MODE>
 __device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4 *__restrict__ cx, int e)
 {
 	const int np = tb.n_pad;
-	int4 id = __ldg(&tb.idx[e]);
+	// Load order matters: the vertex gathers depend on the index load, the SoA columns do not -- issue
+	// index first, then all independent columns, and only then touch the indices.
+	const int4 id = __ldg(&tb.idx[e]);
+	E bi[9], u[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) bi[k] = __ldg(&tb.dminv[(size_t)k * np + e]);
+#pragma unroll
+	for (int k = 0; k < 9; ++k) u[k] = tb.u[(size_t)k * np + e];
+	const E w = __ldg(&tb.wdt2[e]);
 	double4 p0 = ld_node(&cx[id.x]), p1 = ld_node(&cx[id.y]), p2 = ld_node(&cx[id.z]), p3 = ld_node(&cx[id.w]);
 	// Ds = [x1-x0, x2-x0, x3-x0], differences in fp64 (positions are ~metres, edges ~centimetres)
 	E ds[9] = {E(p1.x - p0.x), E(p1.y - p0.y), E(p1.z - p0.z), E(p2.x - p0.x), E(p2.y - p0.y), E(p2.z - p0.z), E(p3.x - p0.x), E(p3.y - p0.y), E(p3.z - p0.z)};
-	E bi[9], u[9];
-#pragma unroll
-	for (int k = 0; k < 9; ++k) bi[k] = tb.dminv[(size_t)k * np + e];
-#pragma unroll
-	for (int k = 0; k < 9; ++k) u[k] = tb.u[(size_t)k * np + e];
 	// F = Ds * Binv, column-major F[3r+j] = sum_c Ds(j,c) Binv(c,r)   (D_i x, src/TetEnergyTerm.cpp:50-71)
 	E F[9], z[9];
 #pragma unroll
@@ -126,7 +129,6 @@ __device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4
 		y[k] = z[k] - un;
 	}
 	// corner shares of dt^2 D^T W^2 y: corner c>=1: wdt2 * sum_r Binv(c-1,r) y[:,r]; corner 0: minus their sum
-	E w = tb.wdt2[e];
 	E f1[3], f2[3], f3[3];
 #pragma unroll
 	for (int j = 0; j < 3; ++j) {
