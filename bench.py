@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--admm-iters", type=int, default=20)
     ap.add_argument("--linsolver", type=int, default=1, help="1 = NodalMultiColorGS (headline), 0 = LDLT")
     ap.add_argument("--precision", type=int, default=0, help="element data: 0 = fp32 (production), 1 = fp64")
+    ap.add_argument("--floor", action="store_true", help="BASELINE config 3 style: no pins, the beam drops on a Floor handled inside the GS sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=120.0, help="budget of the whole --impl reference run")
@@ -76,13 +77,14 @@ def make_scene(pkg, workload):
     s = (x0[:, 0] - x0[:, 0].min()) / L
     x0[:, 1] -= 0.08 * L * s * s
     x0[:, 2] += 0.02 * L * np.sin(3.0 * s)
-    return dict(verts=v64, tets=tets, masses=masses, pins=pins, x0=x0, dims=(nx, ny, nz))
+    return dict(verts=v64, tets=tets, masses=masses, pins=pins, x0=x0, dims=(nx, ny, nz), floor_y=float(v64[:, 1].min() - 0.05))
 
 
 def workload_name(args, scene):
     nx, ny, nz = scene["dims"]
-    return ("%d-tet %s cantilever beam (%dx%dx%d cubes x 5 tets), %d ADMM iters/step, %s, dt=1/24 s, g=-9.8"
-            % (len(scene["tets"]), MODEL_NAMES.get(args.model, str(args.model)), nx, ny, nz, args.admm_iters,
+    return ("%d-tet %s %s (%dx%dx%d cubes x 5 tets), %d ADMM iters/step, %s, dt=1/24 s, g=-9.8"
+            % (len(scene["tets"]), MODEL_NAMES.get(args.model, str(args.model)),
+               "beam dropped on a Floor (no pins)" if getattr(args, "floor", False) else "cantilever beam", nx, ny, nz, args.admm_iters,
                "NodalMultiColorGS 30 sweeps omega=1.9" if args.linsolver == 1 else "LDLT"))
 
 
@@ -161,7 +163,10 @@ def cpu_solver(args, scene, pkg, admm_iters):
     mu, lam = pkg.meshes.lame(*LAME)
     s.add_nodes(scene["verts"], scene["masses"])
     s.add_tets(scene["verts"], scene["tets"], args.model, mu, lam)
-    s.set_pins(scene["pins"])
+    if getattr(args, "floor", False):
+        s.add_floor(scene["floor_y"])
+    else:
+        s.set_pins(scene["pins"])
     if kind == "oracle" and args.linsolver == 1:
         raise RuntimeError("the oracle port takes its colours from a caller; build oracle/_ref for the CPU arm")
     t0 = time.time()
@@ -286,7 +291,10 @@ def run_b200(args):
         sol.set_rank(rank, world)
     sol.add_nodes(scene["verts"], scene["masses"])
     sol.add_tets(scene["verts"], scene["tets"], args.model, mu, lam)
-    sol.set_pins(scene["pins"])
+    if args.floor:
+        sol.add_floor(scene["floor_y"])
+    else:
+        sol.set_pins(scene["pins"])
     t0 = time.time()
     assert sol.initialize(dt=1.0 / 24, admm_iters=iters, gravity=-9.8, linsolver=args.linsolver)
     init_s = time.time() - t0
