@@ -5,6 +5,7 @@
 #include "sptrsv.cuh"
 #include "mcgs_resident.cuh"
 #include "mcgs_resident_f32.cuh"
+#include "mcgs_owned_f32.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -133,6 +134,7 @@ struct admm_b200_solver {
 	// mcgs, shared-memory-resident variant (mcgs_resident.cuh)
 	bool gs_resident = false;
 	int gs_res_lanes = 1;
+	int gs_owned_threads = 0;  // > 0: mcgs_owned_f32_kernel with that many threads (the production fp32 solve)
 	size_t gs_res_smem = 0;
 	DevBuf<PartDesc> res_parts;
 	DevBuf<uint16_t> res_col;
@@ -332,17 +334,34 @@ void fill_mcgs_params(S *s, McgsParams &P);
 
 // precision FP64: positions in shared memory as doubles (mcgs_resident_kernel<double>);
 // precision FP32: fp32 sweeps on the increment around the fp64 anchor (mcgs_resident_f32_kernel)
-const void *resident_kernel_ptr(bool fp64, int lanes)
+const void *resident_kernel_ptr(bool fp64, int lanes, bool prof)
 {
 	if (fp64) {
 		if (lanes == 1) return (const void *)mcgs_resident_kernel<double, 1>;
 		if (lanes == 2) return (const void *)mcgs_resident_kernel<double, 2>;
 		return (const void *)mcgs_resident_kernel<double, 4>;
 	}
-	if (lanes == 1) return (const void *)mcgs_resident_f32_kernel<1>;
-	if (lanes == 2) return (const void *)mcgs_resident_f32_kernel<2>;
-	return (const void *)mcgs_resident_f32_kernel<4>;
+	if (prof) {
+		if (lanes == 1) return (const void *)mcgs_resident_f32_kernel<1, true>;
+		if (lanes == 2) return (const void *)mcgs_resident_f32_kernel<2, true>;
+		return (const void *)mcgs_resident_f32_kernel<4, true>;
+	}
+	if (lanes == 1) return (const void *)mcgs_resident_f32_kernel<1, false>;
+	if (lanes == 2) return (const void *)mcgs_resident_f32_kernel<2, false>;
+	return (const void *)mcgs_resident_f32_kernel<4, false>;
 }
+
+// mcgs_owned_f32_kernel<threads, slices per warp, obstacles, profiling>: 512 x 4 and 768 x 3 slices
+const void *owned_kernel_ptr(int threads, bool obst, bool prof)
+{
+	if (threads == 512) {
+		if (prof) return obst ? (const void *)mcgs_owned_f32_kernel<512, 4, true, true> : (const void *)mcgs_owned_f32_kernel<512, 4, false, true>;
+		return obst ? (const void *)mcgs_owned_f32_kernel<512, 4, true, false> : (const void *)mcgs_owned_f32_kernel<512, 4, false, false>;
+	}
+	if (prof) return obst ? (const void *)mcgs_owned_f32_kernel<768, 3, true, true> : (const void *)mcgs_owned_f32_kernel<768, 3, false, true>;
+	return obst ? (const void *)mcgs_owned_f32_kernel<768, 3, true, false> : (const void *)mcgs_owned_f32_kernel<768, 3, false, false>;
+}
+inline int owned_capacity(int threads) { return threads == 512 ? 4 * 16 : 3 * 24; }
 
 void launch_mcgs_resident(S *s)
 {
@@ -370,12 +389,17 @@ void launch_mcgs_resident(S *s)
 		R32.tag_base = s->gs_solve_seq << 12;
 		R32.n_nodes_total = s->n_nodes;
 		R32.part0 = s->rank * s->n_sms; R32.world = s->world; R32.rank = s->rank;
+		{ static const char *dbg = getenv("ADMM_B200_GS_DBG"); R32.dbg = dbg ? atoi(dbg) : 0; }
 		R32.dest_mask = s->world > 1 ? s->mg_dest_mask.p : nullptr;
 		for (int q = 0; q < ADMMB200_MAX_RANKS; ++q) { R32.peer_dglob[q] = s->peer_dglob[q]; R32.peer_x[q] = s->peer_x[q]; }
 		if (s->world > 1) { require(s->mg_ready, "multi-GPU solver used before admm_b200_mgpu_ready"); R32.base.tol2 = 0.0; }
 		args[0] = &R32;
 	}
-	CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
+	if (!fp64 && s->gs_owned_threads > 0) {
+		const void *kern = owned_kernel_ptr(s->gs_owned_threads, !s->obstacles.empty(), s->res_prof.p != nullptr);
+		CK(cudaLaunchCooperativeKernel(kern, dim3(s->n_sms), dim3(s->gs_owned_threads), args, s->gs_res_smem, s->stream));
+	} else
+		CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes, s->res_prof.p != nullptr), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
 	s->launches++;
 }
 
@@ -579,7 +603,8 @@ void build_mcgs_resident(S *s)
 	CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
 	const int lanes = plan_default_lanes();
 	s->gs_res_lanes = lanes;
-	const void *kern = resident_kernel_ptr(val_bytes == 8, lanes);
+	const bool prof = getenv("ADMM_B200_GS_PROF") != nullptr;
+	const void *kern = resident_kernel_ptr(val_bytes == 8, lanes, prof);
 	cudaFuncAttributes fa;
 	CK(cudaFuncGetAttributes(&fa, kern));
 	const size_t budget = (size_t)max_optin - fa.sharedSizeBytes;
@@ -619,7 +644,7 @@ void build_mcgs_resident(S *s)
 	}
 	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
 	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
-	if (getenv("ADMM_B200_GS_PROF")) { s->res_prof.alloc(16 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
+	if (prof) { s->res_prof.alloc(16 * (size_t)s->n_sms + 1024 + 128 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
 	if (val_bytes == 8) {
 		s->res_val.alloc(std::max<size_t>(R.val.size(), 1) * 8);
 		if (!R.val.empty()) CK(cudaMemcpyAsync(s->res_val.p, R.val.data(), R.val.size() * 8, cudaMemcpyHostToDevice, s->stream));
@@ -632,10 +657,29 @@ void build_mcgs_resident(S *s)
 		CK(cudaStreamSynchronize(s->stream));
 	}
 	CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+	// static-ownership kernel (mcgs_owned_f32.cuh): fp32 sweeps, one lane per node, every part's slices fit the warps' registers
+	s->gs_owned_threads = 0;
+	if (val_bytes == 4 && lanes == 1 && s->n_colors <= ADMMB200_OWNED_MAX_COLORS) {
+		const char *eo = getenv("ADMM_B200_GS_OWNED"); // 0: keep the table-walking kernel; 512 / 768: force that variant
+		const int want_threads = eo ? atoi(eo) : -1;
+		int pick = 0;
+		if (want_threads == 512 || want_threads == 768) pick = want_threads;
+		else if (want_threads != 0) pick = (int)R.max_slices <= owned_capacity(512) ? 512 : 768;
+		if (pick && (int)R.max_slices <= owned_capacity(pick)) {
+			for (int ob = 0; ob < 2; ++ob) {
+				const void *ko = owned_kernel_ptr(pick, ob != 0, prof);
+				cudaFuncAttributes fo;
+				CK(cudaFuncGetAttributes(&fo, ko));
+				if (need + fo.sharedSizeBytes > (size_t)max_optin) { pick = 0; break; }
+				CK(cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+			}
+			s->gs_owned_threads = pick;
+		}
+	}
 	CK(cudaStreamSynchronize(s->stream));
 	s->gs_res_smem = need;
 	s->gs_resident = true;
-	s->gs_info = std::string("resident: ") + buf;
+	s->gs_info = std::string("resident: ") + buf + (s->gs_owned_threads ? "; static-ownership kernel, " + std::to_string(s->gs_owned_threads) + " threads" : std::string("; table-walking kernel"));
 }
 
 void build_mcgs(S *s)

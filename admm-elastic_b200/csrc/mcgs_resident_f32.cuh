@@ -42,6 +42,7 @@ struct McgsRes32Params {
 	// Boundary values are also pushed into the peers that read them (stores over NVLink into their dglob /
 	// x arrays, mapped through CUDA IPC); nothing is ever READ from a peer, so spinning stays local.
 	int part0, world, rank;
+	int dbg; // timing experiments only (ADMM_B200_GS_DBG, tools/gs_prof.py): 1 no tag wait, 2 no refresh, 4 no interior, 8 no boundary
 	const unsigned int *dest_mask; // [n_nodes] ranks (bit q) that read this node as halo; NULL when world == 1
 	uint2 *peer_dglob[ADMMB200_MAX_RANKS];
 	double4 *peer_x[ADMMB200_MAX_RANKS];
@@ -87,7 +88,9 @@ __device__ __forceinline__ void res32_gather(const float *s_val, const uint16_t 
 	}
 }
 
-template <int T>
+// PROF / DBG: cycle counters and timing experiments (tools/gs_prof.py) are a separate instantiation, so the
+// production kernel carries none of their state (it used to cost 144 B of spills per thread).
+template <int T, bool PROF>
 __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_kernel(McgsRes32Params R)
 {
 	constexpr int G = 32 / T;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	__shared__ int s_nbr[192];
 	__shared__ int s_decision;
 	const McgsParams &P = R.base;
-	const long long t_kernel = R.prof ? clock64() : 0;
+	const long long t_kernel = PROF ? clock64() : 0;
 	const PartDesc d = R.parts[R.part0 + blockIdx.x];
 	const int tid = threadIdx.x, lane = tid & 31, sub = lane % T, grp = lane / T, warp = tid >> 5, n_warps = blockDim.x >> 5;
 	const int n_loc = d.n_own + d.n_halo, C = P.n_colors;
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	size_t o = 0;
 	auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
 	float4 *s_d = (float4 *)(smem + take(16 * (size_t)n_loc));
-	float *s_val = (float *)(smem + take(sizeof(float) * 32 * (size_t)d.n_rows));
+	float *s_val = (float *)(smem + take(res32_val_region((size_t)d.n_rows, (size_t)n_loc)));
 	uint16_t *s_col = (uint16_t *)(smem + take(sizeof(uint16_t) * 32 * (size_t)d.n_rows));
 	int *s_gid = (int *)(smem + take(sizeof(int) * (size_t)n_loc));
 	int *s_srow = (int *)(smem + take(sizeof(int) * ((size_t)d.n_slices + 1)));
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 	if (d.n_rows > 0) mbar_wait(&tma_bar, 0);
 	__syncthreads();
 
-	const long long t_staged = R.prof ? clock64() : 0;
+	const long long t_staged = PROF ? clock64() : 0;
 	unsigned int bar_target = 0;
 	const bool check = P.tol2 > 0.0;
 	const float omega = (float)P.omega, one_m_omega = (float)(1.0 - P.omega), lb_scale = (float)(1.0 / P.omega - 1.0);
@@ -250,15 +253,15 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 		for (int h = s_hcol[cp] + t0; h < s_hcol[cp + 1]; h += nt) {
 			const uint2 *w = buf + 3 * (size_t)s_gid[d.n_own + h];
 			uint2 a, b, c;
-			do { a = ll_load(w); b = ll_load(w + 1); c = ll_load(w + 2); } while (a.y != tag || b.y != tag || c.y != tag);
+			do { a = ll_load(w); b = ll_load(w + 1); c = ll_load(w + 2); } while ((a.y != tag || b.y != tag || c.y != tag) && !(PROF && (R.dbg & 1)));
 			s_d[d.n_own + h] = make_float4(__uint_as_float(a.x), __uint_as_float(b.x), __uint_as_float(c.x), 0.f);
 		}
 	};
 
 	int it = 0;
 	unsigned int pass = 0; // passes done so far
-	long long pw = 0, pc = 0, pp = 0, pi = 0;
-	const long long t_begin = R.prof ? clock64() : 0;
+	long long pw = 0, pc = 0, pp = 0, pi = 0, pk = 0;
+	const long long t_begin = PROF ? clock64() : 0;
 	for (; it < P.iters; ++it) {
 		lb = 0;
 		for (int color = 0; color < C; ++color) {
@@ -267,27 +270,28 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 			pass_tag = R.tag_base | (pass + 1);
 			pub_off = (size_t)(it & 1) * buf_stride;
 			long long t0 = 0, t1 = 0, t2 = 0;
-			if (R.prof) t0 = clock64();
+			if (PROF) t0 = clock64();
 			if (bwarp) {
-				if (pass > 0) {
+				if (pass > 0 && !(PROF && (R.dbg & 2))) {
 					// what the neighbours changed in the previous pass: the halo nodes of that pass's colour
 					const int cp = (color + C - 1) % C;
 					const int it_prev = color > 0 ? it : it - 1;
 					refresh(cp, R.dglob + (size_t)(it_prev & 1) * buf_stride, R.tag_base | pass, tid, n_bthreads);
 					named_sync(1, n_bthreads);
 				}
-				if (R.prof) t1 = clock64();
-				for (int sl = s1 + warp; sl < s2; sl += n_bwarps) do_slice(sl, true, last);
-				if (R.prof) t2 = clock64();
+				if (PROF) t1 = clock64();
+				if (!(PROF && (R.dbg & 8))) for (int sl = s1 + warp; sl < s2; sl += n_bwarps) do_slice(sl, true, last);
+				if (PROF) t2 = clock64();
 			} else {
-				for (int sl = s0 + (warp - n_bwarps); sl < s1; sl += n_iwarps) do_slice(sl, false, last);
-				if (R.prof) t1 = clock64();
+				if (!(PROF && (R.dbg & 4))) for (int sl = s0 + (warp - n_bwarps); sl < s1; sl += n_iwarps) do_slice(sl, false, last);
+				if (PROF) t1 = clock64();
 			}
 			__syncthreads();
 			++pass;
-			if (R.prof && tid == 0) { long long t3 = clock64(); pw += t1 - t0; pc += t2 - t1; pp += t3 - t2; }
-			if (R.prof && tid == n_bthreads) pi += t1 - t0;
+			if (PROF && tid == 0) { long long t3 = clock64(); pw += t1 - t0; pc += t2 - t1; pp += t3 - t2; }
+			if (PROF && tid == n_bthreads) pi += t1 - t0;
 		}
+		const long long tk0 = PROF ? clock64() : 0;
 		if (check) {
 			// "converged?" (see mcgs_resident.cuh).  A part whose own rows prove |b - A x|^2 >= 4 tol^2 |b|^2
 			// knows the answer without talking to anyone; it only leaves a note for parts that cannot.
@@ -338,9 +342,10 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 				if (r2 / b2 < P.tol2) break;
 			}
 		}
+		if (PROF) pk += clock64() - tk0;
 	}
 	// x = x_ref + d: the only write to the positions
-	const long long t_loop_end = R.prof ? clock64() : 0;
+	const long long t_loop_end = PROF ? clock64() : 0;
 	__syncthreads();
 	for (int l = tid; l < d.n_own; l += blockDim.x) {
 		const int node = s_gid[l];
@@ -354,13 +359,14 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 		}
 	}
 	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
-	if (R.prof && tid == 0) {
+	if (PROF && tid == 0) {
 		unsigned long long *q = R.prof + 16 * blockIdx.x;
 		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pp; q[3] = (unsigned long long)(clock64() - t_kernel);
 		q[13] = (unsigned long long)(t_staged - t_kernel); q[14] = (unsigned long long)(t_begin - t_staged); q[15] = (unsigned long long)(t_loop_end - t_begin);
 	}
-	if (R.prof && tid == n_bthreads) R.prof[16 * blockIdx.x + 4] = (unsigned long long)pi;
-	(void)pw; (void)pc; (void)pp; (void)pi;
+	if (PROF && tid == n_bthreads) R.prof[16 * blockIdx.x + 4] = (unsigned long long)pi;
+	if (PROF && tid == 0) R.prof[16 * blockIdx.x + 5] = (unsigned long long)pk;
+	(void)pk; (void)pw; (void)pc; (void)pp; (void)pi;
 }
 
 } // namespace admmb200

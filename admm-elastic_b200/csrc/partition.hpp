@@ -19,6 +19,15 @@
 
 namespace admmb200 {
 
+#ifdef __CUDACC__
+#define ADMMB200_HD __host__ __device__
+#else
+#define ADMMB200_HD
+#endif
+// fp32 resident solve: the matrix-value region doubles as the place where the anchor positions x_ref of
+// the part's nodes (3 doubles, owned + halo) sit while r0 = b - A x_ref is formed, before the values arrive
+ADMMB200_HD inline size_t res32_val_region(size_t n_rows, size_t n_loc) { const size_t a = 4 * 32 * n_rows, b = 24 * n_loc; return a > b ? a : b; }
+
 struct PartDesc {
 	int n_own, n_halo, n_slices, n_rows; // owned nodes, halo nodes, slices (warps' work items), 32-entry ELL rows
 	long long ent_off;                   // first entry of this part in the global col/val arrays
@@ -59,7 +68,7 @@ struct ResidentPlan {
 		auto take = [&](int i, size_t bytes) { tmp[i] = o; o += (bytes + 15) & ~(size_t)15; };
 		if (mode == 0) take(0, sizeof(double) * 3 * (size_t)d.n_own);               // x of owned nodes
 		else take(0, 16 * ((size_t)d.n_own + d.n_halo));                             // float4 increments, owned + halo
-		take(1, (size_t)(mode == 0 ? val_bytes : 4) * 32 * (size_t)d.n_rows);        // val
+		take(1, mode == 0 ? (size_t)val_bytes * 32 * (size_t)d.n_rows : res32_val_region((size_t)d.n_rows, (size_t)d.n_own + d.n_halo)); // val
 		take(2, sizeof(uint16_t) * 32 * (size_t)d.n_rows);                           // col
 		take(3, sizeof(int) * ((size_t)d.n_own + d.n_halo));                         // gid
 		take(4, sizeof(int) * ((size_t)d.n_slices + 1));                             // slice_row

@@ -69,22 +69,29 @@ template <> struct Num<double> {
 
 // One Jacobi rotation in the (p,q) plane of a symmetric 3x3 matrix; r is the third index.
 // A' = P^T A P, V' = V P with P a proper rotation, so det V stays +1.
+//
+// The angle (|phi| <= pi/4, tan 2phi = 2 apq / (aqq - app)) comes from the half-angle identities instead
+// of the textbook t = sign(theta) / (|theta| + sqrt(theta^2 + 1)): with alpha = aqq - app, beta = 2 apq,
+//     cos 2phi = |alpha| / hypot(alpha, beta),  c^2 = (1 + cos 2phi) / 2,  s = sign(alpha) beta / (2 c hypot)
+// which is two reciprocal square roots (MUFU.RSQ on the device) and no division, no square root, no
+// branch.  apq = 0 gives c = 1, s = 0 exactly, so a negligible off-diagonal needs no special case; only
+// alpha = beta = 0 (hypot underflows) is forced to the identity.
 template <typename T>
 ADMMB200_FN void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &arq,
 	T &v0p, T &v0q, T &v1p, T &v1q, T &v2p, T &v2q)
 {
-	// branch-free: a negligible off-diagonal gets the identity rotation (t = 0 -> c = 1, s = 0)
-	const bool skip = fabs(apq) <= Num<T>::eps() * T(0.125) * (fabs(app) + fabs(aqq)) || fabs(apq) < Num<T>::tiny();
-	const T den = skip ? T(1) : T(2) * apq;
-	T theta = Num<T>::fdiv(aqq - app, den);
-	T t = Num<T>::fdiv(copysign(T(1), theta), fabs(theta) + Num<T>::sqrt(theta * theta + T(1)));
-	t = skip ? T(0) : t;
-	if (fabs(apq) < Num<T>::tiny()) apq = T(0);
-	T c = Num<T>::rsqrt(t * t + T(1));
-	T s = t * c;
+	const T alpha = aqq - app, beta = apq + apq;
+	const T r2 = alpha * alpha + beta * beta;
+	const bool ok = r2 > Num<T>::tiny();
+	const T ir = Num<T>::rsqrt(ok ? r2 : T(1));
+	const T c2 = ok ? T(0.5) + T(0.5) * fabs(alpha) * ir : T(1);
+	const T ic = Num<T>::rsqrt(c2);
+	const T c = c2 * ic;
+	const T s = copysign(T(0.5) * ir * ic, alpha) * (ok ? beta : T(0));
+	const T t = s * ic; // tan phi
 	app -= t * apq;
 	aqq += t * apq;
-	apq = skip ? apq : T(0);
+	apq = T(0);
 	T nrp = c * arp - s * arq, nrq = s * arp + c * arq; arp = nrp; arq = nrq;
 	T a, b;
 	a = c * v0p - s * v0q; b = s * v0p + c * v0q; v0p = a; v0q = b;
@@ -138,15 +145,18 @@ ADMMB200_FN void svd3_signed(const T *F, T *S, T *U, T *V)
 	T b01 = F[0] * v01 + F[3] * v11 + F[6] * v21, b11 = F[1] * v01 + F[4] * v11 + F[7] * v21, b21 = F[2] * v01 + F[5] * v11 + F[8] * v21;
 	T b02 = F[0] * v02 + F[3] * v12 + F[6] * v22, b12 = F[1] * v02 + F[4] * v12 + F[7] * v22, b22 = F[2] * v02 + F[5] * v12 + F[8] * v22;
 	// U by Gram-Schmidt on the (already nearly orthogonal) columns of B, third column = cross product
-	T s0 = Num<T>::sqrt(b00 * b00 + b10 * b10 + b20 * b20);
+	// (norm and its reciprocal from ONE reciprocal square root: s = n2 * rsqrt(n2), <= 2 ulp)
+	const T n0 = b00 * b00 + b10 * b10 + b20 * b20;
+	T s0 = T(0);
 	T u00, u10, u20;
-	if (s0 > Num<T>::tiny()) { T i = T(1) / s0; u00 = b00 * i; u10 = b10 * i; u20 = b20 * i; }
+	if (n0 > Num<T>::tiny()) { T i = Num<T>::rsqrt(n0); s0 = n0 * i; u00 = b00 * i; u10 = b10 * i; u20 = b20 * i; }
 	else { u00 = 1; u10 = 0; u20 = 0; }
 	T d = u00 * b01 + u10 * b11 + u20 * b21;
 	T w0 = b01 - d * u00, w1 = b11 - d * u10, w2 = b21 - d * u20;
-	T s1 = Num<T>::sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+	const T n1 = w0 * w0 + w1 * w1 + w2 * w2;
+	T s1 = T(0);
 	T u01, u11, u21;
-	if (s1 > T(4) * Num<T>::eps() * s0 && s1 > Num<T>::tiny()) { T i = T(1) / s1; u01 = w0 * i; u11 = w1 * i; u21 = w2 * i; }
+	if (n1 > T(16) * Num<T>::eps() * Num<T>::eps() * n0 && n1 > Num<T>::tiny()) { T i = Num<T>::rsqrt(n1); s1 = n1 * i; u01 = w0 * i; u11 = w1 * i; u21 = w2 * i; }
 	else {
 		// rank <= 1: any unit vector orthogonal to u0
 		T ax = fabs(u00), ay = fabs(u10), az = fabs(u20);
@@ -205,7 +215,7 @@ template <typename T> struct Energy<T, TET_NEOHOOKEAN> {
 	}
 	static ADMMB200_FN void derivs(const Material<T> &m, const T *x, T *g, T *h) {
 		T lj = Num<T>::log(x[0] * x[1] * x[2]);
-		T i0 = T(1) / x[0], i1 = T(1) / x[1], i2 = T(1) / x[2];
+		T i0 = Num<T>::frcp(x[0]), i1 = Num<T>::frcp(x[1]), i2 = Num<T>::frcp(x[2]); // <= 1 ulp: 1e-7 relative on g
 		T q = m.l * lj - m.a; // (lambda log J - mu)
 		g[0] = m.a * x[0] + q * i0; g[1] = m.a * x[1] + q * i1; g[2] = m.a * x[2] + q * i2;
 		T p = m.a + m.l - m.l * lj; // mu + lambda (1 - log J)

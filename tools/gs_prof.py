@@ -13,11 +13,21 @@ sol.set_x(scene['x0'].ravel()); sol.upload_state()
 for _ in range(3): sol.step_device()
 print(sol.runtime_data())
 ncol=len(sol.colors()); passes=30*ncol
-p=sol.device().debug_get('gs_prof',16*148).reshape(148,16)
-names=['wait','boundary','publish','total','interior']
+raw=sol.device().debug_get('gs_prof',16*148+1024+128*148)
+p=raw[:16*148].reshape(148,16); tr=raw[16*148:16*148+1024].reshape(32,4,8).astype(np.int64)
+hn=np.maximum(p[:,12],1); print('publish -> usable (ns, global timer; mean over parts | max): vs latest neighbour %.0f | %.0f   vs own previous publish %.0f | %.0f'%((p[:,10]/hn).mean(),(p[:,10]/hn).max(),(p[:,11]/hn).mean(),(p[:,11]/hn).max()))
+names=['wait','boundary','end barrier','total','interior','between passes','sentinel wait','load+retries','sentinel spins','retries']
 print('colours',ncol,'passes',passes,' cycles per pass (mean over parts | max):', {n:(int(p[:,i].mean()/passes), int(p[:,i].max()/passes)) for i,n in enumerate(names)})
-for nm,o in (('boundary warp0',5),('interior warp0',9)):
-    n=p[:,o+3].sum()
-    if n > 0: print(nm,'slices/pass %.2f'%(p[:,o+3].mean()/passes),'cycles per slice: meta %.0f gather %.0f tail %.0f'%(p[:,o].sum()/n,p[:,o+1].sum()/n,p[:,o+2].sum()/n))
 print('kernel phases (cycles, mean over parts): staging %.0f  r0+|b|^2 %.0f  sweeps %.0f  total %.0f'%(p[:,13].mean(),p[:,14].mean(),p[:,15].mean(),p[:,3].mean()))
-print(sol.device().info())
+print('dbg',os.environ.get('ADMM_B200_GS_DBG','0'),sol.device().info())
+print('bwarps info: n_own/halo etc. in info above; solve us:', sol.device().time_kernels(10))
+
+# timeline of passes 40..43 of part (dbg >> 8): per warp, cycles relative to warp 0's pass-40 start
+# events: 0 pass start, 1 poll done, 2 after halo barrier, 3 slice done + published, 4 after end-of-pass barrier
+t00=tr[0,0,0]
+if t00>0:
+    for ps in range(4):
+        print('pass',40+ps)
+        for w in range(16):
+            e=tr[w,ps]
+            print('  warp %2d: '%w+' '.join('%6s'%(int(v-t00) if v>0 else '-') for v in e[:5]))
