@@ -142,6 +142,7 @@ struct admm_b200_solver {
 	DevBuf<int> res_gid, res_slice_row, res_color_slice, res_nbr, res_halo_color;
 	DevBuf<float4> res_nodebuf;
 	DevBuf<uint2> res_dglob;
+	DevBuf<int> res_dest_off; DevBuf<unsigned int> res_dest_slot; int res_total_slots = 0; // mailboxes (plan_mailboxes)
 	unsigned int gs_solve_seq = 0;
 	DevBuf<double> res_val64;
 	DevBuf<unsigned long long> res_prof; // ADMM_B200_GS_PROF=1: per-part cycle counters of the last solve
@@ -384,6 +385,7 @@ void launch_mcgs_resident(S *s)
 		R32.halo_color = s->res_halo_color.p;
 		R32.part_epoch = part_epoch; R32.sweep_flag = sweep_flag; R32.sweep_arrive = sweep_arrive; R32.prof = s->res_prof.p;
 		R32.dglob = s->res_dglob.p; R32.nodebuf = s->res_nodebuf.p; R32.val64 = s->res_val64.p;
+		R32.dest_off = s->res_dest_off.p; R32.dest_slot = s->res_dest_slot.p; R32.total_slots = s->res_total_slots;
 		s->gs_solve_seq = (s->gs_solve_seq + 1) & 0xFFFFFu;
 		if (s->gs_solve_seq == 0) s->gs_solve_seq = 1;
 		R32.tag_base = s->gs_solve_seq << 12;
@@ -639,7 +641,13 @@ void build_mcgs_resident(S *s)
 	}
 	if (val_bytes == 4) {
 		require((long long)s->gs_iters * s->n_colors < 4094, "resident fp32 MCGS: sweeps x colours must stay below 4094 (12-bit pass tags)");
-		s->res_dglob.alloc(6 * (size_t)s->n_nodes); s->res_dglob.zero(s->stream);
+		plan_mailboxes(R, s->n_nodes, s->n_sms);
+		s->res_parts.upload(R.parts, s->stream); // again: now with the mailbox offsets
+		s->res_dest_off.upload(R.dest_off, s->stream);
+		s->res_dest_slot.upload(R.dest_slot, s->stream);
+		s->res_total_slots = (int)R.total_slots;
+		// published increments: [2][n_nodes][3] words by node id (table-walking kernel) or [2][3][slots] (static-ownership kernel)
+		s->res_dglob.alloc(6 * std::max((size_t)s->n_nodes, R.total_slots)); s->res_dglob.zero(s->stream);
 		s->res_nodebuf.alloc(2 * (size_t)s->n_nodes); s->res_nodebuf.zero(s->stream);
 	}
 	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));

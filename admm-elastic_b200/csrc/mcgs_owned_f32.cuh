@@ -27,11 +27,10 @@ namespace admmb200 {
 #define ADMMB200_OWNED_MAX_COLORS 16
 
 struct OwnedSlice {   // registers; everything but l / rb / ia / gid / dm is warp-uniform
-	int meta;         // -1: none; else colour | boundary << 8 | pinned << 9 (pinned is per lane)
+	int meta;         // -1: none; else colour | boundary << 8 | pinned << 9 | readers << 10 (pinned, readers: per lane)
 	int r0, r1;       // ELL rows [r0, r1)
 	int l;            // local node id of this lane, -1: padding lane
-	int gid;          // global node id
-	unsigned int dm;  // peer ranks that read this node (multi-GPU)
+	unsigned int dst0, dst1; // first two mailbox slots this node is published to (slot | rank << 27); count in meta bits 10..15
 	float rb[3];      // r0 = b - A x_ref
 	float ia[3];      // 1 / a_ii
 };
@@ -129,7 +128,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 	OwnedSlice S[KMAX];
 #pragma unroll
 	for (int k = 0; k < KMAX; ++k) {
-		S[k].meta = -1; S[k].r0 = 0; S[k].r1 = 0; S[k].l = -1; S[k].gid = 0; S[k].dm = 0u;
+		S[k].meta = -1; S[k].r0 = 0; S[k].r1 = 0; S[k].l = -1; S[k].dst0 = 0u; S[k].dst1 = 0u;
 		S[k].rb[0] = S[k].rb[1] = S[k].rb[2] = 0.f; S[k].ia[0] = S[k].ia[1] = S[k].ia[2] = 0.f;
 		int c, sl; bool bnd;
 		if (locate(k * NW + warp, c, bnd, sl)) {
@@ -191,8 +190,13 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				const double xi0 = s_x[3 * l], xi1 = s_x[3 * l + 1], xi2 = s_x[3 * l + 2];
 				const double a0 = __ldg(&P.diag[3 * node]), a1 = __ldg(&P.diag[3 * node + 1]), a2 = __ldg(&P.diag[3 * node + 2]);
 				const int ps = P.has_pins ? __ldg(&P.pin_slot[node]) : -1;
-				S[k].gid = node;
-				S[k].dm = R.dest_mask ? __ldg(&R.dest_mask[node]) : 0u;
+				if (S[k].meta & 0x100) {
+					// where this boundary node is published: one mailbox slot per part that reads it
+					const int e0 = __ldg(&R.dest_off[d.own_off + l]), cnt = min(__ldg(&R.dest_off[d.own_off + l + 1]) - e0, 63);
+					if (cnt > 0) S[k].dst0 = __ldg(&R.dest_slot[e0]);
+					if (cnt > 1) S[k].dst1 = __ldg(&R.dest_slot[e0 + 1]);
+					S[k].meta |= cnt << 10;
+				}
 				S[k].rb[0] = (float)(bi.x - sx - a0 * xi0); S[k].rb[1] = (float)(bi.y - sy - a1 * xi1); S[k].rb[2] = (float)(bi.z - sz - a2 * xi2);
 				S[k].ia[0] = (float)(1.0 / a0); S[k].ia[1] = (float)(1.0 / a1); S[k].ia[2] = (float)(1.0 / a2);
 				if (OBST) { xr[OBST ? k : 0][0] = xi0; xr[OBST ? k : 0][1] = xi1; xr[OBST ? k : 0][2] = xi2; }
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 		__syncthreads();
 	}
 	const double thresh = check ? 4.0 * P.tol2 * __ldcg(&P.resid[0]) : 0.0;
-	const size_t buf_stride = 3 * (size_t)R.n_nodes_total;
+	const size_t TS = (size_t)R.total_slots, buf_stride = 3 * TS; // dglob: [sweep parity][x | y | z][slot]
 	long long pw = 0, pc = 0, pb = 0, po = 0, t_prev_end = 0, ps1 = 0, ps2 = 0, n_retry = 0, n_spin = 0, hop_nbr = 0, hop_own = 0, hop_n = 0;
 
 	// Pulls the halo values of colour `cp` published with tag `tag` in buffer `buf` into shared memory
@@ -229,10 +233,10 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 	auto refresh = [&](int cp, const uint2 *buf, unsigned int tag, int t0, int nt) {
 		const int end = s_hcol[cp + 1];
 		for (int h = s_hcol[cp] + t0; h < end; h += nt) {
-			const uint2 *w = buf + 3 * (size_t)s_gid[d.n_own + h];
+			const uint2 *w = buf + (size_t)d.slot_off + h; // consecutive lanes, consecutive slots: coalesced polls
 			uint2 a, b, c;
-			a = ll_load(w); b = ll_load(w + 1); c = ll_load(w + 2);
-			while (a.y != tag || b.y != tag || c.y != tag) { if (PROF) ++n_spin; a = ll_load(w); b = ll_load(w + 1); c = ll_load(w + 2); }
+			a = ll_load(w); b = ll_load(w + TS); c = ll_load(w + 2 * TS);
+			while (a.y != tag || b.y != tag || c.y != tag) { if (PROF) ++n_spin; a = ll_load(w); b = ll_load(w + TS); c = ll_load(w + 2 * TS); }
 			s_d[d.n_own + h] = make_float4(__uint_as_float(a.x), __uint_as_float(b.x), __uint_as_float(c.x), 0.f);
 		}
 	};
@@ -252,6 +256,18 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 			const int role = s_role[color * NW + warp];
 			long long t0 = 0, t1 = 0;
 			if (PROF) { t0 = clk_ordered(); if (t_prev_end) po += t0 - t_prev_end; TR(0); }
+			// readers 3 and 4 of a corner node: their slots come from L2 -- asked for now, used after the gather
+			int pre_e0 = 0; unsigned int pre2 = 0u, pre3 = 0u;
+#pragma unroll
+			for (int k = 0; k < KMAX; ++k) {
+				if (S[k].meta < 0 || (S[k].meta & 0x1ff) != (color | 0x100) || S[k].l < 0) continue;
+				const int cnt = (S[k].meta >> 10) & 63;
+				if (cnt > 2) {
+					pre_e0 = __ldg(&R.dest_off[d.own_off + S[k].l]);
+					pre2 = __ldg(&R.dest_slot[pre_e0 + 2]);
+					if (cnt > 3) pre3 = __ldg(&R.dest_slot[pre_e0 + 3]);
+				}
+			}
 			if (role >= 0) {
 				const int n_poll = 32 * (int)s_npoll[color];
 				if (pass > 0 && !(PROF && (R.dbg & 2))) {
@@ -262,16 +278,6 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				}
 				if (PROF) TR(1);
 				named_sync(1, n_poll);
-				if (PROF && pass > 0 && role == 0 && lane == 0) {
-					// publish -> usable, measured with the global timer: against the latest neighbour and against this part itself
-					__threadfence_block();
-					const unsigned long long now = gtime_ns();
-					volatile unsigned long long *pubt = R.prof + 16 * gridDim.x + 1024;
-					unsigned long long m = 0;
-					for (int i = 0; i < d.n_nbr; ++i) { const unsigned long long v = pubt[(size_t)R.nbr[d.nbr_off + i] * 128 + ((pass - 1) & 127)]; m = v > m ? v : m; }
-					const unsigned long long own = pubt[(size_t)(R.part0 + blockIdx.x) * 128 + ((pass - 1) & 127)];
-					if (m) { hop_nbr += (long long)(now - m); hop_own += (long long)(now - own); ++hop_n; }
-				}
 			}
 			if (PROF) { t1 = clk_ordered(); TR(2); }
 #pragma unroll
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				if ((S[k].meta & 0xff) != color || S[k].meta < 0) continue;
 				if (PROF && (R.dbg & 4) && !(S[k].meta & 0x100)) continue; // timing experiment: no interior work
 				float sx, sy, sz;
-				owned_gather(s_val, s_col, s_d, S[k].r0, S[k].r1, lane, sx, sy, sz);
+				owned_gather(s_val, s_col, s_d, S[k].r0, (PROF && (R.dbg & 32)) ? S[k].r0 : S[k].r1, lane, sx, sy, sz);
 				const int l = S[k].l;
 				if (l < 0) continue;
 				const float4 dold = s_d[l];
@@ -307,16 +313,18 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				}
 				s_d[l] = dn;
 				if ((S[k].meta & 0x100) && !(PROF && (R.dbg & 16))) {
-					const size_t at = pub_off + 3 * (size_t)S[k].gid;
-					uint2 *w = R.dglob + at;
-					ll_store(w, dn.x, pass_tag); ll_store(w + 1, dn.y, pass_tag); ll_store(w + 2, dn.z, pass_tag);
-					if (PROF && lane == 0) ((volatile unsigned long long *)(R.prof + 16 * gridDim.x + 1024))[(size_t)(R.part0 + blockIdx.x) * 128 + (pass & 127)] = gtime_ns();
-					unsigned int dm = S[k].dm;
-					while (dm) { // peers that read this node
-						const int q = __ffs(dm) - 1; dm &= dm - 1;
-						uint2 *wq = R.peer_dglob[q] + at;
-						ll_store_sys(wq, dn.x, pass_tag); ll_store_sys(wq + 1, dn.y, pass_tag); ll_store_sys(wq + 2, dn.z, pass_tag);
-					}
+					const int cnt = (S[k].meta >> 10) & 63;
+					auto put = [&](unsigned int ent) {
+						const unsigned int q = ent >> 27;
+						const size_t at = pub_off + (size_t)(ent & 0x7ffffffu);
+						if ((int)q == R.rank) { uint2 *w = R.dglob + at; ll_store(w, dn.x, pass_tag); ll_store(w + TS, dn.y, pass_tag); ll_store(w + 2 * TS, dn.z, pass_tag); }
+						else { uint2 *w = R.peer_dglob[q] + at; ll_store_sys(w, dn.x, pass_tag); ll_store_sys(w + TS, dn.y, pass_tag); ll_store_sys(w + 2 * TS, dn.z, pass_tag); }
+					};
+					if (cnt > 0) put(S[k].dst0);
+					if (cnt > 1) put(S[k].dst1);
+					if (cnt > 2) put(pre2); // a corner node read by more than two parts
+					if (cnt > 3) put(pre3);
+					for (int e = pre_e0 + 4; e < pre_e0 + cnt; ++e) put(__ldg(&R.dest_slot[e]));
 				}
 			}
 			long long t2 = 0;

@@ -42,6 +42,8 @@ struct McgsRes32Params {
 	// Boundary values are also pushed into the peers that read them (stores over NVLink into their dglob /
 	// x arrays, mapped through CUDA IPC); nothing is ever READ from a peer, so spinning stays local.
 	int part0, world, rank;
+	// mailboxes of the static-ownership kernel (partition.hpp, plan_mailboxes); dglob is then [2][3][total_slots]
+	const int *dest_off; const unsigned int *dest_slot; int total_slots;
 	int dbg; // timing experiments only (ADMM_B200_GS_DBG, tools/gs_prof.py): 1 no tag wait, 2 no refresh, 4 no interior, 8 no boundary
 	const unsigned int *dest_mask; // [n_nodes] ranks (bit q) that read this node as halo; NULL when world == 1
 	uint2 *peer_dglob[ADMMB200_MAX_RANKS];

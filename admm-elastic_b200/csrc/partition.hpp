@@ -39,7 +39,8 @@ struct PartDesc {
 	int nbr_off, n_nbr;                  // into nbr[]: parts this part exchanges halo values with
 	int own_off;                         // number of nodes owned by the parts before this one
 	int hcolor_off;                      // into halo_color[] (n_colors + 1 entries): halo nodes are sorted by colour
-	int pad_[2];
+	int slot_off;                        // first mailbox slot of this part: slot_off + h receives the value of halo node h
+	int pad_[1];
 };
 
 struct ResidentPlan {
@@ -50,6 +51,12 @@ struct ResidentPlan {
 	std::vector<int> gid, slice_row, color_slice, nbr, halo_color;
 	std::vector<short> slice_node;
 	std::vector<int> part_of;      // node -> part (for tests / diagnostics)
+	// Mailboxes (mcgs_owned_f32.cuh): every part has one slot per halo node, in its own halo order, so the
+	// reader's polls are coalesced.  A boundary node is written into the slot of every part that reads it:
+	// dest_off[own_off + l] .. dest_off[own_off + l + 1] indexes dest_slot[], entry = slot | rank << 27.
+	std::vector<int> dest_off;
+	std::vector<unsigned int> dest_slot;
+	size_t total_slots = 0;
 	size_t max_nbr = 0;
 	size_t max_rows = 0, max_own = 0, max_halo = 0, max_slices = 0, entries = 0, nnz = 0;
 	// dynamic shared memory one CTA needs with `val_bytes`-wide matrix values
@@ -152,17 +159,22 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 	std::vector<int> local_of(n, -1);
 	R.parts.resize(n_parts);
 	int own_running = 0;
+	// colour-major, long rows first inside a colour (uniform slices -> little ELL padding), ids last
+	// and inside a colour the interior nodes first: they are updated while the neighbours' flags of
+	// the previous pass are still in flight
+	std::vector<int> owner_local(n, 0); // position of a node in its owner's order
 	for (int p = 0; p < n_parts; ++p) {
 		std::vector<int> &nodes = own[p];
-		// colour-major, long rows first inside a colour (uniform slices -> little ELL padding), ids last
-		// and inside a colour the interior nodes first: they are updated while the neighbours' flags of
-		// the previous pass are still in flight
 		std::sort(nodes.begin(), nodes.end(), [&](int a, int b) {
 			if (color_of[a] != color_of[b]) return color_of[a] < color_of[b];
 			if (boundary[a] != boundary[b]) return boundary[a] < boundary[b];
 			if (rowlen[a] != rowlen[b]) return rowlen[a] > rowlen[b];
 			return a < b;
 		});
+		for (size_t l = 0; l < nodes.size(); ++l) owner_local[nodes[l]] = (int)l;
+	}
+	for (int p = 0; p < n_parts; ++p) {
+		std::vector<int> &nodes = own[p];
 		PartDesc d;
 		std::memset(&d, 0, sizeof(d));
 		d.n_own = (int)nodes.size();
@@ -174,8 +186,8 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 		d.cslice_off = (int)R.color_slice.size();
 		d.ent_off = (long long)R.col.size();
 		for (int l = 0; l < d.n_own; ++l) { local_of[nodes[l]] = l; R.gid.push_back(nodes[l]); }
-		// halo nodes, sorted by colour (then id): after a pass only the halo nodes of that pass's colour
-		// have new values, and they are contiguous
+		// halo nodes, sorted by colour: after a pass only the halo nodes of that pass's colour have new
+		// values, and they are contiguous ...
 		std::vector<int> halo;
 		for (int l = 0; l < d.n_own; ++l) {
 			const int node = nodes[l];
@@ -186,7 +198,13 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 				halo.push_back(g);
 			}
 		}
-		std::sort(halo.begin(), halo.end(), [&](int a, int b) { return color_of[a] != color_of[b] ? color_of[a] < color_of[b] : a < b; });
+		// ... and inside a colour by owner part and the owner's own order: the nodes one neighbour publishes
+		// to this part then sit in consecutive mailbox slots, so its stores coalesce (plan_mailboxes)
+		std::sort(halo.begin(), halo.end(), [&](int a, int b) {
+			if (color_of[a] != color_of[b]) return color_of[a] < color_of[b];
+			if (R.part_of[a] != R.part_of[b]) return R.part_of[a] < R.part_of[b];
+			return owner_local[a] < owner_local[b];
+		});
 		d.hcolor_off = (int)R.halo_color.size();
 		{
 			size_t h = 0;
@@ -266,6 +284,32 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 	}
 	R.entries = R.col.size();
 	return R;
+}
+
+// Fills the mailbox tables of a plan.  parts_per_rank: parts [r * parts_per_rank, ...) run on rank r (n_parts for one GPU).
+inline void plan_mailboxes(ResidentPlan &R, int n_nodes, int parts_per_rank)
+{
+	size_t slots = 0;
+	for (PartDesc &d : R.parts) { d.slot_off = (int)slots; slots += (size_t)d.n_halo; }
+	if (slots >= ((size_t)1 << 27)) throw std::runtime_error("resident plan: too many halo slots");
+	R.total_slots = slots;
+	// node -> position in the owner-ordered numbering (own_off + local id)
+	std::vector<int> owner_pos((size_t)n_nodes, -1);
+	for (const PartDesc &d : R.parts) for (int l = 0; l < d.n_own; ++l) owner_pos[R.gid[d.gid_off + l]] = d.own_off + l;
+	std::vector<int> count((size_t)n_nodes + 1, 0);
+	for (const PartDesc &d : R.parts) for (int h = 0; h < d.n_halo; ++h) ++count[owner_pos[R.gid[d.gid_off + d.n_own + h]] + 1];
+	R.dest_off.assign((size_t)n_nodes + 1, 0);
+	for (int i = 0; i < n_nodes; ++i) R.dest_off[i + 1] = R.dest_off[i] + count[i + 1];
+	R.dest_slot.assign(slots ? slots : 1, 0u);
+	std::vector<int> fill(R.dest_off.begin(), R.dest_off.end() - 1);
+	for (int p = 0; p < R.n_parts; ++p) {
+		const PartDesc &d = R.parts[p];
+		const unsigned int rank = (unsigned int)(p / parts_per_rank);
+		for (int h = 0; h < d.n_halo; ++h) {
+			const int pos = owner_pos[R.gid[d.gid_off + d.n_own + h]];
+			R.dest_slot[fill[pos]++] = (unsigned int)(d.slot_off + h) | (rank << 27);
+		}
+	}
 }
 
 // Multi-GPU: parts [r * parts_per_rank, (r+1) * parts_per_rank) live on rank r.  For every node owned by
