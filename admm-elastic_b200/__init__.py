@@ -198,6 +198,12 @@ class DeviceSolver(object):
         self._ck(_cuda.admm_b200_time_kernels(self.h, int(reps), _dp(out)))
         return {"local_ms": out[0], "assemble_ms": out[1], "global_ms": out[2]}
 
+    def kernel_times(self):
+        """Kernel-only times of the last timed step: {name: (summed ms, launches)} (admm_b200_kernel_times)."""
+        ms, n = np.zeros(3), np.zeros(3, dtype=np.int64)
+        self._ck(_cuda.admm_b200_kernel_times(self.h, _dp(ms), n.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
+        return {"tet_local_kernel": (ms[0], int(n[0])), "assemble_kernel": (ms[1], int(n[1])), "solve_kernel": (ms[2], int(n[2]))}
+
     def info(self):
         return _cuda.admm_b200_solver_info(self.h).decode()
 

@@ -61,7 +61,8 @@ struct TetBatchH {
 	size_t slot_base = 0;
 	DevBuf<int4> d_idx;
 	DevBuf<char> d_dminv, d_wdt2, d_u, d_z; // element precision, raw bytes
-	DevBuf<int> d_defer;                    // [1 + n]: counter, then the queue of degenerate elements
+	DevBuf<char> d_q;                       // [4][n_pad] SVD warm start (quaternions), zero = no guess
+	DevBuf<int> d_defer;                    // [2 + n]: counter, the queue of degenerate elements, consumer blocks done
 };
 struct TriBatchH {
 	int n = 0, n_pad = 0;
@@ -147,6 +148,12 @@ struct admm_b200_solver {
 	DevBuf<double> res_val64;
 	DevBuf<unsigned long long> res_prof; // ADMM_B200_GS_PROF=1: per-part cycle counters of the last solve
 	DevBuf<unsigned int> res_sync; // part_epoch [8 * n_sms] | sweep_flag [iters] | sweep_arrive [iters]
+	// everything the resident solve needs zeroed per launch, in one allocation (one memset per solve):
+	// residual slots (doubles) | grid barrier counter (padded) | res_sync layout
+	DevBuf<double> res_scratch; size_t res_scratch_resid_n = 0;
+	// kernel-only timing (admm_b200_kernel_times)
+	bool fine_on = false; std::vector<cudaEvent_t> fine_pool; size_t fine_used = 0; std::vector<int> fine_kind;
+	double kernel_ms[3] = {0, 0, 0}; long long kernel_n[3] = {0, 0, 0};
 	DevBuf<short> res_slice_node;
 	std::vector<double> h_x0; // rest positions (partitioning)
 	std::string gs_info;
@@ -193,6 +200,8 @@ struct admm_b200_solver {
 namespace {
 
 typedef admm_b200_solver S;
+void fine_begin(S *s, int kind);
+void fine_end(S *s);
 
 template <typename F> int guard(S *s, F fn)
 {
@@ -231,19 +240,21 @@ template <typename E, int MODEL> void launch_tet_model(S *s, TetBatchH *t)
 	tb.wdt2 = (const E *)t->d_wdt2.p;
 	tb.u = (E *)t->d_u.p;
 	tb.z = (E *)t->d_z.p;
+	tb.q = (E *)t->d_q.p;
 	tb.f = (typename Vec4<E>::type *)s->f.p + t->slot_base;
 	tb.mat = Material<E>::make(t->mu, t->lambda, t->kappa);
-	tb.defer_count = t->d_defer.p; tb.defer_list = t->d_defer.p + 1;
+	tb.defer_count = t->d_defer.p; tb.defer_list = t->d_defer.p + 1; tb.defer_done = t->d_defer.p + 1 + t->n;
 	const int threads = 128;
 	int blocks = (t->n + threads - 1) / threads;
 	const bool sz = s->store_z && t->d_z.p;
-	if (MODEL != TET_LINEAR) CK(cudaMemsetAsync(t->d_defer.p, 0, sizeof(int), s->stream));
+	fine_begin(s, 0);
 	if (sz) tet_local_kernel<E, MODEL, true, 4><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else if (sizeof(E) == 8) tet_local_kernel<E, MODEL, false, 4><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else if (s->tet_minblocks >= 8) tet_local_kernel<E, MODEL, false, 8><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else if (s->tet_minblocks >= 6) tet_local_kernel<E, MODEL, false, 6><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else tet_local_kernel<E, MODEL, false, 5><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	CK(cudaGetLastError());
+	fine_end(s);
 	s->launches++;
 	if (MODEL != TET_LINEAR) {
 		// degenerate elements queued by the kernel above (usually none)
@@ -308,11 +319,13 @@ void launch_local(S *s)
 void launch_assemble(S *s)
 {
 	int n = s->n_nodes;
+	fine_begin(s, 1);
 	if (s->precision == ADMM_B200_FP64)
 		assemble_kernel<double><<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->inc_off.p, s->inc_slot.p, (const double4 *)s->f.p, s->pins.d_f.p, s->mxbar.p, s->b.p);
 	else
 		assemble_kernel<float><<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->inc_off.p, s->inc_slot.p, (const float4 *)s->f.p, s->pins.d_f.p, s->mxbar.p, s->b.p);
 	CK(cudaGetLastError());
+	fine_end(s);
 	s->launches++;
 }
 
@@ -331,7 +344,7 @@ template <int T> int mcgs_occupancy()
 	return nb;
 }
 
-void fill_mcgs_params(S *s, McgsParams &P);
+void fill_mcgs_params(S *s, McgsParams &P, bool zero_scratch = true);
 
 // precision FP64: positions in shared memory as doubles (mcgs_resident_kernel<double>);
 // precision FP32: fp32 sweeps on the increment around the fp64 anchor (mcgs_resident_f32_kernel)
@@ -370,9 +383,13 @@ void launch_mcgs_resident(S *s)
 	McgsResParams R;
 	McgsRes32Params R32;
 	McgsParams &B = fp64 ? R.base : R32.base;
-	fill_mcgs_params(s, B);
-	unsigned int *part_epoch = s->res_sync.p, *sweep_flag = s->res_sync.p + 8 * (size_t)s->n_sms, *sweep_arrive = sweep_flag + s->gs_iters;
-	CK(cudaMemsetAsync(s->res_sync.p, 0, s->res_sync.n * sizeof(unsigned int), s->stream));
+	fill_mcgs_params(s, B, false);
+	// scratch: [resid doubles][barrier: 2 uints][part_epoch 8 n_sms | sweep_flag iters | sweep_arrive iters]
+	CK(cudaMemsetAsync(s->res_scratch.p, 0, s->res_scratch.n * sizeof(double), s->stream));
+	B.resid = s->res_scratch.p; B.resid_lb = s->res_scratch.p + (s->gs_iters + 2);
+	unsigned int *scr_u = (unsigned int *)(s->res_scratch.p + s->res_scratch_resid_n);
+	B.barrier = scr_u;
+	unsigned int *part_epoch = scr_u + 2, *sweep_flag = part_epoch + 8 * (size_t)s->n_sms, *sweep_arrive = sweep_flag + s->gs_iters;
 	void *args[1];
 	if (fp64) {
 		R.parts = s->res_parts.p; R.col = s->res_col.p; R.val = s->res_val.p; R.gid = s->res_gid.p;
@@ -397,15 +414,17 @@ void launch_mcgs_resident(S *s)
 		if (s->world > 1) { require(s->mg_ready, "multi-GPU solver used before admm_b200_mgpu_ready"); R32.base.tol2 = 0.0; }
 		args[0] = &R32;
 	}
+	fine_begin(s, 2);
 	if (!fp64 && s->gs_owned_threads > 0) {
 		const void *kern = owned_kernel_ptr(s->gs_owned_threads, !s->obstacles.empty(), s->res_prof.p != nullptr);
 		CK(cudaLaunchCooperativeKernel(kern, dim3(s->n_sms), dim3(s->gs_owned_threads), args, s->gs_res_smem, s->stream));
 	} else
 		CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes, s->res_prof.p != nullptr), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
+	fine_end(s);
 	s->launches++;
 }
 
-void fill_mcgs_params(S *s, McgsParams &P)
+void fill_mcgs_params(S *s, McgsParams &P, bool zero_scratch)
 {
 	P.n_nodes = s->n_nodes; P.n_colors = s->n_colors; P.iters = s->gs_iters; P.omega = s->gs_omega;
 	P.tol2 = s->gs_tol > 0 ? s->gs_tol * s->gs_tol : 0.0;
@@ -415,6 +434,7 @@ void fill_mcgs_params(S *s, McgsParams &P)
 	P.n_obstacles = (int)s->obstacles.size();
 	P.obs = s->d_obstacles.p;
 	P.x = s->cx.p; P.b = s->b.p; P.barrier = s->barrier.p; P.resid = s->gs_resid.p; P.resid_lb = s->gs_resid.p + (s->gs_iters + 2); P.iters_done = s->gs_iters_done.p;
+	if (!zero_scratch) return; // the resident solve zeroes its own scratch block in one go
 	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
 	if (P.tol2 > 0) CK(cudaMemsetAsync(s->gs_resid.p, 0, s->gs_resid.n * sizeof(double), s->stream));
 }
@@ -424,12 +444,14 @@ void launch_mcgs(S *s)
 	if (s->gs_resident) { launch_mcgs_resident(s); return; }
 	McgsParams P;
 	fill_mcgs_params(s, P);
+	fine_begin(s, 2);
 	switch (s->gs_lanes) {
 	case 1: mcgs_launch_T<1>(s, P); break;
 	case 2: mcgs_launch_T<2>(s, P); break;
 	case 8: mcgs_launch_T<8>(s, P); break;
 	default: mcgs_launch_T<4>(s, P); break;
 	}
+	fine_end(s);
 	s->launches++;
 }
 
@@ -448,12 +470,14 @@ void launch_ldlt(S *s)
 	P.bwd_level_ptr = s->d_bwd_level_ptr.p; P.bwd_rows = s->d_bwd_rows.p; P.bwd_rowptr = s->d_bwd_rowptr.p; P.bwd_cols = s->d_bwd_cols.p; P.bwd_vals = s->d_bwd_vals.p;
 	P.dinv_unused = nullptr; P.D = s->d_ld_D.p; P.y = s->d_ld_y.p; P.b = s->b.p; P.x = s->cx.p; P.barrier = s->barrier.p;
 	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
+	fine_begin(s, 2);
 	switch (s->ld_lanes) {
 	case 1: ldlt_launch_T<1>(s, P); break;
 	case 2: ldlt_launch_T<2>(s, P); break;
 	case 8: ldlt_launch_T<8>(s, P); break;
 	default: ldlt_launch_T<4>(s, P); break;
 	}
+	fine_end(s);
 	s->launches++;
 }
 
@@ -512,8 +536,20 @@ void build_incidence(S *s)
 		for (int e = 0; e < t->n; ++e)
 			for (int c = 0; c < 3; ++c) slot[fill[t->idx[3 * e + c]]++] = (int)(t->slot_base + 3 * (size_t)e + c);
 	for (int i = 0; i < s->pins.n; ++i) slot[fill[s->pins.idx[i]]++] = (int)(0x80000000u | (unsigned)i);
-	s->inc_off.upload(off, s->stream);
-	s->inc_slot.upload(slot, s->stream);
+	// sliced + transposed for the kernel (kernels.cuh, assemble_kernel): warp w owns vertices [32 w, 32 w + 32)
+	const int n_warps = (n + 31) / 32;
+	std::vector<int> woff(n_warps + 1, 0);
+	for (int w = 0; w < n_warps; ++w) {
+		int width = 0;
+		for (int l = 0; l < 32 && 32 * w + l < n; ++l) width = std::max(width, off[32 * w + l + 1] - off[32 * w + l]);
+		woff[w + 1] = woff[w] + width;
+	}
+	std::vector<int> tslot((size_t)woff[n_warps] * 32, ADMMB200_NO_SLOT);
+	for (int i = 0; i < n; ++i)
+		for (int k = off[i]; k < off[i + 1]; ++k) tslot[((size_t)woff[i >> 5] + (k - off[i])) * 32 + (i & 31)] = slot[k];
+	if (tslot.empty()) tslot.push_back(ADMMB200_NO_SLOT);
+	s->inc_off.upload(woff, s->stream);
+	s->inc_slot.upload(tslot, s->stream);
 	CK(cudaStreamSynchronize(s->stream));
 }
 
@@ -531,8 +567,11 @@ template <typename E> void upload_elements(S *s)
 		for (int e = 0; e < t->n; ++e) w2[e] = dt2 * t->w[e] * t->w[e];
 		upload_soa<E>(t->d_wdt2, w2, t->n, t->n_pad, 1, s->stream);
 		t->d_u.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_u.zero(s->stream);
+		// SVD warm start (prox.cuh, svd3_signed): measured on the 1M-tet beam it LOSES 2 us of 60 (the sweeps saved
+		// cost less than the extra 32 B/tet and the quaternion conversions), so it is opt-in
+		if (getenv("ADMM_B200_SVD_WARMSTART")) { t->d_q.alloc((size_t)4 * t->n_pad * sizeof(E)); t->d_q.zero(s->stream); }
 		if (s->store_z) { t->d_z.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_z.zero(s->stream); }
-		t->d_defer.alloc((size_t)t->n + 1); t->d_defer.zero(s->stream);
+		t->d_defer.alloc((size_t)t->n + 2); t->d_defer.zero(s->stream);
 	}
 	for (auto t : s->tris) {
 		t->n_pad = pad32(t->n);
@@ -651,6 +690,8 @@ void build_mcgs_resident(S *s)
 		s->res_nodebuf.alloc(2 * (size_t)s->n_nodes); s->res_nodebuf.zero(s->stream);
 	}
 	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
+	s->res_scratch_resid_n = 2 * (size_t)s->gs_iters + 4;
+	s->res_scratch.alloc(s->res_scratch_resid_n + (2 + 8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1) + 1) / 2 + 1);
 	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
 	if (prof) { s->res_prof.alloc(16 * (size_t)s->n_sms + 1024 + 128 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
 	if (val_bytes == 8) {
@@ -823,6 +864,23 @@ void build_ldlt(S *s)
 	s->ld_grid = s->n_sms;
 }
 
+// Events tightly around the hot kernels (timers on): kind 0 tet prox, 1 assemble, 2 solve.  Summed after the step.
+void fine_begin(S *s, int kind)
+{
+	if (!s->fine_on) return;
+	cudaEvent_t a, b;
+	if (s->fine_pool.size() < s->fine_used + 2) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); s->fine_pool.push_back(a); s->fine_pool.push_back(b); }
+	a = s->fine_pool[s->fine_used];
+	CK(cudaEventRecord(a, s->stream));
+	s->fine_kind.push_back(kind);
+}
+void fine_end(S *s)
+{
+	if (!s->fine_on) return;
+	CK(cudaEventRecord(s->fine_pool[s->fine_used + 1], s->stream));
+	s->fine_used += 2;
+}
+
 cudaEvent_t get_event(S *s, size_t i)
 {
 	while (s->events.size() <= i) { cudaEvent_t e; CK(cudaEventCreate(&e)); s->events.push_back(e); }
@@ -847,6 +905,7 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 	s->launches++;
 	zero_duals(s); // curr_u = 0 every step (src/Solver.cpp:71)
 	size_t ev = 0;
+	s->fine_on = rt != nullptr; s->fine_used = 0; s->fine_kind.clear();
 	// events per ADMM iteration: [4it] local [4it+1] assemble [4it+2] solve [4it+3]
 	for (int it = 0; it < admm_iters; ++it) {
 		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
@@ -866,6 +925,7 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 	step_end_kernel<<<nb, 256, 0, s->stream>>>(n, s->dt, s->x.p, s->v.p, s->cx.p);
 	CK(cudaGetLastError());
 	s->launches++;
+	s->fine_on = false;
 	if (rt) {
 		cudaEvent_t e_end = get_event(s, ev++);
 		CK(cudaEventRecord(e_end, s->stream));
@@ -879,6 +939,12 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 			rt->local_ms += a; rt->assemble_ms += b; rt->global_ms += b + c;
 		}
 		if (admm_iters > 0) { float t = 0; CK(cudaEventElapsedTime(&t, s->events[0], e_end)); rt->step_ms = t; }
+		for (int k = 0; k < 3; ++k) { s->kernel_ms[k] = 0; s->kernel_n[k] = 0; }
+		for (size_t i = 0; i < s->fine_kind.size() && 2 * i + 1 < s->fine_used + 1; ++i) {
+			float t = 0;
+			CK(cudaEventElapsedTime(&t, s->fine_pool[2 * i], s->fine_pool[2 * i + 1]));
+			s->kernel_ms[s->fine_kind[i]] += t; s->kernel_n[s->fine_kind[i]]++;
+		}
 		if (s->linsolver == ADMM_B200_MCGS) {
 			std::vector<int> its(admm_iters);
 			if (admm_iters) CK(cudaMemcpy(its.data(), s->iter_log.p, sizeof(int) * admm_iters, cudaMemcpyDeviceToHost));
@@ -1448,6 +1514,14 @@ int admm_b200_time_kernels(admm_b200_solver *s, int reps, double *out_ms)
 }
 
 long long admm_b200_launch_count(const admm_b200_solver *s) { return s ? s->launches : 0; }
+
+int admm_b200_kernel_times(admm_b200_solver *s, double *out_ms, long long *out_n)
+{
+	return guard(s, [&]() {
+		require(out_ms && out_n, "kernel_times: bad arguments");
+		for (int k = 0; k < 3; ++k) { out_ms[k] = s->kernel_ms[k]; out_n[k] = s->kernel_n[k]; }
+	});
+}
 
 // Host-only check of the resident plan (no device): builds the plan, walks it exactly like
 // mcgs_resident_kernel's gather and returns max |(L_offdiag x)_plan - (L_offdiag x)_csr| over all nodes

@@ -82,10 +82,12 @@ struct TetBatch {
 	const E *wdt2;            // [n_pad]   dt^2 w^2
 	E *u;                     // [9][n_pad]
 	E *z;                     // [9][n_pad] or NULL
+	E *q;                     // [4][n_pad] V of the element's last SVD as a quaternion (warm start, see svd3_signed), or NULL
 	typename Vec4<E>::type *f; // [4n]
 	Material<E> mat;
 	int *defer_count;         // queue of degenerate elements (see prox.cuh, PROX_FAST / PROX_REFERENCE)
 	int *defer_list;          // [n]
+	int *defer_done;          // blocks of the consumer kernel that have finished (the last one empties the queue)
 };
 
 // One element of the local step.  MODE = PROX_FAST: the hot kernel; a degenerate element is queued and
@@ -103,6 +105,11 @@ __device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4
 #pragma unroll
 	for (int k = 0; k < 9; ++k) u[k] = tb.u[(size_t)k * np + e];
 	const E w = __ldg(&tb.wdt2[e]);
+	E q[4] = {E(0), E(0), E(0), E(0)};
+	if (tb.q) {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) q[k] = tb.q[(size_t)k * np + e];
+	}
 	double4 p0 = ld_node(&cx[id.x]), p1 = ld_node(&cx[id.y]), p2 = ld_node(&cx[id.z]), p3 = ld_node(&cx[id.w]);
 	// Ds = [x1-x0, x2-x0, x3-x0], differences in fp64 (positions are ~metres, edges ~centimetres)
 	E ds[9] = {E(p1.x - p0.x), E(p1.y - p0.y), E(p1.z - p0.z), E(p2.x - p0.x), E(p2.y - p0.y), E(p2.z - p0.z), E(p3.x - p0.x), E(p3.y - p0.y), E(p3.z - p0.z)};
@@ -115,9 +122,13 @@ __device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4
 			F[3 * r + j] = ds[j] * bi[r] + ds[3 + j] * bi[3 + r] + ds[6 + j] * bi[6 + r];
 			z[3 * r + j] = F[3 * r + j] + u[3 * r + j];
 		}
-	if (prox_tet_mode<E, MODEL, MODE>(tb.mat, z)) {
+	if (prox_tet_mode<E, MODEL, MODE>(tb.mat, z, tb.q ? q : nullptr)) {
 		tb.defer_list[atomicAdd(tb.defer_count, 1)] = e; // MODE == PROX_FAST only
 		return;
+	}
+	if (tb.q) {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) tb.q[(size_t)k * np + e] = q[k];
 	}
 	// u += Dx - z ; y = z - u_new
 	E y[9];
@@ -159,6 +170,13 @@ __global__ void __launch_bounds__(128) tet_local_deferred_kernel(TetBatch<E> tb,
 	const int count = *tb.defer_count;
 	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
 		tet_element<E, MODEL, STORE_Z, PROX_REFERENCE>(tb, cx, tb.defer_list[k]);
+	// the last block to finish empties the queue for the next local step (every block has read `count` by then),
+	// so the hot kernel needs no memset in front of it
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(tb.defer_done, 1) == (int)gridDim.x - 1) { *tb.defer_count = 0; *tb.defer_done = 0; }
+	}
 }
 
 // prox alone on raw deformation gradients (parity tests / micro-benchmarks): zio is [9][n_pad] SoA
@@ -298,20 +316,27 @@ __global__ void pin_local_kernel(PinBatch pb, const double4 *__restrict__ cx)
 
 // ---------------------------------------------------------------------------------------------
 // global step 1: b = M x_bar + dt^2 D^T W^2 (z-u)   (src/Solver.cpp:98), per-vertex segmented sum
-// over the corner shares written by the local kernels.  inc_slot entries: bits 0..28 slot, bits
-// 29..30 which share array (0 = element precision tets/tris, 1 = fp64 pins).
+// over the corner shares written by the local kernels, always in the same order (no float atomics).
+// Incidence: sliced and transposed per warp -- the 32 vertices of a warp share rows [inc_off[w], inc_off[w+1]),
+// row j holds the j-th corner of each of them (inc_slot[row * 32 + lane]), so the index loads are coalesced and
+// independent of each other.  Entry >= 0: slot in the element-precision share array; < 0: fp64 pin share
+// (low 31 bits); ADMMB200_NO_SLOT: padding.
 // ---------------------------------------------------------------------------------------------
+#define ADMMB200_NO_SLOT 0x7fffffff
 template <typename E>
 __global__ void __launch_bounds__(256) assemble_kernel(int n, const int *__restrict__ inc_off, const int *__restrict__ inc_slot,
 	const typename Vec4<E>::type *__restrict__ f, const double4 *__restrict__ fpin, const double4 *__restrict__ mxbar, double4 *__restrict__ b)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	double4 acc = mxbar[i];
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int w = i >> 5, lane = threadIdx.x & 31;
+	if (w * 32 >= n) return;
+	const int r0 = __ldg(&inc_off[w]), r1 = __ldg(&inc_off[w + 1]);
 	double sx = 0, sy = 0, sz = 0;
-	int k0 = inc_off[i], k1 = inc_off[i + 1];
-	for (int k = k0; k < k1; ++k) {
-		int s = __ldg(&inc_slot[k]);
+	const int *sl = inc_slot + (size_t)r0 * 32 + lane;
+#pragma unroll 4
+	for (int r = 0; r < r1 - r0; ++r) {
+		const int s = __ldg(sl + (size_t)r * 32);
+		if (s == ADMMB200_NO_SLOT) continue;
 		if (s >= 0) {
 			typename Vec4<E>::type v = f[s];
 			sx += double(v.x); sy += double(v.y); sz += double(v.z);
@@ -320,6 +345,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(int n, const int *__restr
 			sx += v.x; sy += v.y; sz += v.z;
 		}
 	}
+	if (i >= n) return;
+	const double4 acc = mxbar[i];
 	st_node(&b[i], acc.x + sx, acc.y + sy, acc.z + sz);
 }
 

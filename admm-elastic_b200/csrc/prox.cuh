@@ -102,18 +102,40 @@ ADMMB200_FN void jacobi_rot(T &app, T &aqq, T &apq, T &arp, T &arq,
 // F (column-major, F[3c+r] = F(r,c)) = U diag(S) V^T with U, V in SO(3), S[0] >= S[1] >= |S[2]|,
 // sign(S[2]) = sign(det F): the convention signed_svd (src/FastSVD.hpp:43-68) produces.
 // U, V are column-major too.
+//
+// Warm start: q (in/out, may be null) is V of the previous call for this element as a quaternion (w,x,y,z),
+// not necessarily normalised; all zeros = no guess.  Between two ADMM iterations F + u moves little, so
+// V0^T (F^T F) V0 is already nearly diagonal and the Jacobi iteration needs one or two sweeps instead of
+// four.  A quaternion (normalised on load) cannot drift away from a rotation, however often it is reused.
 template <typename T>
-ADMMB200_FN void svd3_signed(const T *F, T *S, T *U, T *V)
+ADMMB200_FN void svd3_signed(const T *F, T *S, T *U, T *V, T *q = nullptr)
 {
-	// C = F^T F
-	T c00 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
-	T c01 = F[0] * F[3] + F[1] * F[4] + F[2] * F[5];
-	T c02 = F[0] * F[6] + F[1] * F[7] + F[2] * F[8];
-	T c11 = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
-	T c12 = F[3] * F[6] + F[4] * F[7] + F[5] * F[8];
-	T c22 = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
 	// V(r,c): v{r}{c}
 	T v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+	T c00, c01, c02, c11, c12, c22;
+	if (q) {
+		const T qq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+		const bool have = qq > Num<T>::tiny();
+		const T n = Num<T>::rsqrt(have ? qq : T(1));
+		const T w = have ? q[0] * n : T(1), x = q[1] * n, y = q[2] * n, z = q[3] * n;
+		v00 = T(1) - T(2) * (y * y + z * z); v01 = T(2) * (x * y - w * z); v02 = T(2) * (x * z + w * y);
+		v10 = T(2) * (x * y + w * z); v11 = T(1) - T(2) * (x * x + z * z); v12 = T(2) * (y * z - w * x);
+		v20 = T(2) * (x * z - w * y); v21 = T(2) * (y * z + w * x); v22 = T(1) - T(2) * (x * x + y * y);
+		// C = (F V0)^T (F V0)
+		const T b00 = F[0] * v00 + F[3] * v10 + F[6] * v20, b10 = F[1] * v00 + F[4] * v10 + F[7] * v20, b20 = F[2] * v00 + F[5] * v10 + F[8] * v20;
+		const T b01 = F[0] * v01 + F[3] * v11 + F[6] * v21, b11 = F[1] * v01 + F[4] * v11 + F[7] * v21, b21 = F[2] * v01 + F[5] * v11 + F[8] * v21;
+		const T b02 = F[0] * v02 + F[3] * v12 + F[6] * v22, b12 = F[1] * v02 + F[4] * v12 + F[7] * v22, b22 = F[2] * v02 + F[5] * v12 + F[8] * v22;
+		c00 = b00 * b00 + b10 * b10 + b20 * b20; c01 = b00 * b01 + b10 * b11 + b20 * b21; c02 = b00 * b02 + b10 * b12 + b20 * b22;
+		c11 = b01 * b01 + b11 * b11 + b21 * b21; c12 = b01 * b02 + b11 * b12 + b21 * b22; c22 = b02 * b02 + b12 * b12 + b22 * b22;
+	} else {
+		// C = F^T F
+		c00 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+		c01 = F[0] * F[3] + F[1] * F[4] + F[2] * F[5];
+		c02 = F[0] * F[6] + F[1] * F[7] + F[2] * F[8];
+		c11 = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
+		c12 = F[3] * F[6] + F[4] * F[7] + F[5] * F[8];
+		c22 = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+	}
 #pragma unroll 1
 	for (int sweep = 0; sweep < Num<T>::jacobi_sweeps; ++sweep) {
 		jacobi_rot(c00, c11, c01, c02, c12, v00, v01, v10, v11, v20, v21); // (0,1), r=2
@@ -140,6 +162,16 @@ ADMMB200_FN void svd3_signed(const T *F, T *S, T *U, T *V)
 	ADMMB200_SWAPCOL(c00, c22, v00, v10, v20, v02, v12, v22)
 	ADMMB200_SWAPCOL(c11, c22, v01, v11, v21, v02, v12, v22)
 #undef ADMMB200_SWAPCOL
+	if (q) {
+		// V as an (unnormalised) quaternion: of the four equivalent formulas the one with the largest pivot
+		const T tw = T(1) + v00 + v11 + v22, tx = T(1) + v00 - v11 - v22, ty = T(1) - v00 + v11 - v22, tz = T(1) - v00 - v11 + v22;
+		const T a = v21 - v12, b = v02 - v20, c = v10 - v01, d = v01 + v10, e = v02 + v20, f = v12 + v21;
+		const bool pw = tw >= tx && tw >= ty && tw >= tz, px = !pw && tx >= ty && tx >= tz, py = !pw && !px && ty >= tz;
+		q[0] = pw ? tw : (px ? a : (py ? b : c));
+		q[1] = pw ? a : (px ? tx : (py ? d : e));
+		q[2] = pw ? b : (px ? d : (py ? ty : f));
+		q[3] = pw ? c : (px ? e : (py ? f : tz));
+	}
 	// B = F V
 	T b00 = F[0] * v00 + F[3] * v10 + F[6] * v20, b10 = F[1] * v00 + F[4] * v10 + F[7] * v20, b20 = F[2] * v00 + F[5] * v10 + F[8] * v20;
 	T b01 = F[0] * v01 + F[3] * v11 + F[6] * v21, b11 = F[1] * v01 + F[4] * v11 + F[7] * v21, b21 = F[2] * v01 + F[5] * v11 + F[8] * v21;
@@ -533,10 +565,10 @@ ADMMB200_SLOWPATH void prox_lbfgs_reference(double mu, double lambda, double kap
 enum ProxMode { PROX_INLINE = 0, PROX_FAST = 1, PROX_REFERENCE = 2 };
 
 template <typename T, int MODEL, int MODE>
-ADMMB200_FN bool prox_tet_mode(const Material<T> &m, T *z)
+ADMMB200_FN bool prox_tet_mode(const Material<T> &m, T *z, T *q = nullptr)
 {
 	T S[3], U[9], V[9];
-	svd3_signed(z, S, U, V);
+	svd3_signed(z, S, U, V, q);
 	if (MODEL == TET_LINEAR) {
 		// TetEnergyTerm::prox (src/TetEnergyTerm.cpp:73-92): p = U diag(1,1,sign det F) V^T with
 		// Eigen's unsigned factors = U V^T with the proper rotations computed here; z = (p+z)/2.

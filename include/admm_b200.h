@@ -176,6 +176,12 @@ int admm_b200_set_debug( admm_b200_solver *s, int store_z );
  * global (solve) in out_ms[3].  Used by bench.py for the roofline numbers. */
 int admm_b200_time_kernels( admm_b200_solver *s, int reps, double *out_ms );
 
+/* Kernel-only device times of the last timed step (admm_b200_step* with a runtime pointer): CUDA events recorded on
+ * the solver's stream immediately before and after each launch of the three hot kernels -- [0] tet prox kernel
+ * (without its queue consumer), [1] assemble kernel, [2] solve kernel (without its scratch memset).  out_ms = summed
+ * milliseconds, out_n = launches.  bench.py's roofline uses these; the RuntimeData phases include the helpers. */
+int admm_b200_kernel_times( admm_b200_solver *s, double *out_ms /* [3] */, long long *out_n /* [3] */ );
+
 /* Counts of kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long admm_b200_launch_count( const admm_b200_solver *s );
 

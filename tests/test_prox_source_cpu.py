@@ -48,6 +48,13 @@ def shim(cpu):
         L.shim_prox_tris(D(lmin), D(lmax), int(precision), z.shape[0], checkers.dp(z), checkers.dp(out))
         return out
 
+    def prox_tets_warm(model, mu, lam, z, q, precision=0):
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 9)
+        out = np.empty_like(z)
+        assert L.shim_prox_tets_warm(int(model), D(mu), D(lam), D(0.0), int(precision), z.shape[0], checkers.dp(z), checkers.dp(out), checkers.dp(q)) == 0
+        return out
+
+    prox_tets.warm = prox_tets_warm
     return prox_tets, prox_tris
 
 
@@ -93,3 +100,25 @@ def test_device_tri_prox_source_vs_golden(shim):
     for precision, tol in ((1, 1e-10), (0, 2e-6)):
         assert np.abs(shim[1](g["tri_in"], precision=precision) - g["tri_out"]).max() < tol
         assert np.abs(shim[1](g["tri_in"], 0.95, 1.05, precision=precision) - g["tri_lim_out"]).max() < tol
+
+
+@pytest.mark.parametrize("model", [0, 1, 2])
+def test_device_prox_source_warm_started_svd(shim, model):
+    """The SVD warm start (quaternion of V carried between calls, csrc/prox.cuh svd3_signed): same answers as
+    the cold start, call after call on a slowly changing F -- including inverted and resting elements -- and
+    the carried quaternion never leaves the rotations."""
+    rng = np.random.RandomState(11)
+    z = checkers.random_F(2000, 0.3, seed=500 + model)
+    z[:200, 6:9] *= -1.0           # inverted
+    z[200:300] = np.eye(3).ravel()  # at rest: V is arbitrary
+    for precision, tol in ((1, 5e-6), (0, 5e-5)):
+        q = np.zeros((len(z), 4))
+        zz = z.copy()
+        for it in range(6):
+            ref, _ = checkers.prox_tets("oracle", model, MU, LAM, zz)
+            out = shim[0].warm(model, MU, LAM, zz, q, precision=precision)
+            e = np.abs(out - ref).max(axis=1) / np.maximum(1.0, np.abs(ref).max(axis=1))
+            # inverted StVK elements take the reference-faithful path: same tolerance, checked by the degenerate test
+            assert e.max() < tol, (precision, it, e.argmax(), e.max())
+            assert np.isfinite(q).all() and (np.abs(q).max(axis=1) > 0.2).all()
+            zz = zz + 0.02 * rng.randn(*zz.shape)  # the next ADMM iteration's F + u is close to this one's

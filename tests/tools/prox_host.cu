@@ -42,3 +42,24 @@ extern "C" int shim_prox_tris(double lmin, double lmax, int precision, int n, co
 	}
 	return 0;
 }
+
+// warm-started SVD (quaternion of V carried from call to call, as tet_local_kernel does): qio is [n][4], in/out
+template <typename T, int MODEL> static void run_warm(double mu, double lambda, double kappa, int n, const double *zin, double *zout, double *qio)
+{
+	Material<T> m = Material<T>::make(mu, lambda, kappa);
+	for (int e = 0; e < n; ++e) {
+		T z[9], q[4];
+		for (int k = 0; k < 9; ++k) z[k] = T(zin[9 * e + k]);
+		for (int k = 0; k < 4; ++k) q[k] = T(qio[4 * e + k]);
+		prox_tet_mode<T, MODEL, PROX_INLINE>(m, z, q);
+		for (int k = 0; k < 9; ++k) zout[9 * e + k] = double(z[k]);
+		for (int k = 0; k < 4; ++k) qio[4 * e + k] = double(q[k]);
+	}
+}
+extern "C" int shim_prox_tets_warm(int model, double mu, double lambda, double kappa, int precision, int n, const double *zin, double *zout, double *qio)
+{
+	if (model < 0 || model > 2) return 1;
+	if (precision) { if (model == 0) run_warm<double, 0>(mu, lambda, kappa, n, zin, zout, qio); else if (model == 1) run_warm<double, 1>(mu, lambda, kappa, n, zin, zout, qio); else run_warm<double, 2>(mu, lambda, kappa, n, zin, zout, qio); }
+	else { if (model == 0) run_warm<float, 0>(mu, lambda, kappa, n, zin, zout, qio); else if (model == 1) run_warm<float, 1>(mu, lambda, kappa, n, zin, zout, qio); else run_warm<float, 2>(mu, lambda, kappa, n, zin, zout, qio); }
+	return 0;
+}
