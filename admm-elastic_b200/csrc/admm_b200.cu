@@ -3,6 +3,7 @@
 #include "../../include/admm_b200.h"
 #include "kernels.cuh"
 #include "sptrsv.cuh"
+#include "uzawa.cuh"
 #include "mcgs_resident.cuh"
 #include "mcgs_resident_f32.cuh"
 #include "mcgs_owned_f32.cuh"
@@ -130,6 +131,9 @@ struct admm_b200_solver {
 	DevBuf<double> gs_ell_val, gs_diag, gs_resid;
 	DevBuf<unsigned int> barrier;
 	DevBuf<int> gs_iters_done, iter_log;
+	// UzawaCG with passive collisions (uzawa.cuh)
+	DevBuf<int> uz_hv, uz_ctl; DevBuf<double> uz_hn, uz_hc, uz_y, uz_r, uz_d, uz_q3, uz_scal; DevBuf<double4> uz_q1, uz_q2;
+	int uz_max_iters = 20; double uz_tol = 1e-10; // src/UzawaCG.hpp:45-46
 	int gs_grid = 0;
 	size_t gs_nnz = 0, gs_ell_entries = 0;
 	// mcgs, shared-memory-resident variant (mcgs_resident.cuh)
@@ -461,14 +465,14 @@ template <int T> void ldlt_launch_T(S *s, LdltParams &P)
 	CK(cudaLaunchCooperativeKernel((void *)ldlt_solve_kernel<T>, dim3(s->ld_grid), dim3(512), args, 0, s->stream));
 }
 
-void launch_ldlt(S *s)
+void launch_ldlt(S *s, const double4 *rhs = nullptr, double4 *out = nullptr, const int *active = nullptr)
 {
 	LdltParams P;
 	P.n = s->ld_n; P.n_levels_fwd = s->ld_levels_fwd; P.n_levels_bwd = s->ld_levels_bwd;
 	P.perm = s->d_ld_perm.p;
 	P.fwd_level_ptr = s->d_fwd_level_ptr.p; P.fwd_rows = s->d_fwd_rows.p; P.fwd_rowptr = s->d_fwd_rowptr.p; P.fwd_cols = s->d_fwd_cols.p; P.fwd_vals = s->d_fwd_vals.p;
 	P.bwd_level_ptr = s->d_bwd_level_ptr.p; P.bwd_rows = s->d_bwd_rows.p; P.bwd_rowptr = s->d_bwd_rowptr.p; P.bwd_cols = s->d_bwd_cols.p; P.bwd_vals = s->d_bwd_vals.p;
-	P.dinv_unused = nullptr; P.D = s->d_ld_D.p; P.y = s->d_ld_y.p; P.b = s->b.p; P.x = s->cx.p; P.barrier = s->barrier.p;
+	P.dinv_unused = nullptr; P.D = s->d_ld_D.p; P.y = s->d_ld_y.p; P.b = rhs ? rhs : s->b.p; P.x = out ? out : s->cx.p; P.barrier = s->barrier.p; P.active = active;
 	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
 	fine_begin(s, 2);
 	switch (s->ld_lanes) {
@@ -507,9 +511,43 @@ void launch_mgpu_barrier(S *s)
 	s->launches++;
 }
 
+// UzawaCG::solve with passive collisions (uzawa.cuh): a fixed-length sequence of launches, ended early on the device
+void launch_uzawa(S *s)
+{
+	const int n = s->n_nodes, nb = (n + 255) / 256;
+	UzParams U;
+	U.n = n; U.n_obstacles = (int)s->obstacles.size(); U.obs = s->d_obstacles.p;
+	U.hv = s->uz_hv.p; U.hn = s->uz_hn.p; U.hc = s->uz_hc.p; U.y = s->uz_y.p; U.r = s->uz_r.p; U.d = s->uz_d.p; U.q3 = s->uz_q3.p;
+	U.ctl = s->uz_ctl.p; U.scal = s->uz_scal.p; U.tol2 = s->uz_tol * s->uz_tol;
+	const int *active = s->uz_ctl.p + 2;
+	// hits at the current iterate (Solver::step, src/Solver.cpp:87-90), then x = A^-1 (b - C^T y) (:83-84)
+	uz_detect_kernel<<<1, 1024, 0, s->stream>>>(U, s->cx.p);
+	uz_copy_kernel<<<nb, 256, 0, s->stream>>>(n, s->b.p, s->uz_q1.p);
+	uz_scatter_kernel<<<nb, 256, 0, s->stream>>>(U, s->uz_y.p, -1.0, s->uz_q1.p, 0);
+	CK(cudaGetLastError());
+	s->launches += 3;
+	launch_ldlt(s, s->uz_q1.p, s->cx.p, nullptr);
+	uz_init_kernel<<<nb, 256, 0, s->stream>>>(U, s->cx.p);
+	s->launches++;
+	for (int it = 0; it < s->uz_max_iters; ++it) {
+		// q2 = A^-1 C^T d; alpha, y, r, beta, d on the rows; x -= alpha q2   (:93-118)
+		uz_copy_kernel<<<nb, 256, 0, s->stream>>>(n, nullptr, s->uz_q1.p);
+		uz_scatter_kernel<<<nb, 256, 0, s->stream>>>(U, s->uz_d.p, 1.0, s->uz_q1.p, 1);
+		launch_ldlt(s, s->uz_q1.p, s->uz_q2.p, active);
+		uz_step_kernel<<<1, 1024, 0, s->stream>>>(U, s->uz_q2.p);
+		uz_axpy_kernel<<<nb, 256, 0, s->stream>>>(n, s->uz_ctl.p, s->uz_scal.p, s->uz_q2.p, s->cx.p);
+		CK(cudaGetLastError());
+		s->launches += 4;
+	}
+	uz_finish_kernel<<<1, 1, 0, s->stream>>>(s->uz_ctl.p, s->gs_iters_done.p);
+	CK(cudaGetLastError());
+	s->launches++;
+}
+
 void launch_global(S *s)
 {
 	if (s->linsolver == ADMM_B200_MCGS) launch_mcgs(s);
+	else if (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty()) launch_uzawa(s);
 	else launch_ldlt(s); // LDLT, and UzawaCG with an empty constraint matrix (src/UzawaCG.hpp:78-81)
 	launch_mgpu_barrier(s);
 }
@@ -856,6 +894,15 @@ void build_ldlt(S *s)
 	s->d_bwd_rowptr.upload(s->ld_Lp, s->stream); s->d_bwd_cols.upload(s->ld_Li, s->stream); s->d_bwd_vals.upload(s->ld_Lx, s->stream);
 	s->d_ld_D.upload(s->ld_D, s->stream);
 	s->d_ld_y.alloc(n);
+	if (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty()) {
+		// UzawaCG with passive collisions (uzawa.cuh): at most one constraint row per node
+		s->uz_hv.alloc(n); s->uz_hn.alloc(3 * (size_t)n); s->uz_hc.alloc(n); s->uz_y.alloc(n); s->uz_r.alloc(n); s->uz_d.alloc(n); s->uz_q3.alloc(n);
+		s->uz_q1.alloc(n); s->uz_q2.alloc(n); s->uz_ctl.alloc(8); s->uz_scal.alloc(2);
+		s->uz_y.zero(s->stream); s->uz_ctl.zero(s->stream); s->uz_scal.zero(s->stream);
+		if (!s->gs_iters_done.p) s->gs_iters_done.alloc(1);
+		s->d_obstacles.upload(s->obstacles, s->stream);
+		CK(cudaStreamSynchronize(s->stream));
+	}
 	CK(cudaStreamSynchronize(s->stream));
 	const char *env = getenv("ADMM_B200_LDLT_LANES");
 	int T = env ? atoi(env) : 4;
@@ -916,7 +963,7 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 		launch_global(s);
 		if (rt) {
 			CK(cudaEventRecord(get_event(s, ev++), s->stream));
-			if (s->linsolver == ADMM_B200_MCGS) {
+			if (s->linsolver == ADMM_B200_MCGS || (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty())) {
 				// inner_iters += solve() (src/Solver.cpp:99): read back after the step
 				CK(cudaMemcpyAsync(s->iter_log.p + it, s->gs_iters_done.p, sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
 			}
@@ -945,7 +992,7 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 			CK(cudaEventElapsedTime(&t, s->fine_pool[2 * i], s->fine_pool[2 * i + 1]));
 			s->kernel_ms[s->fine_kind[i]] += t; s->kernel_n[s->fine_kind[i]]++;
 		}
-		if (s->linsolver == ADMM_B200_MCGS) {
+		if (s->linsolver == ADMM_B200_MCGS || (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty())) {
 			std::vector<int> its(admm_iters);
 			if (admm_iters) CK(cudaMemcpy(its.data(), s->iter_log.p, sizeof(int) * admm_iters, cudaMemcpyDeviceToHost));
 			for (int i : its) rt->inner_iters += i;
@@ -1371,7 +1418,6 @@ int admm_b200_finalize(admm_b200_solver *s, double dt, int linsolver, int gs_ite
 		s->dt = dt; s->linsolver = linsolver; s->gs_iters = gs_iters; s->gs_omega = gs_omega; s->gs_tol = gs_tol; s->precision = precision;
 		// No collisions with the LDLT solver (src/Solver.cpp:249-254)
 		if (linsolver == ADMM_B200_LDLT) require(s->obstacles.empty(), "**Solver::add_obstacle Error: No collisions with LDLT solver");
-		if (linsolver == ADMM_B200_UZAWA) require(s->obstacles.empty(), "UzawaCG with passive collisions is not on the B200 path yet (SURVEY.md 8f rank 1)");
 		build_incidence(s);
 		if (precision == ADMM_B200_FP64) upload_elements<double>(s); else upload_elements<float>(s);
 		upload_pins(s);
@@ -1452,7 +1498,7 @@ int admm_b200_linsolve(admm_b200_solver *s, double *x, const double *b, int *ite
 		unpack4_to3_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(n, s->cx.p, s->stage3.p);
 		CK(cudaMemcpyAsync(x, s->stage3.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
 		int it = 1;
-		if (s->linsolver == ADMM_B200_MCGS) CK(cudaMemcpyAsync(&it, s->gs_iters_done.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		if (s->linsolver == ADMM_B200_MCGS || (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty())) CK(cudaMemcpyAsync(&it, s->gs_iters_done.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
 		if (iters) *iters = it;
 	});

@@ -36,6 +36,7 @@ struct LdltParams {
 	const double4 *b;         // [n] node order
 	double4 *x;               // [n] node order, out
 	unsigned int *barrier;
+	const int *active;        // NULL, or a device flag: 0 = skip this solve (uzawa.cuh: the CG loop has already ended)
 };
 
 // T lanes cooperate on one row
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(512, 1) ldlt_solve_kernel(LdltParams P)
 	const int group = tid / T;
 	const int n_groups = (gridDim.x * blockDim.x) / T;
 	unsigned int bar_target = 0;
+	if (P.active && *P.active == 0) return; // the same for every block: no barrier is left waiting
 
 	for (int lv = 0; lv < P.n_levels_fwd; ++lv) {
 		const int k0 = P.fwd_level_ptr[lv], k1 = P.fwd_level_ptr[lv + 1];

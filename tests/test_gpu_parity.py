@@ -430,6 +430,45 @@ def test_floor_and_sphere_match_oracle(pkg, cpu):
         assert err < 5e-6, err
 
 
+def test_uzawa_with_collisions_matches_oracle(pkg, cpu):
+    """UzawaCG::solve with passive hits (src/UzawaCG.hpp:57-125, csrc/uzawa.cuh): conjugate gradients on the
+    Schur complement, the constraint rows detected on the device.  Compared solve by solve on identical
+    (x_in, b) -- whole trajectories are chaotic here (a vertex left exactly ON the floor is re-tested with
+    dx < 0 next time, src/PassiveObject.hpp:38-39) -- over a sequence of solves, so that both the reset and
+    the warm start of the multipliers (:69-74) are exercised."""
+    scene = scenes.beam(pkg.meshes, 6, 2, 2)
+    v = scene[0]
+    floor_y = v[:, 1].min() + 0.15   # cuts through the beam: many hits
+    c = np.array([v[:, 0].mean(), v[:, 1].min() - 0.3, v[:, 2].mean()])
+    rng = np.random.RandomState(5)
+    for kw in (dict(floor=floor_y), dict(sphere=(c, 0.75))):
+        gpu, orc = _pair(pkg, scene, 1, 1, 2, 4, pin=False, **kw)
+        x0 = scenes.bend(v).ravel()
+        rp, ci, va = gpu.system_matrix()
+        import scipy.sparse as sp
+        A = sp.csr_matrix((va, ci, rp), shape=(len(v), len(v)))
+        counts = []
+        for k in range(6):
+            x_in = x0 + (0.0 if k % 2 else 0.02) * rng.randn(x0.size)   # odd solves repeat the hit set: y is warm-started
+            b = (A @ (x_in.reshape(-1, 3) + 0.01 * rng.randn(len(v), 3))).ravel()
+            xg, itg = gpu.device().linsolve(x_in, b)
+            xo, ito = orc.linsolve(x_in, b)
+            err = np.abs(xg - xo).max() / np.abs(xo).max()
+            record("uzawa_collisions", floor=float("floor" in kw), solve=k, err=err, iters=itg)
+            assert err < 1e-8, (k, err)
+            assert abs(itg - ito) <= 1, (itg, ito)
+            counts.append(itg)
+        assert any(c != 1 for c in counts)  # the constrained branch ran (an unconstrained solve returns exactly 1)
+        if "floor" in kw:
+            assert min(counts) > 3              # many rows: conjugate gradients really iterate
+    # whole steps: the solved positions respect the floor up to the CG tolerance
+    gpu, _ = _pair(pkg, scene, 1, 1, 2, 8, pin=False, floor=v[:, 1].min() - 0.02)
+    for _ in range(8):
+        gpu.step()
+    rd = gpu.runtime_data()
+    assert np.isfinite(gpu.get_x()).all() and rd["inner_iters"] >= 8
+
+
 def test_device_resident_steps_equal_host_steps(pkg):
     """step_device()+sync_state() (state stays in HBM) gives bit-identical results to step() (host
     buffers every step): the e2e path and the resident path are the same arithmetic."""
