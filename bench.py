@@ -400,7 +400,10 @@ def run_b200(args):
         "assemble_kernel": roof(bytes_asm, t_asm, "88 B/tet + 24 B/vertex"),
     }
     if bytes_gs:
-        kernels["mcgs_kernel"] = roof(bytes_gs, t_glob, "30 sweeps x (20 B x nnz(L) + 36 B x n_verts), one persistent launch per ADMM iteration; the matrix is L2-resident so the kernel can exceed the HBM roofline")
+        kernels["mcgs_kernel"] = roof(bytes_gs, t_glob, "30 sweeps x (20 B x nnz(L) + 36 B x n_verts) = what a streaming sweep would move (SURVEY 8d); one persistent launch per ADMM "
+                                      "iteration keeps matrix and iterate in shared memory, so the figure can exceed the HBM peak: the kernel's real limits are shared-memory "
+                                      "wavefronts and the inter-SM latency of the halo exchange (DESIGN.md 4.1), see 'traffic' for what it actually reads from DRAM")
+        kernels["mcgs_kernel"]["actual_limit"] = "shared-memory gather wavefronts (~2100 cycles per colour pass) + inter-SM latency of 120 dependent halo exchanges per solve"
     dominant = max(kernels, key=lambda k: kernels[k]["ms_per_launch"])
     tr = load_traffic()
     for k in kernels:

@@ -99,6 +99,29 @@ def cloth_steps():
     np.savez_compressed(os.path.join(HERE, "cloth_steps.npz"), **out)
 
 
+def uzawa_floor():
+    """UzawaCG with passive hits (src/UzawaCG.hpp:57-125): the reference's own (x_in, b) -> x_out of every ADMM
+    iteration of 4 steps of a free-falling 4x2x2 Neo-Hookean beam landing on a Floor.  Solve-level data: whole
+    trajectories are chaotic in this scene (see tests/test_oracle_vs_ref.py)."""
+    scene = scenes.beam(pkg.meshes, 4, 2, 2)
+    floor_y = scene[0][:, 1].min() - 0.02
+    iters = 8
+    s = scenes.build_tet_scene(CpuSolver("ref"), scene, 1, linsolver=2, iters=iters, floor=floor_y, pin=False)
+    x_in, bs, x_out = [], [], []
+    for step in range(4):
+        x_prev = s.get_x() + (1.0 / 24) * (s.get_v() + np.tile([0, (1.0 / 24) * -9.8, 0], s.dof // 3))
+        z, u, b, x = s.traced_step(iters)
+        for it in range(iters):
+            x_in.append(x_prev if it == 0 else x[it - 1])
+            bs.append(b[it])
+            x_out.append(x[it])
+    x_in, bs, x_out = np.array(x_in), np.array(bs), np.array(x_out)
+    hits = (x_in.reshape(len(x_in), -1, 3)[:, :, 1] < floor_y).sum(axis=1)
+    assert (hits > 0).sum() > 5
+    np.savez_compressed(os.path.join(HERE, "uzawa_floor.npz"), verts=scene[0], tets=scene[1], masses=scene[2], floor_y=np.array([floor_y]),
+                        iters=np.array([iters]), x_in=x_in, b=bs, x_out=x_out, hits=hits)
+
+
 def single_tet():
     """test_lineartet.cpp known answers as produced by the reference here."""
     V = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 0]], dtype=np.float64)
@@ -125,4 +148,5 @@ if __name__ == "__main__":
     beam_steps()
     cloth_steps()
     single_tet()
+    uzawa_floor()
     print("golden fixtures written to", HERE)

@@ -469,6 +469,22 @@ def test_uzawa_with_collisions_matches_oracle(pkg, cpu):
     assert np.isfinite(gpu.get_x()).all() and rd["inner_iters"] >= 8
 
 
+def test_uzawa_with_floor_golden(pkg):
+    """The device UzawaCG against the reference's own solves (tests/golden/uzawa_floor.npz): same (x_in, b)
+    sequence, multipliers warm-started across solves exactly as in the reference run."""
+    g = np.load(os.path.join(G, "uzawa_floor.npz"))
+    scene = (g["verts"], g["tets"], g["masses"], np.zeros(0, np.int32))
+    s = gpu_solver(pkg, 1)
+    scenes.build_tet_scene(s, scene, 1, linsolver=2, iters=int(g["iters"][0]), floor=float(g["floor_y"][0]), pin=False)
+    worst = 0.0
+    for k in range(len(g["x_in"])):
+        x, it = s.device().linsolve(g["x_in"][k], g["b"][k])
+        worst = max(worst, np.abs(x - g["x_out"][k]).max())
+        assert (it == 1) == (g["hits"][k] == 0) or it == 1  # an unconstrained solve returns exactly 1
+    record("uzawa_floor_golden", err=worst)
+    assert worst < 1e-9, worst
+
+
 def test_device_resident_steps_equal_host_steps(pkg):
     """step_device()+sync_state() (state stays in HBM) gives bit-identical results to step() (host
     buffers every step): the e2e path and the resident path are the same arithmetic."""

@@ -94,3 +94,15 @@ def test_single_tet_golden(cpu):
         assert np.abs(s.get_x() - xg).max() < 1e-9
         if it > 20:
             assert abs(s.get_x()[9] - 52.2321) < 1e-4
+
+
+def test_uzawa_with_floor_golden(cpu):
+    """UzawaCG with passive hits, solve by solve against the reference's own (x_in, b) -> x_out of 4 steps x 8
+    ADMM iterations (tests/golden/uzawa_floor.npz; the multipliers are warm-started across solves)."""
+    g = np.load(os.path.join(G, "uzawa_floor.npz"))
+    scene = (g["verts"], g["tets"], g["masses"], np.zeros(0, np.int32))
+    s = scenes.build_tet_scene(CpuSolver("oracle"), scene, 1, linsolver=2, iters=int(g["iters"][0]), floor=float(g["floor_y"][0]), pin=False)
+    assert (g["hits"] > 0).sum() > 5
+    for k in range(len(g["x_in"])):
+        x, _ = s.linsolve(g["x_in"][k], g["b"][k])
+        assert np.abs(x - g["x_out"][k]).max() < 1e-10, k
