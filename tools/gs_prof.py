@@ -15,8 +15,7 @@ print(sol.runtime_data())
 ncol=len(sol.colors()); passes=30*ncol
 raw=sol.device().debug_get('gs_prof',16*148+1024+128*148)
 p=raw[:16*148].reshape(148,16); tr=raw[16*148:16*148+1024].reshape(32,4,8).astype(np.int64)
-hn=np.maximum(p[:,12],1); print('publish -> usable (ns, global timer; mean over parts | max): vs latest neighbour %.0f | %.0f   vs own previous publish %.0f | %.0f'%((p[:,10]/hn).mean(),(p[:,10]/hn).max(),(p[:,11]/hn).mean(),(p[:,11]/hn).max()))
-names=['wait','boundary','end barrier','total','interior','between passes','sentinel wait','load+retries','sentinel spins','retries']
+names=['wait (poll + halo barrier)','slice compute','end barrier','total','-','between passes']
 print('colours',ncol,'passes',passes,' cycles per pass (mean over parts | max):', {n:(int(p[:,i].mean()/passes), int(p[:,i].max()/passes)) for i,n in enumerate(names)})
 print('kernel phases (cycles, mean over parts): staging %.0f  r0+|b|^2 %.0f  sweeps %.0f  total %.0f'%(p[:,13].mean(),p[:,14].mean(),p[:,15].mean(),p[:,3].mean()))
 print('dbg',os.environ.get('ADMM_B200_GS_DBG','0'),sol.device().info())
