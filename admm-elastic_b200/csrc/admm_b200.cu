@@ -187,7 +187,10 @@ struct admm_b200_solver {
 	int linsolver = 0, gs_iters = 30, precision = 0;
 	double gs_omega = 1.9, gs_tol = 1e-10;
 	bool store_z = false;
-	int tet_minblocks = 6; // resident blocks/SM the fp32 tet kernel is compiled for (ADMM_B200_TET_MINBLOCKS = 5, 6, 8)
+	// resident blocks/SM the fp32 tet kernel is compiled for (ADMM_B200_TET_MINBLOCKS = 5, 6, 8).  Measured local phase on
+	// the 1M-tet beam: 5 (96 regs) 61.6 us, 6 (80) 57.5, 8 (64 regs, 44 B spilled) 55.4, 10 (48) 63.4, 12 (40) 78.0: the kernel
+	// hides its index -> gather latency with resident warps; two elements per thread with hand-hoisted loads lost (58.9).
+	int tet_minblocks = 8;
 
 	// events
 	std::vector<cudaEvent_t> events;
@@ -254,6 +257,7 @@ template <typename E, int MODEL> void launch_tet_model(S *s, TetBatchH *t)
 	fine_begin(s, 0);
 	if (sz) tet_local_kernel<E, MODEL, true, 4><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else if (sizeof(E) == 8) tet_local_kernel<E, MODEL, false, 4><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
+	else if (s->tet_minblocks >= 10) tet_local_kernel<E, MODEL, false, 10><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else if (s->tet_minblocks >= 8) tet_local_kernel<E, MODEL, false, 8><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else if (s->tet_minblocks >= 6) tet_local_kernel<E, MODEL, false, 6><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else tet_local_kernel<E, MODEL, false, 5><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
@@ -606,8 +610,8 @@ template <typename E> void upload_elements(S *s)
 		upload_soa<E>(t->d_wdt2, w2, t->n, t->n_pad, 1, s->stream);
 		t->d_u.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_u.zero(s->stream);
 		// SVD warm start (prox.cuh, svd3_signed): measured on the 1M-tet beam it LOSES 2 us of 60 (the sweeps saved
-		// cost less than the extra 32 B/tet and the quaternion conversions), so it is opt-in
-		if (getenv("ADMM_B200_SVD_WARMSTART")) { t->d_q.alloc((size_t)4 * t->n_pad * sizeof(E)); t->d_q.zero(s->stream); }
+		// cost less than the extra 32 B/tet and the quaternion conversions), so it is a compile-time option (kernels.cuh)
+		if (ADMMB200_SVD_WARMSTART) { t->d_q.alloc((size_t)4 * t->n_pad * sizeof(E)); t->d_q.zero(s->stream); }
 		if (s->store_z) { t->d_z.alloc((size_t)9 * t->n_pad * sizeof(E)); t->d_z.zero(s->stream); }
 		t->d_defer.alloc((size_t)t->n + 2); t->d_defer.zero(s->stream);
 	}
@@ -1416,6 +1420,7 @@ int admm_b200_finalize(admm_b200_solver *s, double dt, int linsolver, int gs_ite
 		require(precision == ADMM_B200_FP32 || precision == ADMM_B200_FP64, "unknown precision");
 		if (dt <= 0.0) dt = 1.0 / 24.0; // src/Solver.cpp:175-179
 		s->dt = dt; s->linsolver = linsolver; s->gs_iters = gs_iters; s->gs_omega = gs_omega; s->gs_tol = gs_tol; s->precision = precision;
+		if (const char *e = getenv("ADMM_B200_TET_MINBLOCKS")) s->tet_minblocks = atoi(e);
 		// No collisions with the LDLT solver (src/Solver.cpp:249-254)
 		if (linsolver == ADMM_B200_LDLT) require(s->obstacles.empty(), "**Solver::add_obstacle Error: No collisions with LDLT solver");
 		build_incidence(s);

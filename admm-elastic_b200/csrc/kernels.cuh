@@ -90,68 +90,97 @@ struct TetBatch {
 	int *defer_done;          // blocks of the consumer kernel that have finished (the last one empties the queue)
 };
 
-// One element of the local step.  MODE = PROX_FAST: the hot kernel; a degenerate element is queued and
-// left untouched.  MODE = PROX_REFERENCE: the queue's consumer redoes such an element from scratch.
-template <typename E, int MODEL, bool STORE_Z, int MODE>
-__device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4 *__restrict__ cx, int e)
+// The streamed part of one element: indices and the SoA columns (everything that comes from DRAM).
+// SVD warm start (prox.cuh, svd3_signed): compiled out by default -- measured slower on the 1M-tet beam (61.8 vs 59.7 us)
+#ifndef ADMMB200_SVD_WARMSTART
+#define ADMMB200_SVD_WARMSTART 0
+#endif
+template <typename E> struct TetStream { int4 id; E bi[9], u[9], w; E q[ADMMB200_SVD_WARMSTART ? 4 : 1]; };
+
+template <typename E>
+__device__ __forceinline__ void tet_load(const TetBatch<E> &tb, int e, TetStream<E> &t)
 {
 	const int np = tb.n_pad;
 	// Load order matters: the vertex gathers depend on the index load, the SoA columns do not -- issue
 	// index first, then all independent columns, and only then touch the indices.
-	const int4 id = __ldg(&tb.idx[e]);
-	E bi[9], u[9];
+	t.id = __ldg(&tb.idx[e]);
 #pragma unroll
-	for (int k = 0; k < 9; ++k) bi[k] = __ldg(&tb.dminv[(size_t)k * np + e]);
+	for (int k = 0; k < 9; ++k) t.bi[k] = __ldg(&tb.dminv[(size_t)k * np + e]);
 #pragma unroll
-	for (int k = 0; k < 9; ++k) u[k] = tb.u[(size_t)k * np + e];
-	const E w = __ldg(&tb.wdt2[e]);
-	E q[4] = {E(0), E(0), E(0), E(0)};
-	if (tb.q) {
+	for (int k = 0; k < 9; ++k) t.u[k] = tb.u[(size_t)k * np + e];
+	t.w = __ldg(&tb.wdt2[e]);
+	if (ADMMB200_SVD_WARMSTART && tb.q) {
 #pragma unroll
-		for (int k = 0; k < 4; ++k) q[k] = tb.q[(size_t)k * np + e];
-	}
+		for (int k = 0; k < (ADMMB200_SVD_WARMSTART ? 4 : 1); ++k) t.q[k] = tb.q[(size_t)k * np + e];
+	} else t.q[0] = E(0);
+}
+
+// One element of the local step.  MODE = PROX_FAST: the hot kernel; a degenerate element is queued and
+// left untouched.  MODE = PROX_REFERENCE: the queue's consumer redoes such an element from scratch.
+template <typename E, int MODEL, bool STORE_Z, int MODE>
+__device__ __forceinline__ void tet_compute(const TetBatch<E> &tb, const double4 *__restrict__ cx, int e, TetStream<E> &t)
+{
+	const int np = tb.n_pad;
+	const int4 id = t.id;
+	E (&bi)[9] = t.bi; E (&u)[9] = t.u;
+	E *q = t.q;
+	const E w = t.w;
 	double4 p0 = ld_node(&cx[id.x]), p1 = ld_node(&cx[id.y]), p2 = ld_node(&cx[id.z]), p3 = ld_node(&cx[id.w]);
 	// Ds = [x1-x0, x2-x0, x3-x0], differences in fp64 (positions are ~metres, edges ~centimetres)
 	E ds[9] = {E(p1.x - p0.x), E(p1.y - p0.y), E(p1.z - p0.z), E(p2.x - p0.x), E(p2.y - p0.y), E(p2.z - p0.z), E(p3.x - p0.x), E(p3.y - p0.y), E(p3.z - p0.z)};
 	// F = Ds * Binv, column-major F[3r+j] = sum_c Ds(j,c) Binv(c,r)   (D_i x, src/TetEnergyTerm.cpp:50-71)
-	E F[9], z[9];
+	// zin = D_i x + u_i is all that has to survive the prox: u_new = u + D_i x - z = zin - z (EnergyTerm::update,
+	// src/EnergyTerm.hpp:130-140), so F, u and Dm^-1 are dead across the SVD + Newton iteration (register pressure
+	// there decides the occupancy, and the occupancy the speed); Dm^-1 is read again afterwards (L1/L2 hit).
+	E zin[9], z[9];
 #pragma unroll
 	for (int r = 0; r < 3; ++r)
 #pragma unroll
 		for (int j = 0; j < 3; ++j) {
-			F[3 * r + j] = ds[j] * bi[r] + ds[3 + j] * bi[3 + r] + ds[6 + j] * bi[6 + r];
-			z[3 * r + j] = F[3 * r + j] + u[3 * r + j];
+			zin[3 * r + j] = (ds[j] * bi[r] + ds[3 + j] * bi[3 + r] + ds[6 + j] * bi[6 + r]) + u[3 * r + j];
+			z[3 * r + j] = zin[3 * r + j];
 		}
-	if (prox_tet_mode<E, MODEL, MODE>(tb.mat, z, tb.q ? q : nullptr)) {
+	if (prox_tet_mode<E, MODEL, MODE>(tb.mat, z, (ADMMB200_SVD_WARMSTART && tb.q) ? q : nullptr)) {
 		tb.defer_list[atomicAdd(tb.defer_count, 1)] = e; // MODE == PROX_FAST only
 		return;
 	}
-	if (tb.q) {
+	if (ADMMB200_SVD_WARMSTART && tb.q) {
 #pragma unroll
-		for (int k = 0; k < 4; ++k) tb.q[(size_t)k * np + e] = q[k];
+		for (int k = 0; k < (ADMMB200_SVD_WARMSTART ? 4 : 1); ++k) tb.q[(size_t)k * np + e] = q[k];
 	}
 	// u += Dx - z ; y = z - u_new
 	E y[9];
 #pragma unroll
 	for (int k = 0; k < 9; ++k) {
-		E un = u[k] + (F[k] - z[k]);
+		const E un = zin[k] - z[k];
 		tb.u[(size_t)k * np + e] = un;
 		if (STORE_Z) tb.z[(size_t)k * np + e] = z[k];
 		y[k] = z[k] - un;
 	}
+	E b2[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) b2[k] = __ldg(&tb.dminv[(size_t)k * np + e]);
 	// corner shares of dt^2 D^T W^2 y: corner c>=1: wdt2 * sum_r Binv(c-1,r) y[:,r]; corner 0: minus their sum
 	E f1[3], f2[3], f3[3];
 #pragma unroll
 	for (int j = 0; j < 3; ++j) {
-		f1[j] = w * (bi[0] * y[j] + bi[1] * y[3 + j] + bi[2] * y[6 + j]);
-		f2[j] = w * (bi[3] * y[j] + bi[4] * y[3 + j] + bi[5] * y[6 + j]);
-		f3[j] = w * (bi[6] * y[j] + bi[7] * y[3 + j] + bi[8] * y[6 + j]);
+		f1[j] = w * (b2[0] * y[j] + b2[1] * y[3 + j] + b2[2] * y[6 + j]);
+		f2[j] = w * (b2[3] * y[j] + b2[4] * y[3 + j] + b2[5] * y[6 + j]);
+		f3[j] = w * (b2[6] * y[j] + b2[7] * y[3 + j] + b2[8] * y[6 + j]);
 	}
 	typename Vec4<E>::type *f = tb.f + (size_t)4 * e;
 	f[0] = Vec4<E>::make(-(f1[0] + f2[0] + f3[0]), -(f1[1] + f2[1] + f3[1]), -(f1[2] + f2[2] + f3[2]));
 	f[1] = Vec4<E>::make(f1[0], f1[1], f1[2]);
 	f[2] = Vec4<E>::make(f2[0], f2[1], f2[2]);
 	f[3] = Vec4<E>::make(f3[0], f3[1], f3[2]);
+}
+
+template <typename E, int MODEL, bool STORE_Z, int MODE>
+__device__ __forceinline__ void tet_element(const TetBatch<E> &tb, const double4 *__restrict__ cx, int e)
+{
+	TetStream<E> t;
+	tet_load(tb, e, t);
+	tet_compute<E, MODEL, STORE_Z, MODE>(tb, cx, e, t);
 }
 
 // MINB = resident blocks per SM asked of the compiler (register budget 65536 / (128 MINB))
