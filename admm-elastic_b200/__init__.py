@@ -198,6 +198,20 @@ class DeviceSolver(object):
         self._ck(_cuda.admm_b200_time_kernels(self.h, int(reps), _dp(out)))
         return {"local_ms": out[0], "assemble_ms": out[1], "global_ms": out[2]}
 
+    def set_deferred_timers(self, on=True):
+        """Timed steps without a synchronise per step (admm_b200_set_deferred_timers); read with collect_timers()."""
+        self._ck(_cuda.admm_b200_set_deferred_timers(self.h, int(bool(on))))
+
+    def collect_timers(self):
+        """Sums over all steps since the last collection: RuntimeData fields + 'steps' (admm_b200_collect_timers)."""
+        class _RT(ctypes.Structure):
+            _fields_ = [("global_ms", ctypes.c_double), ("local_ms", ctypes.c_double), ("collision_ms", ctypes.c_double),
+                        ("inner_iters", ctypes.c_int), ("assemble_ms", ctypes.c_double), ("step_ms", ctypes.c_double)]
+        rt, steps = _RT(), ctypes.c_int(0)
+        self._ck(_cuda.admm_b200_collect_timers(self.h, ctypes.byref(rt), ctypes.byref(steps)))
+        return {"global_ms": rt.global_ms, "local_ms": rt.local_ms, "collision_ms": rt.collision_ms, "inner_iters": rt.inner_iters,
+                "assemble_ms": rt.assemble_ms, "step_ms": rt.step_ms, "steps": steps.value}
+
     def kernel_times(self):
         """Kernel-only times of the last timed step: {name: (summed ms, launches)} (admm_b200_kernel_times)."""
         ms, n = np.zeros(3), np.zeros(3, dtype=np.int64)
@@ -299,11 +313,19 @@ class Solver(object):
         """colors: list of node lists (colour -> nodes), e.g. read from the reference."""
         self._user_colors = [np.asarray(c, dtype=np.int32) for c in colors]
 
-    def initialize(self, dt=1.0 / 24.0, admm_iters=10, gravity=-9.8, linsolver=0, constraint_w=-1.0):
+    def _apply_options(self):
         o = self._opts
         _host.admmhost_set_options(self.h, int(o["device"]), int(o["precision"]), int(o["gs_max_iters"]),
                                    ctypes.c_double(o["gs_tol"]), ctypes.c_double(o["gs_omega"]), int(o["coloring"]),
                                    int(bool(o["keep_z"])), int(bool(o["timers"])), ctypes.c_void_p(o["stream"] or 0))
+
+    def set_timers(self, on):
+        """DeviceOptions::timers after initialize(): whether step() / step_device() fill RuntimeData (and synchronise)."""
+        self._opts["timers"] = bool(on)
+        self._apply_options()
+
+    def initialize(self, dt=1.0 / 24.0, admm_iters=10, gravity=-9.8, linsolver=0, constraint_w=-1.0):
+        self._apply_options()
         if self._user_colors is not None:
             off = np.zeros(len(self._user_colors) + 1, dtype=np.int32)
             off[1:] = np.cumsum([len(c) for c in self._user_colors])

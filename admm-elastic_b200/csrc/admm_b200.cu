@@ -158,6 +158,9 @@ struct admm_b200_solver {
 	// kernel-only timing (admm_b200_kernel_times)
 	bool fine_on = false; std::vector<cudaEvent_t> fine_pool; size_t fine_used = 0; std::vector<int> fine_kind;
 	double kernel_ms[3] = {0, 0, 0}; long long kernel_n[3] = {0, 0, 0};
+	struct TimerBlockT { size_t ev0; int iters; size_t fine0, fine1; int log0; };
+	std::vector<TimerBlockT> tblocks; size_t ev_next = 0; int log_next = 0, timer_steps = 0; bool deferred_timers = false;
+	admm_b200_runtime pend = {0, 0, 0, 0, 0, 0}; double pend_kernel_ms[3] = {0, 0, 0}; long long pend_kernel_n[3] = {0, 0, 0}; int pend_steps = 0;
 	DevBuf<short> res_slice_node;
 	std::vector<double> h_x0; // rest positions (partitioning)
 	std::string gs_info;
@@ -207,6 +210,7 @@ struct admm_b200_solver {
 namespace {
 
 typedef admm_b200_solver S;
+typedef admm_b200_solver::TimerBlockT TimerBlock;
 void fine_begin(S *s, int kind);
 void fine_end(S *s);
 
@@ -920,6 +924,7 @@ void fine_begin(S *s, int kind)
 {
 	if (!s->fine_on) return;
 	cudaEvent_t a, b;
+	s->fine_used = 2 * s->fine_kind.size();
 	if (s->fine_pool.size() < s->fine_used + 2) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); s->fine_pool.push_back(a); s->fine_pool.push_back(b); }
 	a = s->fine_pool[s->fine_used];
 	CK(cudaEventRecord(a, s->stream));
@@ -945,62 +950,94 @@ void zero_duals(S *s)
 	s->pins.d_u.zero(s->stream);
 }
 
+// Timers.  Immediate mode (a runtime pointer is passed): events of this step only, summed after a stream
+// synchronise at the end of the step -- what Solver::runtime_data() needs.  Deferred mode
+// (admm_b200_set_deferred_timers): every step records into fresh events and returns WITHOUT synchronising, so
+// the host can queue the next step while this one runs; admm_b200_collect_timers sums all steps since the
+// last collection.  One block of events per step: 4 per ADMM iteration + 1, plus 2 per hot-kernel launch.
+void sum_timer_blocks(S *s, admm_b200_runtime *rt)
+{
+	CK(cudaStreamSynchronize(s->stream));
+	rt->global_ms = rt->local_ms = rt->collision_ms = rt->assemble_ms = rt->step_ms = 0; rt->inner_iters = 0;
+	for (int k = 0; k < 3; ++k) { s->kernel_ms[k] = 0; s->kernel_n[k] = 0; }
+	const bool logged = s->linsolver == ADMM_B200_MCGS || (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty());
+	for (const TimerBlock &tb : s->tblocks) {
+		for (int it = 0; it < tb.iters; ++it) {
+			float a = 0, b = 0, c = 0;
+			CK(cudaEventElapsedTime(&a, s->events[tb.ev0 + 4 * it], s->events[tb.ev0 + 4 * it + 1]));
+			CK(cudaEventElapsedTime(&b, s->events[tb.ev0 + 4 * it + 1], s->events[tb.ev0 + 4 * it + 2]));
+			CK(cudaEventElapsedTime(&c, s->events[tb.ev0 + 4 * it + 2], s->events[tb.ev0 + 4 * it + 3]));
+			rt->local_ms += a; rt->assemble_ms += b; rt->global_ms += b + c;
+		}
+		if (tb.iters > 0) { float t = 0; CK(cudaEventElapsedTime(&t, s->events[tb.ev0], s->events[tb.ev0 + 4 * tb.iters])); rt->step_ms += t; }
+		for (size_t i = tb.fine0; i < tb.fine1; ++i) {
+			float t = 0;
+			CK(cudaEventElapsedTime(&t, s->fine_pool[2 * i], s->fine_pool[2 * i + 1]));
+			s->kernel_ms[s->fine_kind[i]] += t; s->kernel_n[s->fine_kind[i]]++;
+		}
+		if (logged) {
+			std::vector<int> its(tb.iters);
+			if (tb.iters) CK(cudaMemcpy(its.data(), s->iter_log.p + tb.log0, sizeof(int) * tb.iters, cudaMemcpyDeviceToHost));
+			for (int i : its) rt->inner_iters += i;
+		} else rt->inner_iters += tb.iters; // LDLT / empty-C Uzawa return 1 per solve
+	}
+	s->timer_steps = (int)s->tblocks.size();
+	s->tblocks.clear(); s->ev_next = 0; s->fine_used = 0; s->fine_kind.clear(); s->log_next = 0;
+}
+
 void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 {
 	require(s->finalized, "step before finalize");
-	require(admm_iters >= 0 && (!rt || admm_iters <= (int)s->iter_log.n), "admm_iters out of range");
+	require(admm_iters >= 0 && admm_iters <= (int)s->iter_log.n, "admm_iters out of range");
+	const bool timed = rt != nullptr || s->deferred_timers;
+	if (timed) {
+		// immediate mode starts from a clean slate; deferred mode appends (and folds into the pending sums when the
+		// iteration log or the event pools would grow without bound)
+		if (rt && !s->tblocks.empty()) { admm_b200_runtime tmp; sum_timer_blocks(s, &tmp); }
+		if (!rt && (s->log_next + admm_iters > (int)s->iter_log.n || s->tblocks.size() >= 256)) {
+			admm_b200_runtime tmp; double km[3]; long long kn[3];
+			sum_timer_blocks(s, &tmp);
+			for (int k = 0; k < 3; ++k) { km[k] = s->kernel_ms[k]; kn[k] = s->kernel_n[k]; }
+			s->pend.global_ms += tmp.global_ms; s->pend.local_ms += tmp.local_ms; s->pend.assemble_ms += tmp.assemble_ms; s->pend.step_ms += tmp.step_ms; s->pend.inner_iters += tmp.inner_iters;
+			for (int k = 0; k < 3; ++k) { s->pend_kernel_ms[k] += km[k]; s->pend_kernel_n[k] += kn[k]; }
+			s->pend_steps += s->timer_steps;
+		}
+	}
 	const int n = s->n_nodes;
 	const int nb = (n + 255) / 256;
 	step_begin_kernel<<<nb, 256, 0, s->stream>>>(n, s->dt, gravity, s->x.p, s->v.p, s->m.p, s->mxbar.p, s->cx.p);
 	CK(cudaGetLastError());
 	s->launches++;
 	zero_duals(s); // curr_u = 0 every step (src/Solver.cpp:71)
-	size_t ev = 0;
-	s->fine_on = rt != nullptr; s->fine_used = 0; s->fine_kind.clear();
+	TimerBlock tb;
+	tb.ev0 = s->ev_next; tb.iters = admm_iters; tb.fine0 = s->fine_kind.size(); tb.log0 = s->log_next;
+	size_t ev = s->ev_next;
+	s->fine_on = timed;
+	const bool logged = s->linsolver == ADMM_B200_MCGS || (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty());
 	// events per ADMM iteration: [4it] local [4it+1] assemble [4it+2] solve [4it+3]
 	for (int it = 0; it < admm_iters; ++it) {
-		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
+		if (timed) CK(cudaEventRecord(get_event(s, ev++), s->stream));
 		launch_local(s);
-		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
+		if (timed) CK(cudaEventRecord(get_event(s, ev++), s->stream));
 		launch_assemble(s);
-		if (rt) CK(cudaEventRecord(get_event(s, ev++), s->stream));
+		if (timed) CK(cudaEventRecord(get_event(s, ev++), s->stream));
 		launch_global(s);
-		if (rt) {
+		if (timed) {
 			CK(cudaEventRecord(get_event(s, ev++), s->stream));
-			if (s->linsolver == ADMM_B200_MCGS || (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty())) {
-				// inner_iters += solve() (src/Solver.cpp:99): read back after the step
-				CK(cudaMemcpyAsync(s->iter_log.p + it, s->gs_iters_done.p, sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-			}
+			// inner_iters += solve() (src/Solver.cpp:99): read back when the timers are summed
+			if (logged) CK(cudaMemcpyAsync(s->iter_log.p + tb.log0 + it, s->gs_iters_done.p, sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
 		}
 	}
 	step_end_kernel<<<nb, 256, 0, s->stream>>>(n, s->dt, s->x.p, s->v.p, s->cx.p);
 	CK(cudaGetLastError());
 	s->launches++;
 	s->fine_on = false;
-	if (rt) {
-		cudaEvent_t e_end = get_event(s, ev++);
-		CK(cudaEventRecord(e_end, s->stream));
-		CK(cudaStreamSynchronize(s->stream));
-		rt->global_ms = rt->local_ms = rt->collision_ms = rt->assemble_ms = rt->step_ms = 0; rt->inner_iters = 0;
-		for (int it = 0; it < admm_iters; ++it) {
-			float a = 0, b = 0, c = 0;
-			CK(cudaEventElapsedTime(&a, s->events[4 * it], s->events[4 * it + 1]));
-			CK(cudaEventElapsedTime(&b, s->events[4 * it + 1], s->events[4 * it + 2]));
-			CK(cudaEventElapsedTime(&c, s->events[4 * it + 2], s->events[4 * it + 3]));
-			rt->local_ms += a; rt->assemble_ms += b; rt->global_ms += b + c;
-		}
-		if (admm_iters > 0) { float t = 0; CK(cudaEventElapsedTime(&t, s->events[0], e_end)); rt->step_ms = t; }
-		for (int k = 0; k < 3; ++k) { s->kernel_ms[k] = 0; s->kernel_n[k] = 0; }
-		for (size_t i = 0; i < s->fine_kind.size() && 2 * i + 1 < s->fine_used + 1; ++i) {
-			float t = 0;
-			CK(cudaEventElapsedTime(&t, s->fine_pool[2 * i], s->fine_pool[2 * i + 1]));
-			s->kernel_ms[s->fine_kind[i]] += t; s->kernel_n[s->fine_kind[i]]++;
-		}
-		if (s->linsolver == ADMM_B200_MCGS || (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty())) {
-			std::vector<int> its(admm_iters);
-			if (admm_iters) CK(cudaMemcpy(its.data(), s->iter_log.p, sizeof(int) * admm_iters, cudaMemcpyDeviceToHost));
-			for (int i : its) rt->inner_iters += i;
-		} else rt->inner_iters = admm_iters; // LDLT / empty-C Uzawa return 1 per solve
+	if (timed) {
+		CK(cudaEventRecord(get_event(s, ev++), s->stream)); // end of the step: events[ev0 + 4 iters]
+		tb.fine1 = s->fine_kind.size();
+		s->ev_next = ev; s->log_next += admm_iters;
+		s->tblocks.push_back(tb);
+		if (rt) sum_timer_blocks(s, rt);
 	}
 }
 
@@ -1565,6 +1602,28 @@ int admm_b200_time_kernels(admm_b200_solver *s, int reps, double *out_ms)
 }
 
 long long admm_b200_launch_count(const admm_b200_solver *s) { return s ? s->launches : 0; }
+
+int admm_b200_set_deferred_timers(admm_b200_solver *s, int on)
+{
+	return guard(s, [&]() {
+		if (!s->tblocks.empty()) { admm_b200_runtime tmp; sum_timer_blocks(s, &tmp); }
+		s->deferred_timers = on != 0;
+		s->pend = admm_b200_runtime{0, 0, 0, 0, 0, 0}; s->pend_steps = 0;
+		for (int k = 0; k < 3; ++k) { s->pend_kernel_ms[k] = 0; s->pend_kernel_n[k] = 0; }
+	});
+}
+
+int admm_b200_collect_timers(admm_b200_solver *s, admm_b200_runtime *sum, int *steps)
+{
+	return guard(s, [&]() {
+		require(sum != nullptr, "collect_timers: null output");
+		sum_timer_blocks(s, sum);
+		sum->global_ms += s->pend.global_ms; sum->local_ms += s->pend.local_ms; sum->assemble_ms += s->pend.assemble_ms; sum->step_ms += s->pend.step_ms; sum->inner_iters += s->pend.inner_iters;
+		for (int k = 0; k < 3; ++k) { s->kernel_ms[k] += s->pend_kernel_ms[k]; s->kernel_n[k] += s->pend_kernel_n[k]; s->pend_kernel_ms[k] = 0; s->pend_kernel_n[k] = 0; }
+		if (steps) *steps = s->timer_steps + s->pend_steps;
+		s->pend = admm_b200_runtime{0, 0, 0, 0, 0, 0}; s->pend_steps = 0;
+	});
+}
 
 int admm_b200_kernel_times(admm_b200_solver *s, double *out_ms, long long *out_n)
 {

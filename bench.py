@@ -320,25 +320,24 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, n):
-        """n calls of fn bracketed by barrier+sync, CUDA events on the solver's stream, max over ranks."""
+        """n calls of fn bracketed by barrier+sync, CUDA events on the solver's stream, max over ranks.  The per-phase and
+        per-kernel events of every step are recorded inside this region but read only after it (deferred timers,
+        admm_b200_collect_timers): no host synchronise per step, the next step's launches queue behind the running one."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        acc = {"local_ms": 0.0, "assemble_ms": 0.0, "global_ms": 0.0, "step_ms": 0.0}
-        kt = {}
+        sol.set_timers(False)
+        dev.set_deferred_timers(True)
         barrier()
         with torch.cuda.stream(stream):
             e0.record(stream)
             for _ in range(n):
                 fn()
-                rd = sol.runtime_data()
-                for k in acc:
-                    acc[k] += rd[k]
-                for k, (ms_k, n_k) in dev.kernel_times().items():   # events tightly around each hot kernel launch
-                    a = kt.setdefault(k, [0.0, 0])
-                    a[0] += ms_k
-                    a[1] += n_k
             e1.record(stream)
-        acc["kernels"] = kt
         barrier()
+        acc = dev.collect_timers()
+        acc["kernels"] = {k: list(v) for k, v in dev.kernel_times().items()}   # events tightly around each hot kernel launch
+        dev.set_deferred_timers(False)
+        sol.set_timers(True)
+        assert acc["steps"] == n, acc
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)

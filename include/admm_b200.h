@@ -176,6 +176,14 @@ int admm_b200_set_debug( admm_b200_solver *s, int store_z );
  * global (solve) in out_ms[3].  Used by bench.py for the roofline numbers. */
 int admm_b200_time_kernels( admm_b200_solver *s, int reps, double *out_ms );
 
+/* Deferred timers: with `on`, admm_b200_step / _step_host called WITHOUT a runtime pointer still record their CUDA
+ * events but do not synchronise, so the host can queue the next step while this one runs (a runtime pointer makes a
+ * step wait for its own events).  admm_b200_collect_timers waits for the stream and returns the SUMS over all steps
+ * since the last collection (RuntimeData fields summed; *steps = how many); admm_b200_kernel_times then holds the
+ * kernel-only sums of the same steps. */
+int admm_b200_set_deferred_timers( admm_b200_solver *s, int on );
+int admm_b200_collect_timers( admm_b200_solver *s, admm_b200_runtime *sum, int *steps );
+
 /* Kernel-only device times of the last timed step (admm_b200_step* with a runtime pointer): CUDA events recorded on
  * the solver's stream immediately before and after each launch of the three hot kernels -- [0] tet prox kernel
  * (without its queue consumer), [1] assemble kernel, [2] solve kernel (without its scratch memset).  out_ms = summed

@@ -504,6 +504,33 @@ def test_device_resident_steps_equal_host_steps(pkg):
     assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
 
 
+def test_deferred_timers(pkg):
+    """Deferred timers (admm_b200_set_deferred_timers / _collect_timers): the steps run without a host synchronise
+    each, give bit-identical positions, and the collected sums cover every step, iteration and kernel launch."""
+    scene = scenes.beam(pkg.meshes, 8, 3, 3)
+    res = []
+    for deferred in (False, True):
+        s = gpu_solver(pkg, 0)
+        scenes.build_tet_scene(s, scene, 1, linsolver=1, iters=5)
+        s.set_x(scenes.bend(scene[0]).ravel())
+        s.upload_state()
+        if deferred:
+            s.set_timers(False)
+            s.device().set_deferred_timers(True)
+        for _ in range(3):
+            s.step_device()
+        if deferred:
+            acc = s.device().collect_timers()
+            kt = s.device().kernel_times()
+            assert acc["steps"] == 3 and acc["inner_iters"] == 3 * 5 * 30
+            assert all(n == 15 for _, n in kt.values()) and all(ms > 0 for ms, _ in kt.values())
+            assert acc["step_ms"] > 0 and acc["local_ms"] > 0 and acc["global_ms"] > acc["assemble_ms"] > 0
+            assert s.device().collect_timers()["steps"] == 0   # collected once
+        s.sync_state()
+        res.append(s.get_x())
+    assert (res[0] == res[1]).all()
+
+
 def test_no_silent_fallback(pkg):
     """The product path must be the CUDA one: kernels were launched by this handle."""
     scene = scenes.beam(pkg.meshes, 4, 2, 2)
