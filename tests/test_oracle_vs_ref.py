@@ -147,6 +147,24 @@ def test_uzawa_with_floor_matches_reference(pkg, cpu):
     assert n_constrained > 5  # the constrained branch was exercised
 
 
+def test_uzawa_with_sphere_matches_reference(pkg, cpu):
+    """As above with a Sphere (normals differ per hit, src/PassiveObject.hpp:47-64): solve by solve on the
+    reference's own (x_in, b)."""
+    scene = scenes.beam(pkg.meshes, 4, 2, 2)
+    c = np.array([scene[0][:, 0].mean(), scene[0][:, 1].min() - 0.45, scene[0][:, 2].mean()])
+    ref, orc = _pair(pkg, scene, 1, linsolver=2, iters=8, sphere=(c, 0.5), pin=False)
+    n_constrained = 0
+    for step in range(5):
+        x_prev = ref.get_x() + (1.0 / 24) * (ref.get_v() + np.tile([0, (1.0 / 24) * -9.8, 0], ref.dof // 3))
+        z, u, b, x = ref.traced_step(8)
+        for it in range(8):
+            x_in = x_prev if it == 0 else x[it - 1]
+            xo, iters = orc.linsolve(x_in, b[it])
+            assert np.abs(xo - x[it]).max() < 1e-10
+            n_constrained += int((np.linalg.norm(x_in.reshape(-1, 3) - c, axis=1) < 0.5).any())
+    assert n_constrained > 3  # the constrained branch was exercised
+
+
 @pytest.mark.parametrize("linsolver", [0, 2])
 @pytest.mark.parametrize("limits", [(-100.0, 100.0), (0.95, 1.05)])
 def test_cloth_steps_match_reference(pkg, cpu, linsolver, limits):
