@@ -160,6 +160,12 @@ def cpu_solver(args, scene, pkg, admm_iters):
         import __graft_entry__ as g
         g.build()
     s = checkers.CpuSolver(kind)
+    if kind == "ref" and os.environ.get("TORCHELASTIC_RUN_ID") and os.environ.get("OMP_NUM_THREADS") == "1":
+        # torchrun imposes OMP_NUM_THREADS=1 on its workers; the reference arm is meant to use all host cores
+        try:
+            checkers.ref_lib().ref_set_omp_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            pass  # an older oracle/_ref build without the setter
     mu, lam = pkg.meshes.lame(*LAME)
     s.add_nodes(scene["verts"], scene["masses"])
     s.add_tets(scene["verts"], scene["tets"], args.model, mu, lam)

@@ -339,5 +339,7 @@ double ref_tet_energy( int model, double mu, double lambda, const double *verts1
 }
 
 int ref_omp_threads(){ return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to its workers: bench.py's reference arm asks for the host's cores again
+void ref_set_omp_threads( int n ){ if( n > 0 ){ omp_set_num_threads(n); } }
 
 } // extern C
