@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 	}
 	const double thresh = check ? 4.0 * P.tol2 * __ldcg(&P.resid[0]) : 0.0;
 	const size_t TS = (size_t)R.total_slots, buf_stride = 3 * TS; // dglob: [sweep parity][x | y | z][slot]
-	long long pw = 0, pc = 0, pb = 0, po = 0, t_prev_end = 0, ps1 = 0, ps2 = 0, n_retry = 0, n_spin = 0, hop_nbr = 0, hop_own = 0, hop_n = 0;
+	long long pw = 0, pc = 0, pb = 0, po = 0, t_prev_end = 0, ps1 = 0, ps2 = 0, n_retry = 0, n_spin = 0, hop_nbr = 0, hop_own = 0, hop_first = 0, hop_n = 0;
 
 	// Pulls the halo values of colour `cp` published with tag `tag` in buffer `buf` into shared memory
 	// (thread t0 of nt takes every nt-th node).
@@ -278,6 +278,18 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				}
 				if (PROF) TR(1);
 				named_sync(1, n_poll);
+				if (PROF && pass > 0 && role == 0 && lane == 0) {
+					// when did the neighbours publish what has just arrived?  (global timer; single GPU only)
+					const unsigned long long now = gtime_ns();
+					volatile unsigned long long *pubt = (volatile unsigned long long *)(R.prof + 16 * gridDim.x + 1024);
+					unsigned long long latest = 0, earliest = ~0ull;
+					for (int i = 0; i < d.n_nbr; ++i) {
+						const unsigned long long v = pubt[(size_t)__ldg(&R.nbr[d.nbr_off + i]) * 128 + ((pass - 1) & 127)];
+						if (v != 0 && v <= now && now - v < 100000ull) { latest = v > latest ? v : latest; earliest = v < earliest ? v : earliest; }
+					}
+					const unsigned long long own = pubt[(size_t)(R.part0 + blockIdx.x) * 128 + ((pass - 1) & 127)];
+					if (latest != 0 && own != 0 && own <= now) { hop_nbr += (long long)(now - latest); hop_first += (long long)(now - earliest); hop_own += (long long)(now - own); ++hop_n; }
+				}
 			}
 			if (PROF) { t1 = clk_ordered(); TR(2); }
 #pragma unroll
@@ -325,6 +337,8 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 					if (cnt > 2) put(pre2); // a corner node read by more than two parts
 					if (cnt > 3) put(pre3);
 					for (int e = pre_e0 + 4; e < pre_e0 + cnt; ++e) put(__ldg(&R.dest_slot[e]));
+					if (PROF && (R.dbg & 64)) __threadfence(); // timing experiment: does a fence get the published words out sooner?
+					if (PROF && lane == 0 && R.world == 1) atomicMax(R.prof + 16 * gridDim.x + 1024 + (size_t)(R.part0 + blockIdx.x) * 128 + (pass & 127), gtime_ns());
 				}
 			}
 			long long t2 = 0;
@@ -411,11 +425,11 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 	if (blockIdx.x == 0 && tid == 0) *P.iters_done = it;
 	if (PROF && tid == 0) {
 		unsigned long long *q = R.prof + 16 * blockIdx.x;
-		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pb; q[3] = (unsigned long long)(clock64() - t_kernel); q[4] = 0; q[5] = (unsigned long long)po; q[6] = (unsigned long long)ps1; q[7] = (unsigned long long)ps2; q[8] = (unsigned long long)n_spin; q[9] = (unsigned long long)n_retry;
+		q[0] = (unsigned long long)pw; q[1] = (unsigned long long)pc; q[2] = (unsigned long long)pb; q[3] = (unsigned long long)(clock64() - t_kernel); q[5] = (unsigned long long)po; q[6] = (unsigned long long)ps1; q[7] = (unsigned long long)ps2; q[8] = (unsigned long long)n_spin; q[9] = (unsigned long long)n_retry;
 		q[13] = (unsigned long long)(t_staged - t_kernel); q[14] = (unsigned long long)(t_begin - t_staged); q[15] = (unsigned long long)(t_loop_end - t_begin);
 	}
-	if (PROF && lane == 0 && hop_n) { unsigned long long *q = R.prof + 16 * blockIdx.x; q[10] = (unsigned long long)hop_nbr; q[11] = (unsigned long long)hop_own; q[12] = (unsigned long long)hop_n; }
-	(void)hop_nbr; (void)hop_own; (void)hop_n;
+	if (PROF && lane == 0 && hop_n) { unsigned long long *q = R.prof + 16 * blockIdx.x; q[10] = (unsigned long long)hop_nbr; q[11] = (unsigned long long)hop_own; q[12] = (unsigned long long)hop_n; q[4] = (unsigned long long)hop_first; }
+	(void)hop_nbr; (void)hop_own; (void)hop_first; (void)hop_n;
 	(void)pw; (void)pc; (void)pb; (void)po; (void)t_prev_end; (void)ps1; (void)ps2; (void)n_retry; (void)n_spin;
 }
 

@@ -44,7 +44,7 @@ struct McgsRes32Params {
 	int part0, world, rank;
 	// mailboxes of the static-ownership kernel (partition.hpp, plan_mailboxes); dglob is then [2][3][total_slots]
 	const int *dest_off; const unsigned int *dest_slot; int total_slots;
-	int dbg; // timing experiments only (ADMM_B200_GS_DBG, tools/gs_prof.py): 1 no tag wait, 2 no refresh, 4 no interior, 8 no boundary
+	int dbg; // timing experiments only (ADMM_B200_GS_DBG, tools/gs_prof.py): 1 no tag wait, 2 no refresh, 4 no interior, 8 no boundary (owned kernel: 2, 4, 16 no publish, 32 no gather, 64 fence after publish; bits 8.. = part whose passes 40..43 are traced)
 	const unsigned int *dest_mask; // [n_nodes] ranks (bit q) that read this node as halo; NULL when world == 1
 	uint2 *peer_dglob[ADMMB200_MAX_RANKS];
 	double4 *peer_x[ADMMB200_MAX_RANKS];

@@ -15,6 +15,10 @@ print(sol.runtime_data())
 ncol=len(sol.colors()); passes=30*ncol
 raw=sol.device().debug_get('gs_prof',16*148+1024+128*148)
 p=raw[:16*148].reshape(148,16); tr=raw[16*148:16*148+1024].reshape(32,4,8).astype(np.int64)
+hn=np.maximum(p[:,12],1.0); ok=p[:,12]>0
+if ok.any():
+    print('global timer, ns, mean over parts (and the slowest part): halo complete after the LATEST neighbour published %.0f (%.0f), after the EARLIEST %.0f, after this part\'s own previous publish %.0f'
+          % ((p[ok,10]/hn[ok]).mean(), (p[ok,10]/hn[ok]).max(), (p[ok,4]/hn[ok]).mean(), (p[ok,11]/hn[ok]).mean()))
 names=['wait (poll + halo barrier)','slice compute','end barrier','total','-','between passes']
 print('colours',ncol,'passes',passes,' cycles per pass (mean over parts | max):', {n:(int(p[:,i].mean()/passes), int(p[:,i].max()/passes)) for i,n in enumerate(names)})
 print('kernel phases (cycles, mean over parts): staging %.0f  r0+|b|^2 %.0f  sweeps %.0f  total %.0f'%(p[:,13].mean(),p[:,14].mean(),p[:,15].mean(),p[:,3].mean()))
