@@ -7,6 +7,7 @@
 #include "mcgs_resident.cuh"
 #include "mcgs_resident_f32.cuh"
 #include "mcgs_owned_f32.cuh"
+#include "dataflow_plan.hpp"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -1636,6 +1637,33 @@ int admm_b200_kernel_times(admm_b200_solver *s, double *out_ms, long long *out_n
 // Host-only check of the resident plan (no device): builds the plan, walks it exactly like
 // mcgs_resident_kernel's gather and returns max |(L_offdiag x)_plan - (L_offdiag x)_csr| over all nodes
 // for the given x (n values); stats = {shared bytes needed, max own, max halo, entries, nnz, parts used}.
+// Host-only model of the barrier-free schedule (csrc/dataflow_plan.hpp): plans it for the given scalar matrix and
+// colouring, executes `sweeps` SOR sweeps under `n_seeds` random legal schedules and requires bit-identical results to
+// colour-by-colour sweeps.  stats = {max own-slice dependencies, max halo references per slice, tasks executed, parts used}.
+int admm_b200_dataflow_check(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int n_parts, int n_warps, int sweeps, int n_seeds, long long *stats)
+{
+	try {
+		ResidentPlan R = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts, 1);
+		DataflowPlan D = plan_dataflow(R, n_colors, n_warps);
+		std::vector<double> diag(n, 1.0), rhs(n);
+		for (int i = 0; i < n; ++i) for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) if (cols[q] == i) diag[i] = vals[q];
+		long long tasks = 0, used = 0;
+		for (const PartDesc &d : R.parts) if (d.n_own) ++used;
+		for (int sd = 0; sd < n_seeds; ++sd) {
+			std::mt19937 rng(1000 + sd);
+			std::uniform_real_distribution<double> U(-1.0, 1.0);
+			for (int i = 0; i < n; ++i) rhs[i] = U(rng);
+			tasks += simulate_dataflow(R, D, n, n_colors, diag.data(), rhs.data(), 1.9, sweeps, (unsigned int)(77 + sd), nullptr);
+		}
+		if (stats) { stats[0] = (long long)D.max_deps; stats[1] = (long long)D.max_halo_refs; stats[2] = tasks; stats[3] = used; }
+		return 0;
+	} catch (std::exception &e) {
+		g_create_error = e.what();
+		return 1;
+	}
+}
+
 int admm_b200_plan_check(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
 	const double *pos3, int n_parts, int val_bytes, int lanes, const double *x, double *max_err, long long *stats, int *part_of)
 {

@@ -214,6 +214,13 @@ int admm_b200_mgpu_ready( admm_b200_solver *s );
 int admm_b200_mgpu_plan_check( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
 	const double *pos3, int sms, int world, int rank, unsigned int *mask_out, int *ghost_out, int *owner_out );
 
+/* Host-only model of a barrier-free (slice-level dataflow) schedule of the resident Gauss-Seidel, the next step of
+ * DESIGN.md 9.1 (csrc/dataflow_plan.hpp): random legal schedules must reproduce colour-by-colour SOR sweeps bit for
+ * bit and never deadlock.  No kernel uses the schedule yet.  stats[4] = {max own-slice dependencies, max halo
+ * references of a slice, tasks executed, parts used}. */
+int admm_b200_dataflow_check( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int n_parts, int n_warps, int sweeps, int n_seeds, long long *stats );
+
 /* Host-only self check of the shared-memory-resident Gauss-Seidel plan (no device needed): see
  * csrc/partition.hpp.  Returns 0 when the plan covers every node exactly once and reproduces
  * L_offdiag * x; the message of a failure is available from admm_b200_last_error(NULL). */

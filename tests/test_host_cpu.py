@@ -148,3 +148,31 @@ def test_resident_gauss_seidel_plan(pkg, dims, parts):
         sizes = np.bincount(part, minlength=parts)
         if n >= 4 * parts:
             assert sizes.max() <= 1.5 * n / parts + 8   # balanced
+
+
+@pytest.mark.parametrize("dims,parts,warps", [((6, 2, 2), 5, 4), ((10, 4, 3), 12, 16), ((8, 3, 3), 148, 16)])
+def test_barrier_free_schedule_model(pkg, dims, parts, warps):
+    """csrc/dataflow_plan.hpp: per-slice dependencies + tagged mailboxes are enough -- random legal schedules of the
+    barrier-free Gauss-Seidel reproduce colour-by-colour sweeps bit for bit and never deadlock (host model)."""
+    import ctypes
+    import scipy.sparse as sp
+    verts, tets = pkg.meshes.make_tet_blocks(*dims)
+    n = len(verts)
+    rows, cols = np.repeat(tets, 4, axis=1).ravel(), np.tile(tets, (1, 4)).ravel()
+    A = sp.csr_matrix((np.random.RandomState(0).rand(rows.size) + 0.1, (rows, cols)), shape=(n, n))
+    A = (A + A.T).tolil()
+    A.setdiag(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)   # diagonally dominant: the sweeps stay bounded
+    A = A.tocsr()
+    A.sort_indices()
+    colors = pkg.color_matrix(A.indptr, A.indices, A.data, 0)
+    off = np.zeros(len(colors) + 1, np.int32)
+    off[1:] = np.cumsum([len(c) for c in colors])
+    nodes = np.concatenate(colors).astype(np.int32)
+    pos = np.ascontiguousarray(verts.astype(np.float64))
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    stats = (ctypes.c_longlong * 4)()
+    rc = pkg.cuda_lib.admm_b200_dataflow_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), parts, warps, 4, 3, stats)
+    assert rc == 0, pkg.cuda_lib.admm_b200_last_error(None)
+    assert stats[2] > 0 and stats[0] >= 1
