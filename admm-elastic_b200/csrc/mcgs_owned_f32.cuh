@@ -352,23 +352,26 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 			const int proven = __syncthreads_or((double)lb >= thresh && lb > 0.f);
 			if (PROF) { t_prev_end = clk_ordered(); pb += t_prev_end - t2; --pass; TR(4); ++pass; }
 			if (proven) {
-				// leave a note for parts that cannot prove it themselves; nobody waits here
-				if (tid == 0) { st_relaxed_u32(&R.sweep_flag[it], 1u); atomicAdd(&R.sweep_arrive[it], 1u); }
+				// leave a note for parts that cannot prove it themselves; nobody waits here.  ONE atomic carries both
+				// "arrived" (low 16 bits) and "proved it" (high bits): a waiting part reads a single word, so it can never
+				// see all arrivals without the proof that came with one of them (a separate flag store could be overtaken)
+				if (tid == 0) atomicAdd(&R.sweep_arrive[it], 0x10001u);
 				continue;
 			}
 			double s = block_sum((double)lb, red);
 			if (tid == 0) {
 				int decision = -1;
-				if (s >= thresh) { st_relaxed_u32(&R.sweep_flag[it], 1u); atomicAdd(&R.sweep_arrive[it], 1u); decision = 1; }
+				if (s >= thresh) { atomicAdd(&R.sweep_arrive[it], 0x10001u); decision = 1; } // arrived + proved, in one word
 				else {
 					if (s > 0.0) atomicAdd(&P.resid_lb[it], s);
 					__threadfence();
 					atomicAdd(&R.sweep_arrive[it], 1u);
 					while (decision < 0) {
-						if (ld_relaxed_u32(&R.sweep_flag[it]) != 0u) decision = 1;
-						else if (ld_relaxed_u32(&R.sweep_arrive[it]) == gridDim.x) {
+						const unsigned int v = ld_relaxed_u32(&R.sweep_arrive[it]);
+						if ((v >> 16) != 0u) decision = 1;             // somebody proved "not converged"
+						else if ((v & 0xffffu) == gridDim.x) {          // everybody is here and nobody could: look at the summed bound
 							fence_acq_rel_gpu();
-							decision = (ld_relaxed_u32(&R.sweep_flag[it]) != 0u || __ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
+							decision = (__ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
 						}
 					}
 				}

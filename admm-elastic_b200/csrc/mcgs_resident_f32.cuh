@@ -300,16 +300,17 @@ __global__ void __launch_bounds__(ADMMB200_RES_THREADS, 1) mcgs_resident_f32_ker
 			double s = block_sum(lb, red);
 			if (tid == 0) {
 				int decision = -1;
-				if (s >= thresh) { st_relaxed_u32(&R.sweep_flag[it], 1u); atomicAdd(&R.sweep_arrive[it], 1u); decision = 1; }
+				if (s >= thresh) { atomicAdd(&R.sweep_arrive[it], 0x10001u); decision = 1; } // arrived + proved, in one word
 				else {
 					if (s > 0.0) atomicAdd(&P.resid_lb[it], s);
 					__threadfence();
 					atomicAdd(&R.sweep_arrive[it], 1u);
 					while (decision < 0) {
-						if (ld_relaxed_u32(&R.sweep_flag[it]) != 0u) decision = 1;
-						else if (ld_relaxed_u32(&R.sweep_arrive[it]) == gridDim.x) {
+						const unsigned int v = ld_relaxed_u32(&R.sweep_arrive[it]);
+						if ((v >> 16) != 0u) decision = 1;             // somebody proved "not converged"
+						else if ((v & 0xffffu) == gridDim.x) {          // everybody is here and nobody could: look at the summed bound
 							fence_acq_rel_gpu();
-							decision = (ld_relaxed_u32(&R.sweep_flag[it]) != 0u || __ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
+							decision = (__ldcg(&P.resid_lb[it]) >= thresh) ? 1 : 0;
 						}
 					}
 				}
