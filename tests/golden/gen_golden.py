@@ -122,6 +122,24 @@ def uzawa_floor():
                         iters=np.array([iters]), x_in=x_in, b=bs, x_out=x_out, hits=hits)
 
 
+def unstructured_steps():
+    """Delaunay blob (tests/scenes.py: blob), Neo-Hookean, 3 steps x 8 ADMM iterations with LDLT and with the
+    multi-colour Gauss-Seidel (the reference's colours are stored)."""
+    scene = scenes.blob(pkg.meshes)
+    out = {"verts": scene[0], "tets": scene[1], "masses": scene[2], "pins": scene[3], "x0": scenes.bend(scene[0], 0.08)}
+    for linsolver in (0, 1):
+        s = scenes.build_tet_scene(CpuSolver("ref"), scene, 1, linsolver=linsolver, iters=8)
+        s.set_x(out["x0"].ravel())
+        if linsolver == 1:
+            colors = s.get_colors()
+            out["ls1_color_off"] = np.cumsum([0] + [len(c) for c in colors]).astype(np.int32)
+            out["ls1_color_nodes"] = np.concatenate(colors).astype(np.int32)
+        for _ in range(3):
+            s.step()
+        out["ls%d_x3" % linsolver] = s.get_x()
+    np.savez_compressed(os.path.join(HERE, "unstructured_steps.npz"), **out)
+
+
 def single_tet():
     """test_lineartet.cpp known answers as produced by the reference here."""
     V = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 0]], dtype=np.float64)
@@ -149,4 +167,5 @@ if __name__ == "__main__":
     cloth_steps()
     single_tet()
     uzawa_floor()
+    unstructured_steps()
     print("golden fixtures written to", HERE)

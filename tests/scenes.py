@@ -25,6 +25,31 @@ def cloth(meshes, n=8):
     return v64, tris, masses.astype(np.float64), pins
 
 
+def blob(meshes, n_points=160, seed=3):
+    """An UNSTRUCTURED tet mesh: Delaunay tetrahedralisation of random points in a 1.6 x 1 x 1 box (irregular valence,
+    badly shaped elements near the hull, more colours than a block beam), slivers below 2 % of the mean volume
+    dropped, all elements oriented positively.  Nodes with x below the 12 % quantile are pinned."""
+    from scipy.spatial import Delaunay
+    rng = np.random.RandomState(seed)
+    pts = rng.rand(n_points, 3) * np.array([1.6, 1.0, 1.0])
+    tets = Delaunay(pts).simplices.astype(np.int32)
+    p = pts[tets]
+    vol = np.einsum("ij,ij->i", np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), p[:, 3] - p[:, 0]) / 6.0
+    flip = vol < 0
+    tets[flip] = tets[flip][:, [0, 2, 1, 3]]
+    vol = np.abs(vol)
+    tets = np.ascontiguousarray(tets[vol > 0.02 * vol.mean()])
+    used = np.unique(tets)
+    remap = -np.ones(n_points, dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    verts = np.ascontiguousarray(pts[used].astype(np.float32))   # the reference's meshes are float (AddMeshes.hpp:120)
+    tets = remap[tets].astype(np.int32)
+    masses = meshes.lumped_masses_tets(verts, tets)
+    v64 = verts.astype(np.float64)
+    pins = np.nonzero(v64[:, 0] < np.quantile(v64[:, 0], 0.12))[0].astype(np.int32)
+    return v64, tets, masses.astype(np.float64), pins
+
+
 def bend(x, amount=0.05):
     """A smooth non-rigid deformation so that the prox runs away from F = I."""
     x = x.copy()

@@ -106,3 +106,16 @@ def test_uzawa_with_floor_golden(cpu):
     for k in range(len(g["x_in"])):
         x, _ = s.linsolve(g["x_in"][k], g["b"][k])
         assert np.abs(x - g["x_out"][k]).max() < 1e-10, k
+
+
+@pytest.mark.parametrize("linsolver", [0, 1])
+def test_unstructured_mesh_golden(cpu, linsolver):
+    """Delaunay blob (irregular valence, >= 5 colours): the oracle against the reference's positions after 3 steps."""
+    g = np.load(os.path.join(G, "unstructured_steps.npz"))
+    scene = (g["verts"], g["tets"], g["masses"], g["pins"])
+    colors = colors_from(g, "ls1") if linsolver == 1 else None
+    s = scenes.build_tet_scene(CpuSolver("oracle"), scene, 1, linsolver=linsolver, iters=8, colors=colors)
+    s.set_x(g["x0"].ravel())
+    for _ in range(3):
+        s.step()
+    assert np.abs(s.get_x() - g["ls%d_x3" % linsolver]).max() < 5e-7

@@ -147,6 +147,25 @@ def test_uzawa_with_floor_matches_reference(pkg, cpu):
     assert n_constrained > 5  # the constrained branch was exercised
 
 
+@pytest.mark.parametrize("model,linsolver", [(1, 0), (2, 0), (1, 1), (0, 2)])
+def test_unstructured_mesh_steps_match_reference(pkg, cpu, model, linsolver):
+    """A Delaunay mesh instead of the block beams: irregular valence, poorly shaped elements near the hull, more
+    colours.  Whole steps (prox of every element, assembly, LDLT / multi-colour Gauss-Seidel with the reference's own
+    colours / Uzawa)."""
+    scene = scenes.blob(pkg.meshes)
+    assert len(scene[1]) > 400
+    ref, orc = _pair(pkg, scene, model, linsolver=linsolver, iters=8)
+    if linsolver == 1:
+        assert len(ref.get_colors()) >= 5
+    x0 = scenes.bend(scene[0], 0.08).ravel()
+    ref.set_x(x0)
+    orc.set_x(x0)
+    for step in range(3):
+        ref.step()
+        orc.step()
+    assert np.abs(ref.get_x() - orc.get_x()).max() < 5e-7
+
+
 def test_uzawa_with_sphere_matches_reference(pkg, cpu):
     """As above with a Sphere (normals differ per hit, src/PassiveObject.hpp:47-64): solve by solve on the
     reference's own (x_in, b)."""
