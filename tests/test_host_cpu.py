@@ -176,3 +176,50 @@ def test_barrier_free_schedule_model(pkg, dims, parts, warps):
     rc = pkg.cuda_lib.admm_b200_dataflow_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), parts, warps, 4, 3, stats)
     assert rc == 0, pkg.cuda_lib.admm_b200_last_error(None)
     assert stats[2] > 0 and stats[0] >= 1
+
+
+def test_host_code_on_an_unstructured_mesh(pkg):
+    """The host pieces that only ever saw block beams and cloth -- colouring, nested-dissection LDL^T, resident plan,
+    mailboxes -- on a Delaunay mesh with irregular valence (tests/scenes.py: blob)."""
+    import ctypes
+    import scipy.sparse as sp
+    import scenes
+    verts, tets, masses, pins = scenes.blob(pkg.meshes)
+    n = len(verts)
+    rows, cols = np.repeat(tets, 4, axis=1).ravel(), np.tile(tets, (1, 4)).ravel()
+    A = sp.csr_matrix((np.random.RandomState(0).rand(rows.size) + 0.1, (rows, cols)), shape=(n, n))
+    A = (A + A.T).tolil()
+    A.setdiag(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)
+    A = A.tocsr()
+    A.sort_indices()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
+    # colouring: valid, every node once
+    for method in (0, 1):
+        colors = pkg.color_matrix(rp, ci, va, method)
+        color_of = -np.ones(n, int)
+        for c, l in enumerate(colors):
+            assert (color_of[l] == -1).all()
+            color_of[l] = c
+        coo = A.tocoo()
+        off = coo.row != coo.col
+        assert (color_of >= 0).all() and (color_of[coo.row[off]] != color_of[coo.col[off]]).all()
+    # LDL^T
+    b = np.random.RandomState(1).randn(n)
+    x, stats = pkg.ldlt_solve_host(rp, ci, va, np.ascontiguousarray(verts), b)
+    assert np.abs(A @ x - b).max() < 1e-9 * np.abs(b).max()
+    # resident plan + mailboxes + split-free walk, several part counts and lane widths
+    off = np.zeros(len(colors) + 1, np.int32)
+    off[1:] = np.cumsum([len(c) for c in colors])
+    nodes = np.concatenate(colors).astype(np.int32)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    xx = np.random.RandomState(2).randn(n)
+    pos = np.ascontiguousarray(verts)
+    for parts, lanes in ((148, 1), (9, 1), (148, 4)):
+        err, st, part = ctypes.c_double(0), (ctypes.c_longlong * 6)(), np.zeros(n, np.int32)
+        rc = pkg.cuda_lib.admm_b200_plan_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), parts, 4, lanes,
+                                               dp(xx), ctypes.byref(err), st, ip(part))
+        assert rc == 0, pkg.cuda_lib.admm_b200_last_error(None)
+        assert err.value < 1e-12 and st[4] == A.nnz - n
+    stats4 = (ctypes.c_longlong * 4)()
+    assert pkg.cuda_lib.admm_b200_dataflow_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), 9, 4, 3, 2, stats4) == 0
