@@ -16,9 +16,16 @@
 //   * the reference's "converged?" test (see kernels.cuh, mcgs_kernel) is decided by the end-of-pass
 //     barrier itself (barrier.red.or): ONE node whose own residual row exceeds the threshold proves
 //     "not converged".  Only a CTA in which no node can prove it takes the slow path of the old kernel.
-// Halo exchange (flag-in-data words, double-buffered by sweep parity), multi-GPU pushes, pins, obstacles
-// and the outcome of the convergence test are those of mcgs_resident_f32.cuh; the shared-memory layout
-// is ResidentPlan::layout(mode 1).
+//   * MAILBOXES instead of a node-indexed exchange array: every part has one slot per halo node in its own
+//     halo order (partition.hpp, plan_mailboxes), a boundary node is stored into the slot of every part
+//     that reads it (first two slot ids in registers), so the reader's polls are coalesced.  The words are
+//     the {value, tag} words of mcgs_resident_f32.cuh (no fence, no flag), double-buffered by sweep parity;
+//     a slot on another GPU is written through the peer mapping (st.relaxed.sys), never read.
+//   * x_ref of the part's nodes is staged in the (not yet needed) matrix-value region of shared memory
+//     while r0 = b - A x_ref is formed with the exact fp64 matrix values streamed once; the fp32 values
+//     arrive by TMA bulk copy afterwards.
+// Pins, obstacles and the outcome of the convergence test are those of mcgs_resident_f32.cuh; the
+// shared-memory layout is ResidentPlan::layout(mode 1).
 #pragma once
 #include "mcgs_resident_f32.cuh"
 
@@ -26,7 +33,7 @@ namespace admmb200 {
 
 #define ADMMB200_OWNED_MAX_COLORS 16
 
-struct OwnedSlice {   // registers; everything but l / rb / ia / gid / dm is warp-uniform
+struct OwnedSlice {   // registers; everything but l / rb / ia / dst0 / dst1 is warp-uniform
 	int meta;         // -1: none; else colour | boundary << 8 | pinned << 9 | readers << 10 (pinned, readers: per lane)
 	int r0, r1;       // ELL rows [r0, r1)
 	int l;            // local node id of this lane, -1: padding lane
