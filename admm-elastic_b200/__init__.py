@@ -231,7 +231,7 @@ class Solver(object):
     def __init__(self):
         self.h = ctypes.c_void_p(_host.admmhost_create())
         self._opts = dict(device=0, precision=FP32, gs_max_iters=30, gs_tol=1e-10, gs_omega=1.9,
-                          coloring=COLOR_GREEDY, keep_z=False, timers=True, stream=None)
+                          coloring=COLOR_GREEDY, keep_z=False, timers=True, stream=None, gs_parts=0)
         self._user_colors = None
 
     def close(self):
@@ -318,6 +318,7 @@ class Solver(object):
         _host.admmhost_set_options(self.h, int(o["device"]), int(o["precision"]), int(o["gs_max_iters"]),
                                    ctypes.c_double(o["gs_tol"]), ctypes.c_double(o["gs_omega"]), int(o["coloring"]),
                                    int(bool(o["keep_z"])), int(bool(o["timers"])), ctypes.c_void_p(o["stream"] or 0))
+        _host.admmhost_set_gs_parts(self.h, int(o["gs_parts"]))
 
     def set_timers(self, on):
         """DeviceOptions::timers after initialize(): whether step() / step_device() fill RuntimeData (and synchronise)."""

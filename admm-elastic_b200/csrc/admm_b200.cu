@@ -94,6 +94,7 @@ struct PinsH {
 struct admm_b200_solver {
 	int device = 0;
 	int n_sms = 0;
+	int gs_parts = 0; // parts (= CTAs) of the resident Gauss-Seidel on this GPU: one per SM unless admm_b200_set_gs_parts asked for fewer
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	std::string err;
 	long long launches = 0;
@@ -305,9 +306,11 @@ template <typename E> void launch_tri(S *s, TriBatchH *t)
 	tb.limit_min = E(t->limit_min); tb.limit_max = E(t->limit_max);
 	const int threads = 128;
 	int blocks = (t->n + threads - 1) / threads;
+	fine_begin(s, 0);
 	if (s->store_z && t->d_z.p) tri_local_kernel<E, true><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	else tri_local_kernel<E, false><<<blocks, threads, 0, s->stream>>>(tb, s->cx.p);
 	CK(cudaGetLastError());
+	fine_end(s);
 	s->launches++;
 }
 
@@ -402,7 +405,7 @@ void launch_mcgs_resident(S *s)
 	B.resid = s->res_scratch.p; B.resid_lb = s->res_scratch.p + (s->gs_iters + 2);
 	unsigned int *scr_u = (unsigned int *)(s->res_scratch.p + s->res_scratch_resid_n);
 	B.barrier = scr_u;
-	unsigned int *part_epoch = scr_u + 2, *sweep_flag = part_epoch + 8 * (size_t)s->n_sms, *sweep_arrive = sweep_flag + s->gs_iters;
+	unsigned int *part_epoch = scr_u + 2, *sweep_flag = part_epoch + 8 * (size_t)s->gs_parts, *sweep_arrive = sweep_flag + s->gs_iters;
 	void *args[1];
 	if (fp64) {
 		R.parts = s->res_parts.p; R.col = s->res_col.p; R.val = s->res_val.p; R.gid = s->res_gid.p;
@@ -420,7 +423,7 @@ void launch_mcgs_resident(S *s)
 		if (s->gs_solve_seq == 0) s->gs_solve_seq = 1;
 		R32.tag_base = s->gs_solve_seq << 12;
 		R32.n_nodes_total = s->n_nodes;
-		R32.part0 = s->rank * s->n_sms; R32.world = s->world; R32.rank = s->rank;
+		R32.part0 = s->rank * s->gs_parts; R32.world = s->world; R32.rank = s->rank;
 		{ static const char *dbg = getenv("ADMM_B200_GS_DBG"); R32.dbg = dbg ? atoi(dbg) : 0; }
 		R32.dest_mask = s->world > 1 ? s->mg_dest_mask.p : nullptr;
 		for (int q = 0; q < ADMMB200_MAX_RANKS; ++q) { R32.peer_dglob[q] = s->peer_dglob[q]; R32.peer_x[q] = s->peer_x[q]; }
@@ -430,9 +433,9 @@ void launch_mcgs_resident(S *s)
 	fine_begin(s, 2);
 	if (!fp64 && s->gs_owned_threads > 0) {
 		const void *kern = owned_kernel_ptr(s->gs_owned_threads, !s->obstacles.empty(), s->res_prof.p != nullptr);
-		CK(cudaLaunchCooperativeKernel(kern, dim3(s->n_sms), dim3(s->gs_owned_threads), args, s->gs_res_smem, s->stream));
+		CK(cudaLaunchCooperativeKernel(kern, dim3(s->gs_parts), dim3(s->gs_owned_threads), args, s->gs_res_smem, s->stream));
 	} else
-		CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes, s->res_prof.p != nullptr), dim3(s->n_sms), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
+		CK(cudaLaunchCooperativeKernel(resident_kernel_ptr(fp64, s->gs_res_lanes, s->res_prof.p != nullptr), dim3(s->gs_parts), dim3(ADMMB200_RES_THREADS), args, s->gs_res_smem, s->stream));
 	fine_end(s);
 	s->launches++;
 }
@@ -686,6 +689,15 @@ void build_mcgs_resident(S *s)
 	s->gs_resident = false;
 	if (s->world > 1) require(s->precision == ADMM_B200_FP32 && want != "stream", "multi-GPU needs the resident fp32 Gauss-Seidel (precision FP32)");
 	if (want == "stream") { s->gs_info = "stream (forced)"; return; }
+	if (s->gs_iters < 2) {
+		// The resident kernels stage x_ref (halo included) at the start and write x = x_ref + d at the end of the SAME launch;
+		// what keeps a fast part from overwriting positions a slow neighbour has not staged yet is that it has to wait for that
+		// neighbour's published values first -- guaranteed only when every pair of neighbours exchanges at least once in each
+		// direction, i.e. from the second sweep on.
+		require(s->world == 1 && want != "resident", "the resident Gauss-Seidel needs at least 2 sweeps per solve");
+		s->gs_info = "stream (fewer than 2 sweeps per solve)";
+		return;
+	}
 	const int val_bytes = s->precision == ADMM_B200_FP64 ? 8 : 4;
 	int max_optin = 0;
 	CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
@@ -698,7 +710,7 @@ void build_mcgs_resident(S *s)
 	const size_t budget = (size_t)max_optin - fa.sharedSizeBytes;
 	ResidentPlan R;
 	try {
-		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->n_sms * s->world, lanes);
+		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->gs_parts * s->world, lanes);
 	} catch (std::exception &e) {
 		if (want == "resident" || s->world > 1) throw;
 		s->gs_info = std::string("stream (") + e.what() + ")";
@@ -722,12 +734,12 @@ void build_mcgs_resident(S *s)
 	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);
 	s->res_halo_color.upload(R.halo_color, s->stream);
 	if (s->world > 1) {
-		s->mg_dest_mask.upload(dest_masks(R, s->n_nodes, s->n_sms, s->rank), s->stream);
+		s->mg_dest_mask.upload(dest_masks(R, s->n_nodes, s->gs_parts, s->rank), s->stream);
 		s->mg_flags.alloc(8 * ADMMB200_MAX_RANKS); s->mg_flags.zero(s->stream);
 	}
 	if (val_bytes == 4) {
 		require((long long)s->gs_iters * s->n_colors < 4094, "resident fp32 MCGS: sweeps x colours must stay below 4094 (12-bit pass tags)");
-		plan_mailboxes(R, s->n_nodes, s->n_sms);
+		plan_mailboxes(R, s->n_nodes, s->gs_parts);
 		s->res_parts.upload(R.parts, s->stream); // again: now with the mailbox offsets
 		s->res_dest_off.upload(R.dest_off, s->stream);
 		s->res_dest_slot.upload(R.dest_slot, s->stream);
@@ -736,11 +748,11 @@ void build_mcgs_resident(S *s)
 		s->res_dglob.alloc(6 * std::max((size_t)s->n_nodes, R.total_slots)); s->res_dglob.zero(s->stream);
 		s->res_nodebuf.alloc(2 * (size_t)s->n_nodes); s->res_nodebuf.zero(s->stream);
 	}
-	s->res_sync.alloc(8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1));
+	s->res_sync.alloc(8 * (size_t)s->gs_parts + 2 * (size_t)std::max(s->gs_iters, 1));
 	s->res_scratch_resid_n = 2 * (size_t)s->gs_iters + 4;
-	s->res_scratch.alloc(s->res_scratch_resid_n + (2 + 8 * (size_t)s->n_sms + 2 * (size_t)std::max(s->gs_iters, 1) + 1) / 2 + 1);
+	s->res_scratch.alloc(s->res_scratch_resid_n + (2 + 8 * (size_t)s->gs_parts + 2 * (size_t)std::max(s->gs_iters, 1) + 1) / 2 + 1);
 	require(R.max_nbr <= 192, "resident plan: too many neighbour parts");
-	if (prof) { s->res_prof.alloc(16 * (size_t)s->n_sms + 1024 + 128 * (size_t)s->n_sms); s->res_prof.zero(s->stream); }
+	if (prof) { s->res_prof.alloc(16 * (size_t)s->gs_parts + 1024 + 128 * (size_t)s->gs_parts); s->res_prof.zero(s->stream); }
 	if (val_bytes == 8) {
 		s->res_val.alloc(std::max<size_t>(R.val.size(), 1) * 8);
 		if (!R.val.empty()) CK(cudaMemcpyAsync(s->res_val.p, R.val.data(), R.val.size() * 8, cudaMemcpyHostToDevice, s->stream));
@@ -918,6 +930,9 @@ void build_ldlt(S *s)
 	if (T != 1 && T != 2 && T != 4 && T != 8) T = 4;
 	s->ld_lanes = T;
 	s->ld_grid = s->n_sms;
+	char buf[256];
+	snprintf(buf, sizeof(buf), "ldlt: n %d, nnz(L) %lld, dependency levels %d forward + %d backward, %d lane(s)/row, %d CTAs", n, (long long)Lp[n], nlf, nlb, T, s->ld_grid);
+	s->gs_info = buf;
 }
 
 // Events tightly around the hot kernels (timers on): kind 0 tet prox, 1 assemble, 2 solve.  Summed after the step.
@@ -1172,6 +1187,7 @@ int admm_b200_create(int device, admm_b200_solver **out)
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, device));
 		s->n_sms = prop.multiProcessorCount;
+		s->gs_parts = s->n_sms;
 		if (!prop.cooperativeLaunch) throw std::runtime_error("device lacks cooperative launch");
 		CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
 		s->stream = s->own_stream;
@@ -1366,6 +1382,17 @@ int admm_b200_set_rank(admm_b200_solver *s, int rank, int world)
 }
 
 int admm_b200_device_sms(const admm_b200_solver *s) { return s ? s->n_sms : 0; }
+
+int admm_b200_gs_parts(const admm_b200_solver *s) { return s ? s->gs_parts : 0; }
+
+int admm_b200_set_gs_parts(admm_b200_solver *s, int n_parts)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_gs_parts after finalize");
+		require(n_parts >= 0 && n_parts <= s->n_sms, "set_gs_parts: between 1 and the SM count (0 = one part per SM)");
+		s->gs_parts = n_parts > 0 ? n_parts : s->n_sms;
+	});
+}
 
 namespace {
 struct IpcBlob { cudaIpcMemHandle_t x, dglob, flags; int rank, n_nodes; };

@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 	for (int i = tid; i < n_loc; i += NT) {
 		const int g = R.gid[d.gid_off + i];
 		s_gid[i] = g; s_d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-		const double4 xg = ld_node(&P.x[g]);
+		// L2-coherent loads: other parts (and peer GPUs) write P.x at the end of this same kernel and of the previous
+		// solve; the read-only path is not allowed to see memory that changes during the kernel
+		const double4 xg = ld_node_cg(&P.x[g]);
 		s_x[3 * i] = xg.x; s_x[3 * i + 1] = xg.y; s_x[3 * i + 2] = xg.z;
 	}
 	for (int i = tid; i <= 2 * C; i += NT) s_cslice[i] = R.color_slice[d.cslice_off + i];
@@ -140,6 +142,9 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 		int c, sl; bool bnd;
 		if (locate(k * NW + warp, c, bnd, sl)) {
 			S[k].meta = c | (bnd ? 0x100 : 0);
+			// a warp's SECOND boundary slice of one colour (parts with more than NW boundary slices in a colour): bit 16
+#pragma unroll
+			for (int j = 0; j < k; ++j) if (bnd && S[j].meta >= 0 && (S[j].meta & 0x1ff) == (c | 0x100)) S[k].meta |= 0x10000;
 			S[k].r0 = __ldg(&R.slice_row[d.slice_off + sl]);
 			S[k].r1 = __ldg(&R.slice_row[d.slice_off + sl + 1]);
 			S[k].l = (int)__ldg(&R.slice_node[d.snode_off + sl * 32 + lane]);
@@ -264,10 +269,12 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 			long long t0 = 0, t1 = 0;
 			if (PROF) { t0 = clk_ordered(); if (t_prev_end) po += t0 - t_prev_end; TR(0); }
 			// readers 3 and 4 of a corner node: their slots come from L2 -- asked for now, used after the gather
+			// (prefetched for the FIRST boundary slice of this colour the warp owns; a part with more than NW
+			// boundary slices of one colour gives a warp a second one, which loads its slots after its gather instead)
 			int pre_e0 = 0; unsigned int pre2 = 0u, pre3 = 0u;
 #pragma unroll
 			for (int k = 0; k < KMAX; ++k) {
-				if (S[k].meta < 0 || (S[k].meta & 0x1ff) != (color | 0x100) || S[k].l < 0) continue;
+				if (S[k].meta < 0 || (S[k].meta & 0x101ff) != (color | 0x100) || S[k].l < 0) continue;
 				const int cnt = (S[k].meta >> 10) & 63;
 				if (cnt > 2) {
 					pre_e0 = __ldg(&R.dest_off[d.own_off + S[k].l]);
@@ -341,9 +348,13 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 					};
 					if (cnt > 0) put(S[k].dst0);
 					if (cnt > 1) put(S[k].dst1);
-					if (cnt > 2) put(pre2); // a corner node read by more than two parts
-					if (cnt > 3) put(pre3);
-					for (int e = pre_e0 + 4; e < pre_e0 + cnt; ++e) put(__ldg(&R.dest_slot[e]));
+					if (cnt > 2) { // a corner node read by more than two parts
+						int e0 = pre_e0; unsigned int p2 = pre2, p3 = pre3;
+						if (S[k].meta & 0x10000) { e0 = __ldg(&R.dest_off[d.own_off + l]); p2 = __ldg(&R.dest_slot[e0 + 2]); if (cnt > 3) p3 = __ldg(&R.dest_slot[e0 + 3]); }
+						put(p2);
+						if (cnt > 3) put(p3);
+						for (int e = e0 + 4; e < e0 + cnt; ++e) put(__ldg(&R.dest_slot[e]));
+					}
 					if (PROF && (R.dbg & 64)) __threadfence(); // timing experiment: does a fence get the published words out sooner?
 					if (PROF && lane == 0 && R.world == 1) atomicMax(R.prof + 16 * gridDim.x + 1024 + (size_t)(R.part0 + blockIdx.x) * 128 + (pass & 127), gtime_ns());
 				}

@@ -321,6 +321,7 @@ public:
 		// SAME scene; initialize() keeps the elements that touch a node this rank owns.  After initialize()
 		// the ranks swap mgpu_export() blobs and feed them to mgpu_import() (see include/admm_b200.h).
 		int rank = 0, world = 1;
+		int gs_parts = 0;                // parts of the resident Gauss-Seidel per GPU (0: one per SM), see admm_b200_set_gs_parts
 	} device_options;
 
 	Solver() : initialized(false), handle(nullptr) {}
@@ -452,6 +453,7 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 		throw std::runtime_error(ss.str());
 	}
 	if (device_options.stream) check(admm_b200_set_stream(handle, device_options.stream), "set_stream");
+	if (device_options.gs_parts > 0) check(admm_b200_set_gs_parts(handle, device_options.gs_parts), "set_gs_parts");
 
 	// Energy-based hard constraints (src/Solver.cpp:190-196).  The reference appends them again on
 	// every initialize(); here terms added by an earlier initialize() are dropped first
@@ -541,7 +543,7 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 		if (m_settings.linsolver != 1) throw std::runtime_error("**admm_b200::Solver Error: multi-GPU needs the NodalMultiColorGS solver (-ls 1)");
 		if (!rgroups.empty() || !p_idx.empty()) throw std::runtime_error("**admm_b200::Solver Error: multi-GPU supports tet meshes only");
 		check(admm_b200_set_rank(handle, rank, world), "set_rank");
-		const int sms = admm_b200_device_sms(handle);
+		const int sms = admm_b200_gs_parts(handle);
 		std::vector<int> part(n_nodes);
 		if (admm_b200_plan_parts(n_nodes, scalarL.rowptr.data(), scalarL.cols.data(), scalarL.vals.data(), m_x.data(), world * sms, part.data()))
 			throw std::runtime_error(std::string("**admm_b200 plan_parts: ") + admm_b200_last_error(nullptr));

@@ -83,6 +83,8 @@ int admmhost_set_options(void *h_, int device, int precision, int gs_max_iters, 
 	return 0;
 }
 
+int admmhost_set_gs_parts(void *h_, int n_parts) { ((Host *)h_)->solver.device_options.gs_parts = n_parts; return 0; }
+
 int admmhost_set_rank(void *h_, int rank, int world) {
 	Host *h = (Host *)h_;
 	h->solver.device_options.rank = rank; h->solver.device_options.world = world;

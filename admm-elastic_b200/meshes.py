@@ -66,6 +66,47 @@ def make_plane(nx, ny, width=2.0):
     return verts.astype(np.float32), tris
 
 
+def make_plane_sym(tess_x, tess_y):
+    """mcl::factory::make_plane (deps/mclscene/include/MCL/ShapeFactory.hpp:424-484): a [-1,1]^2 sheet in the xy-plane,
+    (tess_x+1)(tess_y+1) grid vertices followed by one centre vertex per cell, 4 triangles per cell in mkquad_sym's
+    order (ll,lr,c) (lr,ur,c) (c,ur,ul) (ll,c,ul).  512 x 512 gives BASELINE config 4's 525 313 vertices / 1 048 576
+    triangles.  float32 arithmetic like the reference."""
+    tx, ty = max(1, tess_x), max(1, tess_y)
+    gx, gy = np.meshgrid(np.arange(tx + 1), np.arange(ty + 1), indexing="ij")
+    f = np.float32
+    grid = np.stack([f(-1.0) + f(2.0) * gx.ravel().astype(f) / f(tx), f(-1.0) + f(2.0) * gy.ravel().astype(f) / f(ty),
+                     np.zeros(gx.size, f)], axis=1)
+    cx, cy = np.meshgrid(np.arange(tx), np.arange(ty), indexing="ij")
+    cx, cy = cx.ravel(), cy.ravel()
+    cen = np.stack([f(-1.0) + f(2.0) * cx.astype(f) / f(tx) + f(1.0) / f(tx), f(-1.0) + f(2.0) * cy.astype(f) / f(ty) + f(1.0) / f(ty),
+                    np.zeros(cx.size, f)], axis=1)
+    verts = np.concatenate([grid, cen], axis=0).astype(np.float32)
+    ll = cy + cx * (ty + 1)
+    lr = cy + (cx + 1) * (ty + 1)
+    ul, ur = ll + 1, lr + 1
+    c = (tx + 1) * (ty + 1) + cx * ty + cy
+    quads = np.stack([np.stack([ll, lr, c], 1), np.stack([lr, ur, c], 1), np.stack([c, ur, ul], 1), np.stack([ll, c, ul], 1)], axis=1)
+    return verts, quads.reshape(-1, 3).astype(np.int32)
+
+
+def cloth_corner_pins(verts):
+    """get_pins of samples/sca2016/trianglestrain.cpp:103-135: among the vertices of the top edge (y >= max_y - 1e-3) the
+    one with the smallest and the one with the largest x, scanned in index order with the sample's if / else-if."""
+    v = np.asarray(verts, dtype=np.float32)
+    top = np.nonzero(~(v[:, 1] < v[:, 1].max() - np.float32(1e-3)))[0]
+    left = right = -1
+    mn, mx = np.float32(99999.0), np.float32(-99999.0)
+    for i in top:
+        x = v[i, 0]
+        if x < mn:
+            left, mn = int(i), x
+        elif x > mx:
+            right, mx = int(i), x
+    if left < 0 or right < 0:
+        raise RuntimeError("Failed to find pin locations")
+    return np.array([left, right], dtype=np.int32)
+
+
 def lumped_masses_tets(verts, tets, density=1522.0):
     """float32 lumped vertex masses, a quarter of each tet's mass per corner."""
     v = verts.astype(np.float32)

@@ -195,8 +195,8 @@ long long admm_b200_launch_count( const admm_b200_solver *s );
 
 /* ---- multi-GPU: one handle per rank (process), at most 8 ranks on one NVLink box ----------------
  * Every rank is handed the SAME nodes, system matrix, colours and pins, but only the elements that touch
- * a node it owns (node -> part from admm_b200_plan_parts with n_parts = world * admm_b200_device_sms();
- * owner rank = part / sms).  Elements on a cut are therefore computed by both neighbours (a few per
+ * a node it owns (node -> part from admm_b200_plan_parts with n_parts = world * admm_b200_gs_parts();
+ * owner rank = part / gs_parts).  Elements on a cut are therefore computed by both neighbours (a few per
  * cent), which makes the right-hand side assembly local.  The one exchange of the path -- neighbour
  * values inside the Gauss-Seidel sweeps and the solved positions of cut nodes -- is done by the solve
  * kernel itself with stores into the peers' memory (CUDA IPC mappings of their buffers); the 256-byte
@@ -205,6 +205,12 @@ long long admm_b200_launch_count( const admm_b200_solver *s );
 #define ADMM_B200_IPC_BYTES 256
 int admm_b200_set_rank( admm_b200_solver *s, int rank, int world );                /* before finalize */
 int admm_b200_device_sms( const admm_b200_solver *s );
+/* Parts (= CTAs, one per SM by default) of the shared-memory-resident Gauss-Seidel on this GPU.  Fewer, larger parts
+ * are a testing aid: a 100k-tet mesh cut into 16 parts gives each part as many nodes, slices per warp, halo nodes and
+ * neighbours as the 1M-tet bench mesh has with 148, at a size the CPU reference finishes in a second.  Before finalize;
+ * 0 = one part per SM.  With several ranks the owner of a node is part / admm_b200_gs_parts(). */
+int admm_b200_set_gs_parts( admm_b200_solver *s, int n_parts );
+int admm_b200_gs_parts( const admm_b200_solver *s );
 int admm_b200_plan_parts( int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, int n_parts, int *part_of );
 int admm_b200_mgpu_export( admm_b200_solver *s, void *blob );                      /* after finalize */
 int admm_b200_mgpu_import( admm_b200_solver *s, int peer_rank, const void *blob );

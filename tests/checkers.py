@@ -88,6 +88,8 @@ class CpuSolver(object):
             self.L, self.p = ref_lib(), "ref_"
         self.h = ctypes.c_void_p(self._f("create")())
         self.linsolver = 0
+        self._initialized = False
+        self._colors = None
 
     def _f(self, name):
         return getattr(self.L, self.p + name)
@@ -149,6 +151,8 @@ class CpuSolver(object):
         off[1:] = np.cumsum([len(c) for c in colors])
         nodes = np.concatenate([np.asarray(c, dtype=np.int32) for c in colors]).astype(np.int32)
         self._colors = (off, nodes)
+        if self.kind == "ref" and not self._initialized:
+            return  # NodalMultiColorGS exists only after initialize(): applied there
         self._f("set_colors")(self.h, len(colors), ip(off), ip(nodes))
 
     def get_colors(self):
@@ -165,7 +169,12 @@ class CpuSolver(object):
         self.linsolver = linsolver
         if self.kind == "oracle":
             return self._ck(self.L.oracle_initialize(self.h, D(dt), int(admm_iters), D(gravity), int(linsolver)))
-        return self._ck(self.L.ref_initialize(self.h, D(dt), int(admm_iters), D(gravity), int(linsolver), D(constraint_w)))
+        ok = self._ck(self.L.ref_initialize(self.h, D(dt), int(admm_iters), D(gravity), int(linsolver), D(constraint_w)))
+        self._initialized = bool(ok)
+        if ok and linsolver == 1 and self._colors is not None:
+            off, nodes = self._colors   # replace the reference's own (randomised) colour lists by the caller's
+            self.L.ref_set_colors(self.h, len(off) - 1, ip(off), ip(nodes))
+        return ok
 
     def step(self):
         self._ck(self._f("step")(self.h))

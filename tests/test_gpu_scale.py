@@ -1,0 +1,198 @@
+"""Parity of the PRODUCTION fp32 path at production density, against the compiled reference (oracle/_ref, the
+unmodified admm::Solver built by oracle/Makefile) on identical inputs and identical colour lists.
+
+The small-scene tests of test_gpu_parity.py give every part of the resident Gauss-Seidel 1-16 nodes, so a warp owns at
+most one slice.  Here the parts are as large as on the 1M-tet bench mesh (>= 1000 owned nodes, several slices per warp,
+hundreds of halo nodes, a dozen neighbour parts):
+
+  * 100k-tet beam cut into 16 parts (admm_b200_set_gs_parts): 1 458 nodes per part -- the reference needs ~0.3 s per
+    ADMM iteration, so whole steps with both colourings (ours, 4 colours -> mcgs_owned_f32<512,4>; the reference's own
+    randomised ~13 colours -> the 768-thread / table-walking variants) stay cheap;
+  * ONE 5-iteration step of the 1M-tet bench scene itself with 148 parts (marked slow but kept in -m gpu).
+
+Gate: max |x_gpu - x_ref| <= 1e-4 x bounding-box diagonal; the achieved figure is recorded in
+gpurun_out/parity_report.jsonl.  Each test also asserts WHICH solve kernel ran (admm_b200_solver_info).
+"""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+import checkers
+import scenes
+from checkers import CpuSolver
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MU, LAM = scenes.lame(*scenes.LAME_SOFT)
+GATE = 1e-4          # x bbox diagonal
+DENSITY = 1522.0
+
+
+def record(name, **kw):
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=name, **{k: (v if isinstance(v, str) else float(v)) for k, v in kw.items()})) + "\n")
+    except OSError:
+        pass
+
+
+def bench_beam(meshes, nx, ny, nz):
+    """The bench scene (bench.py: make_scene): a cantilever block beam started from a smoothly bent state."""
+    verts, tets = meshes.make_tet_blocks(nx, ny, nz)
+    masses = meshes.lumped_masses_tets(verts, tets, DENSITY).astype(np.float64)
+    v64 = verts.astype(np.float64)
+    pins = np.nonzero(v64[:, 0] < v64[:, 0].min() + 1e-2)[0].astype(np.int32)
+    x0 = v64.copy()
+    L = x0[:, 0].max() - x0[:, 0].min()
+    s = (x0[:, 0] - x0[:, 0].min()) / L
+    x0[:, 1] -= 0.08 * L * s * s
+    x0[:, 2] += 0.02 * L * np.sin(3.0 * s)
+    return (v64, tets, masses, pins), x0
+
+
+def need_ref():
+    if not checkers.have_ref():
+        pytest.skip("oracle/_ref/libadmm_ref.so is not built (needs /root/reference at build time)")
+
+
+def ref_solver(scene, model, iters, colors=None, floor=None):
+    s = CpuSolver("ref")
+    try:
+        checkers.ref_lib().ref_set_omp_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    scenes.build_tet_scene(s, scene, model, linsolver=1, iters=iters, colors=colors, floor=floor, pin=floor is None)
+    return s
+
+
+def gpu_solver(pkg, scene, model, iters, colors=None, floor=None, gs_parts=0):
+    s = pkg.Solver()
+    s.set_options(precision=pkg.FP32, gs_parts=gs_parts)
+    if colors is not None:
+        s.set_colors(colors)
+        s.set_options(coloring=pkg.COLOR_USER)
+    scenes.build_tet_scene(s, scene, model, linsolver=1, iters=iters, floor=floor, pin=floor is None)
+    return s
+
+
+def run_pair(pkg, scene, x0, model, iters, steps, whose_colors, gs_parts, floor=None):
+    """Same scene, same start, same colour lists on both sides; returns (max |dx| / bbox, info, n_colors, inner_iters)."""
+    if whose_colors == "gpu":
+        gpu = gpu_solver(pkg, scene, model, iters, floor=floor, gs_parts=gs_parts)
+        colors = gpu.colors()
+        ref = ref_solver(scene, model, iters, colors=colors, floor=floor)
+    else:
+        ref = ref_solver(scene, model, iters, floor=floor)
+        colors = ref.get_colors()
+        gpu = gpu_solver(pkg, scene, model, iters, colors=colors, floor=floor, gs_parts=gs_parts)
+    assert [list(c) for c in gpu.colors()] == [list(c) for c in colors]   # colour lists bit-exact on both sides
+    for s in (gpu, ref):
+        s.set_x(x0.ravel())
+    inner = 0
+    t_ref = 0.0
+    for _ in range(steps):
+        gpu.step()
+        inner += gpu.runtime_data()["inner_iters"]
+        t0 = time.time()
+        ref.step()
+        t_ref += time.time() - t0
+        assert ref.runtime_data()["inner_iters"] == 30 * iters
+    xg, xr = gpu.get_x(), ref.get_x()
+    assert np.isfinite(xg).all()
+    bbox = float(np.linalg.norm(scene[0].max(0) - scene[0].min(0)))
+    err = float(np.abs(xg - xr).max()) / bbox
+    moved = float(np.abs(xr - x0.ravel()).max()) / bbox
+    info = gpu.device().info()
+    ref.close()
+    gpu.close()
+    return err, info, len(colors), inner, moved, t_ref
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_100k_beam_production_kernel_vs_reference(pkg, cpu, model):
+    """mcgs_owned_f32<512,4> + tet_local_kernel<float,...,8> + assemble_kernel<float>, parts of 1 458 nodes."""
+    need_ref()
+    scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
+    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, model, iters=5, steps=2, whose_colors="gpu", gs_parts=16)
+    record("scale_100k_owned512", model=model, err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref)
+    assert "static-ownership kernel, 512 threads" in info, info
+    assert inner == 2 * 5 * 30
+    assert moved > 10 * GATE       # the beam really moved: the comparison is not vacuous
+    assert err < GATE, err
+
+
+def test_100k_beam_reference_colouring(pkg, cpu):
+    """The reference's own randomised colour lists (12-14 colours): more slices per part than the 512-thread variant
+    holds, so the 768-thread variant or the table-walking kernel run -- whichever finalize picks is named and checked."""
+    need_ref()
+    scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
+    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=2, whose_colors="ref", gs_parts=16)
+    record("scale_100k_refcolors", err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref)
+    assert nc >= 8, nc
+    assert info.startswith("resident"), info
+    assert inner == 2 * 5 * 30
+    assert err < GATE, err
+
+
+def test_100k_beam_reference_colouring_148_parts(pkg, cpu):
+    """Same with the default one part per SM (small parts, many colours)."""
+    need_ref()
+    scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
+    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=1, whose_colors="ref", gs_parts=0)
+    record("scale_100k_refcolors_148", err_over_bbox=err, n_colors=nc, info=info, ref_seconds=t_ref)
+    assert info.startswith("resident"), info
+    assert err < GATE, err
+
+
+def test_100k_beam_floor_inside_the_sweep(pkg, cpu):
+    """BASELINE config 3 style at production density: StVK, no pins, the beam drops on a Floor handled inside the
+    Gauss-Seidel sweep (the OBST instantiation of the production kernel)."""
+    need_ref()
+    scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
+    floor_y = float(x0[:, 1].min() + 0.02)   # the bent tip starts below the floor: hits from the first sweep on
+    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 2, iters=5, steps=2, whose_colors="gpu", gs_parts=16, floor=floor_y)
+    record("scale_100k_floor", err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref)
+    assert "static-ownership kernel" in info, info
+    assert err < GATE, err
+
+
+@pytest.mark.slow
+def test_1m_bench_scene_one_step_vs_reference(pkg, cpu):
+    """The benchmarked configuration itself: 1M-tet Neo-Hookean beam, 148 parts, greedy colours, ONE 5-iteration step."""
+    need_ref()
+    scene, x0 = bench_beam(pkg.meshes, 320, 25, 25)
+    t0 = time.time()
+    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=1, whose_colors="gpu", gs_parts=0)
+    record("scale_1m_bench_scene", err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref, total_seconds=time.time() - t0)
+    assert "static-ownership kernel, 512 threads" in info, info
+    assert inner == 5 * 30
+    assert err < GATE, err
+
+
+@pytest.mark.parametrize("linsolver", [0, 1])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_unstructured_mesh_golden(pkg, linsolver, precision):
+    """Delaunay blob (irregular valence, badly shaped hull elements, the reference's 12 colours): the device path against
+    the compiled reference's positions after 3 steps (tests/golden/unstructured_steps.npz)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "unstructured_steps.npz"))
+    scene = (g["verts"], g["tets"], g["masses"], g["pins"])
+    s = pkg.Solver()
+    s.set_options(precision=precision)
+    if linsolver == 1:
+        off, nodes = g["ls1_color_off"], g["ls1_color_nodes"]
+        s.set_colors([nodes[off[i]:off[i + 1]] for i in range(len(off) - 1)])
+        s.set_options(coloring=pkg.COLOR_USER)
+    scenes.build_tet_scene(s, scene, 1, linsolver=linsolver, iters=8)
+    s.set_x(g["x0"].ravel())
+    for _ in range(3):
+        s.step()
+    bbox = float(np.linalg.norm(g["verts"].max(0) - g["verts"].min(0)))
+    err = float(np.abs(s.get_x() - g["ls%d_x3" % linsolver]).max())
+    record("unstructured_golden", linsolver=linsolver, precision=precision, err=err, err_over_bbox=err / bbox)
+    assert err < (2e-6 if precision else GATE * bbox), err

@@ -7,7 +7,7 @@ pkg=g.load_package()
 args=argparse.Namespace(workload='beam_1m',model=1,admm_iters=20,linsolver=1,precision=0)
 scene=bench.make_scene(pkg,'beam_1m'); mu,lam=pkg.meshes.lame(*bench.LAME)
 sol=pkg.Solver(); sol.set_options(precision=0,timers=True)
-sol.add_nodes(scene['verts'],scene['masses']); sol.add_tets(scene['verts'],scene['tets'],1,mu,lam); sol.set_pins(scene['pins'])
+sol.add_nodes(scene['verts'],scene['masses']); sol.add_tets(scene['verts'],scene['elems'],1,mu,lam); sol.set_pins(scene['pins'])
 assert sol.initialize(dt=1/24,admm_iters=20,gravity=-9.8,linsolver=1)
 sol.set_x(scene['x0'].ravel()); sol.upload_state()
 for _ in range(3): sol.step_device()

@@ -1,0 +1,181 @@
+// tools/micro/gather_bench.cu -- what does ONE slice of the resident Gauss-Seidel cost on an SM?  (study aid, not product)
+//
+// mcgs_owned_f32_kernel spends ~2 200 cycles on a slice (32 nodes x ~18 sliced-ELL rows gathered from shared memory)
+// whether 4 or 12 warps are busy; the shared-memory pipe would allow ~200.  This program runs the gather of
+// mcgs_owned_f32.cuh on a synthetic part of the bench mesh's size (1 530 own + 820 halo nodes, 873 rows, 48 slices)
+// and prints cycles per slice for 1..16 concurrently active warps and for several formulations of the inner loop:
+//   v0  owned_gather as shipped (batches of 8, clamped tail)
+//   v1  plain loop, unroll 4
+//   v2  batches of 8 without the clamp (rows padded to a multiple of 8 in the data)
+//   v3  columns pre-multiplied (byte offsets as u16 * 16 via shift hoisted), values as float
+//   v4  one 32-bit word per entry: column in the high 16 bits, value as bf16-truncated fp32?  NO -- precision; instead
+//       v4 = two entries per 64-bit word (u16 col, u16 col, packed) + separate float2 values: half the index loads
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gather_bench tools/micro/gather_bench.cu && ./gather_bench
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+__device__ __forceinline__ void gather_v0(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
+	int r0, int r1, int lane, float &sx, float &sy, float &sz)
+{
+	sx = 0.f; sy = 0.f; sz = 0.f;
+	const float *v = s_val + r0 * 32 + lane;
+	const uint16_t *c = s_col + r0 * 32 + lane;
+	const int n = r1 - r0;
+	for (int r = 0; r < n; r += 8) {
+		int cc[8]; float a[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const int rr = min(r + j, n - 1);
+			cc[j] = c[rr * 32];
+			a[j] = (r + j < n) ? v[rr * 32] : 0.f;
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const float4 dv = s_d[cc[j]];
+			sx = fmaf(a[j], dv.x, sx); sy = fmaf(a[j], dv.y, sy); sz = fmaf(a[j], dv.z, sz);
+		}
+	}
+}
+
+__device__ __forceinline__ void gather_v1(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
+	int r0, int r1, int lane, float &sx, float &sy, float &sz)
+{
+	sx = 0.f; sy = 0.f; sz = 0.f;
+#pragma unroll 4
+	for (int r = r0; r < r1; ++r) {
+		const int c = s_col[r * 32 + lane];
+		const float a = s_val[r * 32 + lane];
+		const float4 dv = s_d[c];
+		sx = fmaf(a, dv.x, sx); sy = fmaf(a, dv.y, sy); sz = fmaf(a, dv.z, sz);
+	}
+}
+
+// whole batches only: the caller guarantees (r1 - r0) % 8 == 0 (padding rows carry a zero coefficient)
+__device__ __forceinline__ void gather_v2(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
+	int r0, int r1, int lane, float &sx, float &sy, float &sz)
+{
+	sx = 0.f; sy = 0.f; sz = 0.f;
+	const float *v = s_val + r0 * 32 + lane;
+	const uint16_t *c = s_col + r0 * 32 + lane;
+	const int n = r1 - r0;
+	for (int r = 0; r < n; r += 8) {
+		int cc[8]; float a[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) { cc[j] = c[(r + j) * 32]; a[j] = v[(r + j) * 32]; }
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const float4 dv = s_d[cc[j]];
+			sx = fmaf(a[j], dv.x, sx); sy = fmaf(a[j], dv.y, sy); sz = fmaf(a[j], dv.z, sz);
+		}
+	}
+}
+
+// the whole row (<= 24 entries) in flight at once: 3 batches issued before the first use
+__device__ __forceinline__ void gather_v3(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
+	int r0, int r1, int lane, float &sx, float &sy, float &sz)
+{
+	sx = 0.f; sy = 0.f; sz = 0.f;
+	const float *v = s_val + r0 * 32 + lane;
+	const uint16_t *c = s_col + r0 * 32 + lane;
+	const int n = r1 - r0;
+	for (int r = 0; r < n; r += 16) {
+		int cc[16]; float a[16];
+#pragma unroll
+		for (int j = 0; j < 16; ++j) {
+			const int rr = min(r + j, n - 1);
+			cc[j] = c[rr * 32];
+			a[j] = (r + j < n) ? v[rr * 32] : 0.f;
+		}
+		float4 dv[16];
+#pragma unroll
+		for (int j = 0; j < 16; ++j) dv[j] = s_d[cc[j]];
+#pragma unroll
+		for (int j = 0; j < 16; ++j) { sx = fmaf(a[j], dv[j].x, sx); sy = fmaf(a[j], dv[j].y, sy); sz = fmaf(a[j], dv[j].z, sz); }
+	}
+}
+
+template <int V>
+__global__ void __launch_bounds__(512, 1) bench_kernel(const float *g_val, const uint16_t *g_col, const int *g_srow, int n_loc, int n_rows, int n_slices,
+	int active_warps, int reps, int sync_mode, long long *out)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	float4 *s_d = (float4 *)smem;
+	float *s_val = (float *)(smem + 16 * (size_t)n_loc);
+	uint16_t *s_col = (uint16_t *)(smem + 16 * (size_t)n_loc + 4 * 32 * (size_t)n_rows);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (int i = tid; i < n_loc; i += blockDim.x) s_d[i] = make_float4(1e-3f * i, 2e-3f * i, -1e-3f * i, 0.f);
+	for (int i = tid; i < 32 * n_rows; i += blockDim.x) { s_val[i] = g_val[i]; s_col[i] = g_col[i]; }
+	__syncthreads();
+	float acc = 0.f;
+	long long t0 = clock64();
+	for (int rep = 0; rep < reps; ++rep) {
+		if (warp < active_warps) {
+			const int sl = (warp + rep * 5) % n_slices;
+			const int r0 = g_srow[sl], r1 = g_srow[sl + 1];
+			float sx, sy, sz;
+			if (V == 0) gather_v0(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
+			else if (V == 1) gather_v1(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
+			else if (V == 2) gather_v2(s_val, s_col, s_d, r0, r0 + ((r1 - r0) & ~7), lane, sx, sy, sz);
+			else gather_v3(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
+			// the update: write the node's own entry (as the sweep does)
+			const int l = (sl * 32 + lane) % n_loc;
+			float4 dold = s_d[l];
+			s_d[l] = make_float4(0.1f * dold.x + 1e-6f * sx, 0.1f * dold.y + 1e-6f * sy, 0.1f * dold.z + 1e-6f * sz, 0.f);
+			acc += sx;
+		}
+		if (sync_mode == 1) __syncthreads();
+	}
+	long long t1 = clock64();
+	if (lane == 0) out[blockIdx.x * 16 + warp] = t1 - t0;
+	if (acc == 123.456f) out[0] = 0;
+}
+
+int main()
+{
+	const int n_own = 1530, n_halo = 820, n_loc = n_own + n_halo, n_slices = 48;
+	std::vector<int> srow(n_slices + 1, 0);
+	srand(1);
+	for (int s = 0; s < n_slices; ++s) srow[s + 1] = srow[s] + 16 + (s % 5); // 16..20 rows per slice, ~873 in total
+	const int n_rows = srow[n_slices];
+	std::vector<float> val(32 * (size_t)n_rows);
+	std::vector<uint16_t> col(32 * (size_t)n_rows);
+	for (size_t i = 0; i < val.size(); ++i) { val[i] = (float)(rand() % 1000) * 1e-3f; col[i] = (uint16_t)(rand() % n_loc); }
+	// a second column pattern with mesh-like locality: neighbours within +-64 of the node
+	std::vector<uint16_t> col_local(col.size());
+	for (int s = 0; s < n_slices; ++s) for (int r = srow[s]; r < srow[s + 1]; ++r) for (int l = 0; l < 32; ++l) {
+		int node = (s * 32 + l) % n_own;
+		int c = node + (rand() % 129) - 64; if (c < 0) c += n_loc; if (c >= n_loc) c -= n_loc;
+		col_local[(size_t)r * 32 + l] = (uint16_t)c;
+	}
+	float *d_val; uint16_t *d_col, *d_col2; int *d_srow; long long *d_out;
+	CK(cudaMalloc(&d_val, val.size() * 4)); CK(cudaMalloc(&d_col, col.size() * 2)); CK(cudaMalloc(&d_col2, col.size() * 2)); CK(cudaMalloc(&d_srow, srow.size() * 4)); CK(cudaMalloc(&d_out, 148 * 16 * 8));
+	CK(cudaMemcpy(d_val, val.data(), val.size() * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_col, col.data(), col.size() * 2, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_col2, col_local.data(), col.size() * 2, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_srow, srow.data(), srow.size() * 4, cudaMemcpyHostToDevice));
+	const size_t smem = 16 * (size_t)n_loc + 6 * 32 * (size_t)n_rows;
+	printf("part: %d local nodes, %d rows, %d slices, %zu B shared memory\n", n_loc, n_rows, n_slices, smem);
+	const void *kern[4] = {(const void *)bench_kernel<0>, (const void *)bench_kernel<1>, (const void *)bench_kernel<2>, (const void *)bench_kernel<3>};
+	for (int v = 0; v < 4; ++v) CK(cudaFuncSetAttribute(kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const int reps = 200;
+	for (int pat = 0; pat < 2; ++pat)
+		for (int v = 0; v < 4; ++v)
+			for (int sync_mode = 0; sync_mode < 2; ++sync_mode)
+				for (int aw : {1, 2, 4, 8, 12, 16}) {
+					const uint16_t *dc = pat ? d_col2 : d_col;
+					int nl = n_loc, nr = n_rows, ns = n_slices, r = reps, sm = sync_mode;
+					void *args[] = {&d_val, &dc, &d_srow, &nl, &nr, &ns, &aw, &r, &sm, &d_out};
+					for (int w = 0; w < 2; ++w) CK(cudaLaunchKernel(kern[v], dim3(148), dim3(512), args, smem, 0));
+					CK(cudaDeviceSynchronize());
+					long long h[16];
+					CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+					printf("columns %-6s v%d %-12s active warps %2d: %6.0f cycles per slice-step (warp 0), %6.0f cycles per slice of pipe time\n", pat ? "local" : "random", v,
+						sync_mode ? "syncthreads" : "free-running", aw, (double)h[0] / reps, (double)h[0] / reps / aw);
+				}
+	return 0;
+}
