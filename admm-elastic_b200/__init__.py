@@ -391,6 +391,19 @@ class Solver(object):
         _host.admmhost_get_row_offsets(self.h, _ip(out))
         return out
 
+    def tet_rest_data(self):
+        """(idx [n,4], Dm^-1 [n,9], weight [n], g_index [n]) of the tet terms as handed to the device."""
+        n = _host.admmhost_get_tet_rest(self.h, None, None, None, None)
+        idx, dminv, w, row = np.zeros((n, 4), np.int32), np.zeros((n, 9)), np.zeros(n), np.zeros(n, np.int32)
+        _host.admmhost_get_tet_rest(self.h, _ip(idx), _dp(dminv), _dp(w), _ip(row))
+        return idx, dminv, w, row
+
+    def tri_rest_data(self):
+        n = _host.admmhost_get_tri_rest(self.h, None, None, None, None)
+        idx, rest, w, row = np.zeros((n, 3), np.int32), np.zeros((n, 4)), np.zeros(n), np.zeros(n, np.int32)
+        _host.admmhost_get_tri_rest(self.h, _ip(idx), _dp(rest), _dp(w), _ip(row))
+        return idx, rest, w, row
+
     def system_matrix(self):
         shape = (ctypes.c_longlong * 2)()
         _host.admmhost_system_shape(self.h, shape)

@@ -159,6 +159,28 @@ void admmhost_get_colors(void *h_, int *offsets, int *nodes) {
 }
 // g_index of every energy term, in energyterms order (after initialize)
 void admmhost_get_row_offsets(void *h_, int *out) { auto &et = ((Host *)h_)->solver.energyterms; for (size_t i = 0; i < et.size(); ++i) out[i] = et[i]->global_index(); }
+// Rest data of the tet / triangle terms exactly as handed to the device, in energyterms order (parity tests compare them
+// with what the reference-side binding harvests from the reference's get_reduction triplets)
+int admmhost_get_tet_rest(void *h_, int *idx4, double *dminv9, double *w, int *row) {
+	int e = 0;
+	for (auto &t : ((Host *)h_)->solver.energyterms) {
+		if (t->kind() != EnergyTerm::TET) continue;
+		TetEnergyTerm *tt = static_cast<TetEnergyTerm *>(t.get());
+		if (idx4) { for (int c = 0; c < 4; ++c) idx4[4 * e + c] = tt->indices()[c]; for (int k = 0; k < 9; ++k) dminv9[9 * e + k] = tt->rest_inverse()[k]; w[e] = tt->get_weight(); row[e] = tt->global_index(); }
+		++e;
+	}
+	return e;
+}
+int admmhost_get_tri_rest(void *h_, int *idx3, double *rest4, double *w, int *row) {
+	int e = 0;
+	for (auto &t : ((Host *)h_)->solver.energyterms) {
+		if (t->kind() != EnergyTerm::TRI) continue;
+		TriEnergyTerm *tt = static_cast<TriEnergyTerm *>(t.get());
+		if (idx3) { for (int c = 0; c < 3; ++c) idx3[3 * e + c] = tt->indices()[c]; for (int k = 0; k < 4; ++k) rest4[4 * e + k] = tt->rest_inverse()[k]; w[e] = tt->get_weight(); row[e] = tt->global_index(); }
+		++e;
+	}
+	return e;
+}
 void *admmhost_device_handle(void *h_) { return ((Host *)h_)->solver.device_handle(); }
 
 // Host-only helpers exposed for CPU tests (no device needed)

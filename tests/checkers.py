@@ -13,6 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_PATH = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libadmm_ref.so")
+BINDING_PATH = os.path.join(ROOT, "oracle", "_ref", "libadmm_gpubinding.so")
 
 _dpt = ctypes.POINTER(ctypes.c_double)
 _ipt = ctypes.POINTER(ctypes.c_int)
@@ -75,6 +76,152 @@ def ref_lib():
 
 class CheckerError(RuntimeError):
     pass
+
+
+_binding = None
+
+
+def have_binding():
+    return os.path.exists(BINDING_PATH)
+
+
+def binding_lib():
+    """oracle/_ref/libadmm_gpubinding.so: the reference-side binding (integration/GpuSolver.hpp, admm::GpuSolver :
+    admm::Solver) compiled against the reference's own headers (oracle/gpu_binding.cpp)."""
+    global _binding
+    if _binding is None:
+        L = ctypes.CDLL(BINDING_PATH)
+        L.gpub_create.restype = ctypes.c_void_p
+        L.gpub_last_error.restype = ctypes.c_char_p
+        L.gpub_last_error.argtypes = [ctypes.c_void_p]
+        L.gpub_solver_info.restype = ctypes.c_char_p
+        L.gpub_solver_info.argtypes = [ctypes.c_void_p]
+        _binding = L
+    return _binding
+
+
+class GpuBinding(object):
+    """admm::GpuSolver through oracle/gpu_binding.cpp: step() runs on the GPU, cpu_step() is the reference's own
+    Solver::step() on the same object (same D, W, A, colours, pins)."""
+
+    def __init__(self, precision=0, gs_parts=0, keep_z=False):
+        self.L = binding_lib()
+        self.h = ctypes.c_void_p(self.L.gpub_create())
+        self.L.gpub_set_options(self.h, int(precision), int(gs_parts), int(bool(keep_z)))
+
+    def close(self):
+        if self.h:
+            self.L.gpub_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc == 2:
+            return False
+        if rc:
+            raise CheckerError(self.L.gpub_last_error(self.h).decode())
+        return True
+
+    def add_nodes(self, x, m):
+        x, m = f64(x).ravel(), f64(m).ravel()
+        if m.size * 3 == x.size:
+            m = np.repeat(m, 3)
+        return self.L.gpub_add_nodes(self.h, dp(x), dp(m), x.size // 3)
+
+    def add_tets(self, verts, inds, model, mu, lam, kappa=0.0, vertex_offset=0, spline=None):
+        verts, inds = f64(verts).ravel(), i32(inds).ravel()
+        sp = spline if spline is not None else (mu, lam, kappa)
+        self._ck(self.L.gpub_add_tets(self.h, dp(verts), ip(inds), inds.size // 4, int(model), D(mu), D(lam), D(sp[0]), D(sp[1]), D(sp[2]), int(vertex_offset)))
+
+    def add_tris(self, verts, inds, mu, lam, limit_min=-100.0, limit_max=100.0, vertex_offset=0):
+        verts, inds = f64(verts).ravel(), i32(inds).ravel()
+        self._ck(self.L.gpub_add_tris(self.h, dp(verts), ip(inds), inds.size // 3, D(mu), D(lam), D(limit_min), D(limit_max), int(vertex_offset)))
+
+    def set_pins(self, inds, points=None):
+        inds = i32(inds).ravel()
+        pts = f64(points).ravel() if points is not None else None
+        self._ck(self.L.gpub_set_pins(self.h, ip(inds), dp(pts), inds.size))
+
+    def add_floor(self, y):
+        self._ck(self.L.gpub_add_floor(self.h, D(y)))
+
+    def add_sphere(self, c, r):
+        cc = f64(c)
+        self._ck(self.L.gpub_add_sphere(self.h, dp(cc), D(r)))
+
+    def initialize(self, dt=1.0 / 24.0, admm_iters=10, gravity=-9.8, linsolver=0):
+        return self._ck(self.L.gpub_initialize(self.h, D(dt), int(admm_iters), D(gravity), int(linsolver)))
+
+    def step(self):
+        self._ck(self.L.gpub_step(self.h))
+
+    def cpu_step(self):
+        self._ck(self.L.gpub_cpu_step(self.h))
+
+    @property
+    def dof(self):
+        return self.L.gpub_dof(self.h)
+
+    def get_x(self):
+        out = np.empty(self.dof)
+        self.L.gpub_get_x(self.h, dp(out))
+        return out
+
+    def get_v(self):
+        out = np.empty(self.dof)
+        self.L.gpub_get_v(self.h, dp(out))
+        return out
+
+    def set_x(self, x):
+        x = f64(x).ravel()
+        self.L.gpub_set_x(self.h, dp(x))
+
+    def set_v(self, v):
+        v = f64(v).ravel()
+        self.L.gpub_set_v(self.h, dp(v))
+
+    def runtime_data(self):
+        out = np.zeros(4)
+        self.L.gpub_runtime(self.h, dp(out))
+        return {"global_ms": out[0], "local_ms": out[1], "collision_ms": out[2], "inner_iters": int(out[3])}
+
+    def info(self):
+        return self.L.gpub_solver_info(self.h).decode()
+
+    def tets(self):
+        n = self.L.gpub_n_tets(self.h)
+        idx, dminv, w, row, model = np.zeros((n, 4), np.int32), np.zeros((n, 9)), np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.L.gpub_get_tets(self.h, ip(idx), dp(dminv), dp(w), ip(row), ip(model))
+        return idx, dminv, w, row, model
+
+    def tris(self):
+        n = self.L.gpub_n_tris(self.h)
+        idx, rest, w, row = np.zeros((n, 3), np.int32), np.zeros((n, 4)), np.zeros(n), np.zeros(n, np.int32)
+        self.L.gpub_get_tris(self.h, ip(idx), dp(rest), dp(w), ip(row))
+        return idx, rest, w, row
+
+    def pins(self):
+        n = self.L.gpub_n_pins(self.h)
+        idx, row, w = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n)
+        self.L.gpub_get_pins(self.h, ip(idx), ip(row), dp(w))
+        return idx, row, w
+
+    def colors(self):
+        nc = self.L.gpub_n_colors(self.h)
+        off, nodes = np.zeros(nc + 1, np.int32), np.zeros(self.dof // 3, np.int32)
+        self.L.gpub_get_colors(self.h, ip(off), ip(nodes))
+        return [nodes[off[i]:off[i + 1]].copy() for i in range(nc)]
+
+    def debug_get(self, name, n):
+        out = np.zeros(int(n))
+        if self.L.gpub_debug_get(self.h, name.encode(), dp(out), ctypes.c_longlong(out.size)):
+            raise CheckerError(self.L.gpub_last_error(self.h).decode())
+        return out
 
 
 class CpuSolver(object):
