@@ -1740,6 +1740,22 @@ int admm_b200_plan_check(int n, const int *rowptr, const int *cols, const double
 	}
 }
 
+// Host-only: modelled shared-memory cycles of the float4 gathers of one sweep (quarter-warp phases x bank-group
+// multiplicity, partition.hpp: rowstep_cycles) with the entries in matrix order and after the conflict-aware scheduling,
+// plus the conflict-free minimum (4 per row-step).  out[3] = {before, after, minimum}.
+int admm_b200_plan_bank_stats(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int n_parts, long long *out)
+{
+	try {
+		ResidentPlan R = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts, 1);
+		out[0] = R.cycles_before; out[1] = R.cycles_after; out[2] = 4 * (long long)(R.entries / 32);
+		return 0;
+	} catch (std::exception &e) {
+		g_create_error = e.what();
+		return 1;
+	}
+}
+
 const char *admm_b200_solver_info(const admm_b200_solver *s) { return s ? s->gs_info.c_str() : ""; }
 
 } // extern "C"

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <stdexcept>
 #include <vector>
@@ -58,6 +59,8 @@ struct ResidentPlan {
 	std::vector<unsigned int> dest_slot;
 	size_t total_slots = 0;
 	size_t max_nbr = 0;
+	bool schedule_banks = true;   // T = 1: order the entries of each row for conflict-free float4 gathers (detail::schedule_slice)
+	long long cycles_before = 0, cycles_after = 0; // modelled shared-memory cycles of all gathers of one sweep, before / after that ordering
 	size_t max_rows = 0, max_own = 0, max_halo = 0, max_slices = 0, entries = 0, nnz = 0;
 	// dynamic shared memory one CTA needs with `val_bytes`-wide matrix values
 	// dynamic shared memory one CTA needs.  mode 0: positions of the owned nodes as 3 doubles, matrix
@@ -88,6 +91,124 @@ struct ResidentPlan {
 };
 
 namespace detail {
+// ---------------------------------------------------------------------------------------------
+// Bank-conflict-aware ordering of the entries of a slice (one lane per node, T = 1).
+//
+// The sweep gathers `float4 d[col]` from shared memory: one LDS.128 per ELL row-step.  A 128-bit warp load is served in
+// four quarter-warp phases (8 lanes x 16 B = the 128-byte bank width); a phase takes as many cycles as the most loaded
+// 16-byte bank group (col mod 8) has DISTINCT words.  With the entries of a row in matrix order the 8 columns of a phase
+// are effectively random: ~2.8 cycles per phase, 11-13 per row-step (tools/micro/gather_bench.cu: 285 cycles per
+// 18-row slice at saturation where 4 per row-step would give ~110).  The order of the entries inside a row is free (a
+// row sum), and padding entries (zero coefficient) may point at any node, so each quarter-warp's entries are scheduled
+// here like an edge colouring of the bipartite multigraph lanes x bank groups: per row-step a matching that gives every
+// lane an entry of a bank group nobody else in its quarter uses in that step.  Lanes with the least slack (remaining
+// entries == remaining steps) are served first, augmenting paths move earlier choices out of the way, bank groups with
+// many remaining entries are preferred.  What cannot be matched stays a conflict (counted by slice_conflict_cycles).
+// ---------------------------------------------------------------------------------------------
+struct SliceEntry { uint16_t col; double val; };
+
+// cycles of the four phases of one row-step: per quarter the largest number of distinct words in one bank group
+inline int rowstep_cycles(const uint16_t *c32)
+{
+	int total = 0;
+	for (int q = 0; q < 4; ++q) {
+		int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		for (int a = 0; a < 8; ++a) {
+			bool dup = false;
+			for (int b = 0; b < a; ++b) if (c32[8 * q + b] == c32[8 * q + a]) dup = true;
+			if (!dup) ++cnt[c32[8 * q + a] & 7];
+		}
+		int m = 1;
+		for (int g = 0; g < 8; ++g) m = std::max(m, cnt[g]);
+		total += m;
+	}
+	return total;
+}
+
+// rows[lane] = the real entries of that lane's row (any order); width = row-steps of the slice; self[lane] = an owned
+// local index a padding entry may fall back to; n_loc = local nodes (padding may point at any of them).
+// Writes col/val [width][32].
+inline void schedule_slice(std::vector<SliceEntry> rows[32], int width, const int *self, int n_loc, uint16_t *col, double *val)
+{
+	for (int q = 0; q < 4; ++q) {
+		std::vector<SliceEntry> *R = rows + 8 * q;
+		int used[8]; // entries of lane a already placed
+		std::vector<char> taken[8];
+		for (int a = 0; a < 8; ++a) { used[a] = 0; taken[a].assign(R[a].size(), 0); }
+		for (int j = 0; j < width; ++j) {
+			const int rs = width - j;
+			int gdeg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // remaining entries per bank group (over the quarter)
+			for (int a = 0; a < 8; ++a) for (size_t e = 0; e < R[a].size(); ++e) if (!taken[a][e]) ++gdeg[R[a][e].col & 7];
+			int lane_of_group[8], pick[8]; // matching: group -> lane, lane -> entry index (-1: none yet)
+			for (int g = 0; g < 8; ++g) lane_of_group[g] = -1;
+			for (int a = 0; a < 8; ++a) pick[a] = -1;
+			int order[8];
+			for (int a = 0; a < 8; ++a) order[a] = a;
+			std::sort(order, order + 8, [&](int a, int b) {
+				const int sa = rs - ((int)R[a].size() - used[a]), sb = rs - ((int)R[b].size() - used[b]);
+				return sa != sb ? sa < sb : a < b; // least slack first
+			});
+			// augmenting-path search: lane a looks for a free group among its remaining entries
+			std::function<bool(int, char *)> augment = [&](int a, char *seen) -> bool {
+				// candidate groups of lane a, most loaded first
+				int cand[8], nc = 0;
+				for (size_t e = 0; e < R[a].size(); ++e) if (!taken[a][e]) {
+					const int g = R[a][e].col & 7;
+					bool have = false;
+					for (int i = 0; i < nc; ++i) if (cand[i] == g) have = true;
+					if (!have) cand[nc++] = g;
+				}
+				std::sort(cand, cand + nc, [&](int x, int y) { return gdeg[x] != gdeg[y] ? gdeg[x] > gdeg[y] : x < y; });
+				for (int i = 0; i < nc; ++i) {
+					const int g = cand[i];
+					if (seen[g]) continue;
+					seen[g] = 1;
+					if (lane_of_group[g] < 0 || augment(lane_of_group[g], seen)) {
+						lane_of_group[g] = a;
+						for (size_t e = 0; e < R[a].size(); ++e) if (!taken[a][e] && (R[a][e].col & 7) == g) { pick[a] = (int)e; break; }
+						return true;
+					}
+				}
+				return false;
+			};
+			for (int oi = 0; oi < 8; ++oi) {
+				const int a = order[oi];
+				if ((int)R[a].size() - used[a] <= 0) continue;
+				char seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+				augment(a, seen);
+			}
+			// lanes without a match: pad if they can, otherwise place a conflicting entry (least loaded group this step)
+			int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+			for (int a = 0; a < 8; ++a) if (pick[a] >= 0) ++load[R[a][pick[a]].col & 7];
+			for (int oi = 0; oi < 8; ++oi) {
+				const int a = order[oi];
+				const int left = (int)R[a].size() - used[a];
+				if (pick[a] >= 0 || left <= 0 || left < rs) continue; // matched, or nothing left, or may pad
+				int best = -1;
+				for (size_t e = 0; e < R[a].size(); ++e) if (!taken[a][e]) { if (best < 0 || load[R[a][e].col & 7] < load[R[a][best].col & 7]) best = (int)e; }
+				pick[a] = best;
+				++load[R[a][best].col & 7];
+			}
+			for (int a = 0; a < 8; ++a) {
+				const size_t at = (size_t)j * 32 + 8 * q + a;
+				if (pick[a] >= 0) {
+					col[at] = R[a][pick[a]].col; val[at] = R[a][pick[a]].val;
+					taken[a][pick[a]] = 1; ++used[a];
+				} else {
+					// padding: zero coefficient, any word of a bank group nobody uses in this step
+					int g = self[8 * q + a] & 7;
+					if (load[g] > 0) for (int t = 0; t < 8; ++t) if (load[t] == 0) { g = t; break; }
+					int c = (self[8 * q + a] & ~7) | g;
+					if (c >= n_loc) c = g < n_loc ? g : self[8 * q + a];
+					col[at] = (uint16_t)c; val[at] = 0.0;
+					++load[g];
+				}
+			}
+		}
+		for (int a = 0; a < 8; ++a) if (used[a] != (int)R[a].size()) throw std::runtime_error("resident plan: slice scheduling lost an entry");
+	}
+}
+
 inline void rcb(std::vector<int> &ids, int lo, int hi, int k, int part0, const double *pos, const std::vector<double> &w, std::vector<int> &part_of)
 {
 	if (k <= 1 || hi - lo <= 0) { for (int i = lo; i < hi; ++i) part_of[ids[i]] = part0; return; }
@@ -244,6 +365,21 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 						}
 					}
 					for (; j < width * T; ++j) R.col[base + (size_t)(j / T) * 32 + g * T + (j % T)] = (uint16_t)self;
+				}
+				if (T == 1 && R.schedule_banks && width > 0) {
+					// re-order the entries of every lane's row so that the quarter-warp phases of the float4 gather hit distinct
+					// shared-memory bank groups (detail::schedule_slice)
+					std::vector<detail::SliceEntry> lane_rows[32];
+					int self[32];
+					for (int g = 0; g < 32; ++g) {
+						const int node = (k + g < k1) ? nodes[k + g] : -1;
+						self[g] = node < 0 ? (k < k1 ? k : 0) : k + g;
+						if (node < 0) continue;
+						for (int j = 0; j < rowlen[node]; ++j) lane_rows[g].push_back({R.col[base + (size_t)j * 32 + g], R.val[base + (size_t)j * 32 + g]});
+					}
+					R.cycles_before += [&]() { long long c = 0; for (int j = 0; j < width; ++j) c += detail::rowstep_cycles(&R.col[base + (size_t)j * 32]); return c; }();
+					detail::schedule_slice(lane_rows, width, self, d.n_own + (int)halo.size(), &R.col[base], &R.val[base]);
+					R.cycles_after += [&]() { long long c = 0; for (int j = 0; j < width; ++j) c += detail::rowstep_cycles(&R.col[base + (size_t)j * 32]); return c; }();
 				}
 				rows += width;
 				++slices;

@@ -233,6 +233,12 @@ int admm_b200_dataflow_check( int n, const int *rowptr, const int *cols, const d
 int admm_b200_plan_check( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
 	const double *pos3, int n_parts, int val_bytes, int lanes, const double *x, double *max_err, long long *stats, int *part_of );
 
+/* Host-only: modelled shared-memory cycles of the resident sweep's float4 gathers (one sweep, all parts) with the row
+ * entries in matrix order, after the bank-conflict-aware ordering of csrc/partition.hpp (detail::schedule_slice), and
+ * the conflict-free minimum.  out[3] = {before, after, minimum}. */
+int admm_b200_plan_bank_stats( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
+	const double *pos3, int n_parts, long long *out );
+
 /* One line describing which global-solve kernel finalize chose and why (diagnostics). */
 const char *admm_b200_solver_info( const admm_b200_solver *s );
 

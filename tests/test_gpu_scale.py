@@ -127,16 +127,35 @@ def test_100k_beam_production_kernel_vs_reference(pkg, cpu, model):
     assert err < GATE, err
 
 
-def test_100k_beam_reference_colouring(pkg, cpu):
-    """The reference's own randomised colour lists (12-14 colours): more slices per part than the 512-thread variant
-    holds, so the 768-thread variant or the table-walking kernel run -- whichever finalize picks is named and checked."""
+@pytest.mark.parametrize("gs_parts", [20, 24])
+def test_100k_beam_reference_colouring(pkg, cpu, gs_parts):
+    """The reference's own randomised colour lists (15-16 colours, the last ones nearly empty): many ragged slices per
+    part.  20 parts: more slices than the 512-thread variant holds; 24 parts: fits it.  Whichever kernel finalize picks
+    is named in the record; it must be a shared-memory-resident one."""
     need_ref()
     scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
-    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=2, whose_colors="ref", gs_parts=16)
-    record("scale_100k_refcolors", err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref)
+    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=2, whose_colors="ref", gs_parts=gs_parts)
+    record("scale_100k_refcolors", gs_parts=gs_parts, err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref)
     assert nc >= 8, nc
     assert info.startswith("resident"), info
     assert inner == 2 * 5 * 30
+    assert err < GATE, err
+
+
+@pytest.mark.parametrize("variant", ["768", "0", "stream"])
+def test_100k_beam_other_solve_kernels(pkg, cpu, variant, monkeypatch):
+    """The 768-thread static-ownership variant, the table-walking resident kernel and the streaming kernel on the same
+    production-density parts (forced through the development knobs ADMM_B200_GS_OWNED / ADMM_B200_GS_KERNEL)."""
+    need_ref()
+    if variant == "stream":
+        monkeypatch.setenv("ADMM_B200_GS_KERNEL", "stream")
+    else:
+        monkeypatch.setenv("ADMM_B200_GS_OWNED", variant)
+    scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
+    err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=2, whose_colors="gpu", gs_parts=16)
+    record("scale_100k_variant_" + variant, err_over_bbox=err, n_colors=nc, info=info)
+    want = {"768": "static-ownership kernel, 768 threads", "0": "table-walking kernel", "stream": "stream"}[variant]
+    assert want in info, info
     assert err < GATE, err
 
 
