@@ -7,6 +7,7 @@
 #include "mcgs_resident.cuh"
 #include "mcgs_resident_f32.cuh"
 #include "mcgs_owned_f32.cuh"
+#include "mcgs_tiled_f32.cuh"
 #include "dataflow_plan.hpp"
 #include <algorithm>
 #include <cstdio>
@@ -141,7 +142,9 @@ struct admm_b200_solver {
 	// mcgs, shared-memory-resident variant (mcgs_resident.cuh)
 	bool gs_resident = false;
 	int gs_res_lanes = 1;
-	int gs_owned_threads = 0;  // > 0: mcgs_owned_f32_kernel with that many threads (the production fp32 solve)
+	int gs_owned_threads = 0;  // > 0: mcgs_owned_f32_kernel with that many threads (round 1's fp32 solve; obstacles, unequal masses)
+	bool gs_tiled = false;     // mcgs_tiled_f32_kernel (the production fp32 solve): short tasks of 8 nodes x 4 lanes
+	DevBuf<float> res_val_scaled; DevBuf<uint4> res_dest4;
 	size_t gs_res_smem = 0;
 	DevBuf<PartDesc> res_parts;
 	DevBuf<uint16_t> res_col;
@@ -431,7 +434,12 @@ void launch_mcgs_resident(S *s)
 		args[0] = &R32;
 	}
 	fine_begin(s, 2);
-	if (!fp64 && s->gs_owned_threads > 0) {
+	if (!fp64 && s->gs_tiled) {
+		McgsTiledExtra X; X.val_scaled = s->res_val_scaled.p; X.dest4 = s->res_dest4.p;
+		void *targs[2] = {&R32, &X};
+		const void *kern = s->res_prof.p ? (const void *)mcgs_tiled_f32_kernel<4, true> : (const void *)mcgs_tiled_f32_kernel<4, false>;
+		CK(cudaLaunchCooperativeKernel(kern, dim3(s->gs_parts), dim3(ADMMB200_TILED_THREADS), targs, s->gs_res_smem, s->stream));
+	} else if (!fp64 && s->gs_owned_threads > 0) {
 		const void *kern = owned_kernel_ptr(s->gs_owned_threads, !s->obstacles.empty(), s->res_prof.p != nullptr);
 		CK(cudaLaunchCooperativeKernel(kern, dim3(s->gs_parts), dim3(s->gs_owned_threads), args, s->gs_res_smem, s->stream));
 	} else
@@ -701,22 +709,36 @@ void build_mcgs_resident(S *s)
 	const int val_bytes = s->precision == ADMM_B200_FP64 ? 8 : 4;
 	int max_optin = 0;
 	CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-	const int lanes = plan_default_lanes();
-	s->gs_res_lanes = lanes;
 	const bool prof = getenv("ADMM_B200_GS_PROF") != nullptr;
-	const void *kern = resident_kernel_ptr(val_bytes == 8, lanes, prof);
-	cudaFuncAttributes fa;
-	CK(cudaFuncGetAttributes(&fa, kern));
-	const size_t budget = (size_t)max_optin - fa.sharedSizeBytes;
+	s->gs_tiled = false;
+	// The production fp32 solve (mcgs_tiled_f32.cuh) needs one diagonal value per node (equal x/y/z masses) and has no
+	// obstacle handling; ADMM_B200_GS_TILED=0 keeps round 1's kernels.
+	bool want_tiled = val_bytes == 4 && s->obstacles.empty();
+	if (const char *et = getenv("ADMM_B200_GS_TILED")) want_tiled = want_tiled && atoi(et) != 0;
+	if (getenv("ADMM_B200_GS_OWNED") || getenv("ADMM_B200_GS_RES_LANES")) want_tiled = false; // a round-1 variant was asked for by name
+	for (int i = 0; i < s->n_nodes && want_tiled; ++i) want_tiled = s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 1] && s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 2];
 	ResidentPlan R;
-	try {
-		R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->gs_parts * s->world, lanes);
-	} catch (std::exception &e) {
-		if (want == "resident" || s->world > 1) throw;
-		s->gs_info = std::string("stream (") + e.what() + ")";
-		return;
+	int lanes = 1;
+	size_t need = 0, budget = 0;
+	const void *kern = nullptr;
+	for (int attempt = want_tiled ? 0 : 1; attempt < 2; ++attempt) {
+		const bool tiled = attempt == 0;
+		lanes = tiled ? 4 : plan_default_lanes();
+		kern = tiled ? (prof ? (const void *)mcgs_tiled_f32_kernel<4, true> : (const void *)mcgs_tiled_f32_kernel<4, false>) : resident_kernel_ptr(val_bytes == 8, lanes, prof);
+		cudaFuncAttributes fa;
+		CK(cudaFuncGetAttributes(&fa, kern));
+		budget = (size_t)max_optin - fa.sharedSizeBytes;
+		try {
+			R = plan_resident(s->n_nodes, s->L_rowptr.data(), s->L_cols.data(), s->L_vals.data(), s->n_colors, s->color_off.data(), s->color_nodes.data(), s->h_x0.data(), s->gs_parts * s->world, lanes);
+		} catch (std::exception &e) {
+			if (want == "resident" || s->world > 1) throw;
+			s->gs_info = std::string("stream (") + e.what() + ")";
+			return;
+		}
+		need = R.smem_bytes(s->n_colors, val_bytes, val_bytes == 8 ? 0 : (tiled ? 2 : 1));
+		if (tiled && need <= budget && R.max_own <= 65535) { s->gs_tiled = true; break; }
 	}
-	const size_t need = R.smem_bytes(s->n_colors, val_bytes, val_bytes == 8 ? 0 : 1);
+	s->gs_res_lanes = lanes;
 	char buf[256];
 	snprintf(buf, sizeof(buf), "%d lane(s)/node, %zu B shared memory per part needed (max own %zu, halo %zu, rows %zu, neighbours %zu; ELL fill %.3f), budget %zu B", lanes, need, R.max_own, R.max_halo, R.max_rows,
 		R.max_nbr, R.entries ? (double)R.nnz / (double)R.entries : 1.0, budget);
@@ -765,9 +787,36 @@ void build_mcgs_resident(S *s)
 		CK(cudaStreamSynchronize(s->stream));
 	}
 	CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+	if (s->gs_tiled) {
+		// a'_ij = omega a_ij / a_ii: the row's node is the one the entry's lane belongs to (T lanes per node, G nodes per slice)
+		const int T = lanes, G = 32 / T;
+		std::vector<float> vs(std::max<size_t>(R.val.size(), 1), 0.f);
+		std::vector<uint4> d4((size_t)s->n_nodes, make_uint4(0u, 0u, 0u, 0u));
+		for (const PartDesc &d : R.parts) {
+			const int *gid = R.gid.data() + d.gid_off;
+			for (int sl = 0; sl < d.n_slices; ++sl)
+				for (int g = 0; g < G; ++g) {
+					const int l = R.slice_node[d.snode_off + sl * G + g];
+					if (l < 0) continue;
+					const int node = gid[l];
+					double aii = s->h_m[3 * (size_t)node];
+					for (int q = s->L_rowptr[node]; q < s->L_rowptr[node + 1]; ++q) if (s->L_cols[q] == node) aii += s->L_vals[q];
+					const double sc = s->gs_omega / aii;
+					for (int r = R.slice_row[d.slice_off + sl]; r < R.slice_row[d.slice_off + sl + 1]; ++r)
+						for (int t = 0; t < T; ++t) { const size_t e = (size_t)d.ent_off + (size_t)r * 32 + g * T + t; vs[e] = (float)(sc * R.val[e]); }
+				}
+			for (int l = 0; l < d.n_own; ++l) {
+				const int e0 = R.dest_off[d.own_off + l], cnt = std::min(R.dest_off[d.own_off + l + 1] - e0, 63);
+				d4[(size_t)d.own_off + l] = make_uint4(cnt > 0 ? R.dest_slot[e0] : 0u, cnt > 1 ? R.dest_slot[e0 + 1] : 0u, (unsigned int)e0, (unsigned int)cnt);
+			}
+		}
+		s->res_val_scaled.upload(vs, s->stream);
+		s->res_dest4.upload(d4, s->stream);
+		CK(cudaStreamSynchronize(s->stream));
+	}
 	// static-ownership kernel (mcgs_owned_f32.cuh): fp32 sweeps, one lane per node, every part's slices fit the warps' registers
 	s->gs_owned_threads = 0;
-	if (val_bytes == 4 && lanes == 1 && s->n_colors <= ADMMB200_OWNED_MAX_COLORS) {
+	if (!s->gs_tiled && val_bytes == 4 && lanes == 1 && s->n_colors <= ADMMB200_OWNED_MAX_COLORS) {
 		const char *eo = getenv("ADMM_B200_GS_OWNED"); // 0: keep the table-walking kernel; 512 / 768: force that variant
 		const int want_threads = eo ? atoi(eo) : -1;
 		int pick = 0;
@@ -787,7 +836,8 @@ void build_mcgs_resident(S *s)
 	CK(cudaStreamSynchronize(s->stream));
 	s->gs_res_smem = need;
 	s->gs_resident = true;
-	s->gs_info = std::string("resident: ") + buf + (s->gs_owned_threads ? "; static-ownership kernel, " + std::to_string(s->gs_owned_threads) + " threads" : std::string("; table-walking kernel"));
+	s->gs_info = std::string("resident: ") + buf + (s->gs_tiled ? std::string("; tiled kernel (8 nodes x 4 lanes per task), 512 threads") :
+		s->gs_owned_threads ? "; static-ownership kernel, " + std::to_string(s->gs_owned_threads) + " threads" : std::string("; table-walking kernel"));
 }
 
 void build_mcgs(S *s)
@@ -1742,13 +1792,17 @@ int admm_b200_plan_check(int n, const int *rowptr, const int *cols, const double
 
 // Host-only: modelled shared-memory cycles of the float4 gathers of one sweep (quarter-warp phases x bank-group
 // multiplicity, partition.hpp: rowstep_cycles) with the entries in matrix order and after the conflict-aware scheduling,
-// plus the conflict-free minimum (4 per row-step).  out[3] = {before, after, minimum}.
+// plus the conflict-free minimum (4 per row-step).  out[8] = {before, after, minimum, tiled plan: shared bytes, max slices, ELL fill x 1000, owned plan: shared bytes, tiled plan: max rows}.
 int admm_b200_plan_bank_stats(int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
 	const double *pos3, int n_parts, long long *out)
 {
 	try {
 		ResidentPlan R = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts, 1);
 		out[0] = R.cycles_before; out[1] = R.cycles_after; out[2] = 4 * (long long)(R.entries / 32);
+		// the tiled kernel's plan (4 lanes per node): shared memory per part, slices, ELL fill in 1/1000
+		ResidentPlan R4 = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts, 4);
+		out[3] = (long long)R4.smem_bytes(n_colors, 4, 2); out[4] = (long long)R4.max_slices; out[5] = R4.entries ? (long long)(1000.0 * (double)R4.nnz / (double)R4.entries) : 0;
+		out[6] = (long long)R.smem_bytes(n_colors, 4, 1); out[7] = (long long)R4.max_rows;
 		return 0;
 	} catch (std::exception &e) {
 		g_create_error = e.what();

@@ -65,7 +65,7 @@ struct ResidentPlan {
 	// dynamic shared memory one CTA needs with `val_bytes`-wide matrix values
 	// dynamic shared memory one CTA needs.  mode 0: positions of the owned nodes as 3 doubles, matrix
 	// values `val_bytes` wide (mcgs_resident_kernel); mode 1: float4 increments of owned AND halo nodes,
-	// float values (mcgs_resident_f32_kernel).
+	// float values (mcgs_resident_f32_kernel, mcgs_owned_f32_kernel); mode 2: the same for mcgs_tiled_f32_kernel.
 	size_t smem_bytes(int n_colors, int val_bytes, int mode = 0) const {
 		size_t worst = 0;
 		for (const PartDesc &d : parts) worst = std::max(worst, layout(d, n_colors, val_bytes, lanes, mode, nullptr));
@@ -80,9 +80,16 @@ struct ResidentPlan {
 		else take(0, 16 * ((size_t)d.n_own + d.n_halo));                             // float4 increments, owned + halo
 		take(1, mode == 0 ? (size_t)val_bytes * 32 * (size_t)d.n_rows : res32_val_region((size_t)d.n_rows, (size_t)d.n_own + d.n_halo)); // val
 		take(2, sizeof(uint16_t) * 32 * (size_t)d.n_rows);                           // col
+		if (mode == 2) {
+			// mcgs_tiled_f32.cuh: no node ids and no per-lane slice tables in shared memory, but the scaled right-hand side
+			take(3, sizeof(float) * 3 * (size_t)d.n_own);                            // rbs = omega r0 / a_ii
+			take(4, sizeof(int) * ((size_t)d.n_slices + 1));                         // slice_row
+			take(5, sizeof(int) * (size_t)d.n_slices);                               // first node | valid nodes << 16
+		} else {
 		take(3, sizeof(int) * ((size_t)d.n_own + d.n_halo));                         // gid
 		take(4, sizeof(int) * ((size_t)d.n_slices + 1));                             // slice_row
 		take(5, sizeof(short) * (size_t)G * d.n_slices);                             // slice_node
+		}
 		take(6, sizeof(int) * (2 * (size_t)n_colors + 1));                           // color_slice
 		take(7, mode == 0 ? 0 : sizeof(int) * ((size_t)n_colors + 1));               // halo_color
 		if (off) std::memcpy(off, tmp, sizeof(tmp));
@@ -239,12 +246,14 @@ inline void rcb(std::vector<int> &ids, int lo, int hi, int k, int part0, const d
 // node -> part: recursive coordinate bisection balanced by padded row length (+ the node's own update)
 inline std::vector<int> plan_partition(int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, int n_parts, int lanes)
 {
-	const int T = lanes;
+	// The weights do not depend on the lane count of the sweep kernel: the host (multi-GPU element selection,
+	// admm_b200_plan_parts) and finalize must arrive at the SAME partition whichever kernel finalize picks.
+	(void)lanes;
 	std::vector<double> w(n);
 	for (int i = 0; i < n; ++i) {
 		int len = 0;
 		for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) if (cols[q] != i && vals[q] != 0.0) ++len;
-		w[i] = (double)((len + T - 1) / T * T) + 2.0;
+		w[i] = (double)((len + 3) / 4 * 4) + 2.0;
 	}
 	std::vector<int> part_of(n, 0), ids(n);
 	std::iota(ids.begin(), ids.end(), 0);

@@ -235,7 +235,8 @@ int admm_b200_plan_check( int n, const int *rowptr, const int *cols, const doubl
 
 /* Host-only: modelled shared-memory cycles of the resident sweep's float4 gathers (one sweep, all parts) with the row
  * entries in matrix order, after the bank-conflict-aware ordering of csrc/partition.hpp (detail::schedule_slice), and
- * the conflict-free minimum.  out[3] = {before, after, minimum}. */
+ * the conflict-free minimum.  out[8] = {before, after, minimum, shared bytes / max slices / ELL fill x 1000 of the tiled
+ * kernel's plan (4 lanes per node), shared bytes of the one-lane plan, max rows of the tiled plan}. */
 int admm_b200_plan_bank_stats( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
 	const double *pos3, int n_parts, long long *out );
 
