@@ -711,10 +711,12 @@ void build_mcgs_resident(S *s)
 	CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
 	const bool prof = getenv("ADMM_B200_GS_PROF") != nullptr;
 	s->gs_tiled = false;
-	// The production fp32 solve (mcgs_tiled_f32.cuh) needs one diagonal value per node (equal x/y/z masses) and has no
-	// obstacle handling; ADMM_B200_GS_TILED=0 keeps round 1's kernels.
-	bool want_tiled = val_bytes == 4 && s->obstacles.empty();
-	if (const char *et = getenv("ADMM_B200_GS_TILED")) want_tiled = want_tiled && atoi(et) != 0;
+	// The tiled fp32 solve (mcgs_tiled_f32.cuh: short tasks of 8 nodes x 4 lanes) is an ALTERNATIVE, selected with
+	// ADMM_B200_GS_TILED=1: measured on the 1M-tet beam it needs 0.59 ms per solve where the static-ownership kernel needs
+	// 0.36 (profiles/r02c_gsprof2.log: the shared-memory pipe, not the task latency, bounds a pass, and four lanes per node
+	// cost more bank conflicts per gathered float4 than one).  Needs equal x/y/z masses per node and no obstacles.
+	bool want_tiled = false;
+	if (const char *et = getenv("ADMM_B200_GS_TILED")) want_tiled = atoi(et) != 0 && val_bytes == 4 && s->obstacles.empty();
 	if (getenv("ADMM_B200_GS_OWNED") || getenv("ADMM_B200_GS_RES_LANES")) want_tiled = false; // a round-1 variant was asked for by name
 	for (int i = 0; i < s->n_nodes && want_tiled; ++i) want_tiled = s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 1] && s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 2];
 	ResidentPlan R;
@@ -1803,6 +1805,7 @@ int admm_b200_plan_bank_stats(int n, const int *rowptr, const int *cols, const d
 		ResidentPlan R4 = plan_resident(n, rowptr, cols, vals, n_colors, color_off, color_nodes, pos3, n_parts, 4);
 		out[3] = (long long)R4.smem_bytes(n_colors, 4, 2); out[4] = (long long)R4.max_slices; out[5] = R4.entries ? (long long)(1000.0 * (double)R4.nnz / (double)R4.entries) : 0;
 		out[6] = (long long)R.smem_bytes(n_colors, 4, 1); out[7] = (long long)R4.max_rows;
+		{ long long c = 0; for (size_t r = 0; r < R4.entries / 32; ++r) c += detail::rowstep_cycles(&R4.col[r * 32]); out[8] = c; out[9] = 4 * (long long)(R4.entries / 32); }
 		return 0;
 	} catch (std::exception &e) {
 		g_create_error = e.what();

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(ADMMB200_TILED_THREADS, 1) mcgs_tiled_f32_kern
 				}
 			}
 			s_d[l] = dn;
-			if (bnd) {
+			if (bnd && !(PROF && (R.dbg & 16))) {
 				const int cnt = (int)dst.w;
 				auto put = [&](unsigned int ent) {
 					const unsigned int q = ent >> 27;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(ADMMB200_TILED_THREADS, 1) mcgs_tiled_f32_kern
 			// interior tasks: nobody outside this part reads them, and they read no halo value that is still in flight
 			for (int sl = i0 + warp; sl < b0; sl += NW) lb += do_task(sl, false, last, it, pass_tag, pub_off);
 			if (PROF) c1 = clk_ordered();
-			if (pass > 0) {
+			if (pass > 0 && !(PROF && (R.dbg & 2))) {
 				// what the neighbours changed in the previous pass: the halo nodes of that pass's colour
 				const int cp = (color + C - 1) % C;
 				const int it_prev = color > 0 ? it : it - 1;

@@ -116,12 +116,12 @@ def run_pair(pkg, scene, x0, model, iters, steps, whose_colors, gs_parts, floor=
 
 @pytest.mark.parametrize("model", [1, 2])
 def test_100k_beam_production_kernel_vs_reference(pkg, cpu, model):
-    """mcgs_tiled_f32<4> + tet_local_kernel<float,...,8> + assemble_kernel<float>, parts of 1 458 nodes."""
+    """mcgs_owned_f32<512,4> + tet_local_kernel<float,...,8> + assemble_kernel<float>, parts of 1 458 nodes."""
     need_ref()
     scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
     err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, model, iters=5, steps=2, whose_colors="gpu", gs_parts=16)
     record("scale_100k_production", model=model, err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref)
-    assert "tiled kernel" in info, info
+    assert "static-ownership kernel, 512 threads" in info, info
     assert inner == 2 * 5 * 30
     assert moved > 10 * GATE       # the beam really moved: the comparison is not vacuous
     assert err < GATE, err
@@ -142,19 +142,21 @@ def test_100k_beam_reference_colouring(pkg, cpu, gs_parts):
     assert err < GATE, err
 
 
-@pytest.mark.parametrize("variant", ["512", "768", "0", "stream"])
+@pytest.mark.parametrize("variant", ["tiled", "768", "0", "stream"])
 def test_100k_beam_other_solve_kernels(pkg, cpu, variant, monkeypatch):
-    """Round 1's static-ownership kernels (512 / 768 threads), the table-walking resident kernel and the streaming kernel on the same
+    """The tiled kernel (8 nodes x 4 lanes per task), the 768-thread static-ownership variant, the table-walking resident kernel and the streaming kernel on the same
     production-density parts (forced through the development knobs ADMM_B200_GS_OWNED / ADMM_B200_GS_KERNEL)."""
     need_ref()
     if variant == "stream":
         monkeypatch.setenv("ADMM_B200_GS_KERNEL", "stream")
+    elif variant == "tiled":
+        monkeypatch.setenv("ADMM_B200_GS_TILED", "1")
     else:
         monkeypatch.setenv("ADMM_B200_GS_OWNED", variant)
     scene, x0 = bench_beam(pkg.meshes, 100, 20, 10)
     err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=2, whose_colors="gpu", gs_parts=16)
     record("scale_100k_variant_" + variant, err_over_bbox=err, n_colors=nc, info=info)
-    want = {"512": "static-ownership kernel, 512 threads", "768": "static-ownership kernel, 768 threads", "0": "table-walking kernel", "stream": "stream"}[variant]
+    want = {"tiled": "tiled kernel", "768": "static-ownership kernel, 768 threads", "0": "table-walking kernel", "stream": "stream"}[variant]
     assert want in info, info
     assert err < GATE, err
 
@@ -189,7 +191,7 @@ def test_1m_bench_scene_one_step_vs_reference(pkg, cpu):
     t0 = time.time()
     err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=1, whose_colors="gpu", gs_parts=0)
     record("scale_1m_bench_scene", err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref, total_seconds=time.time() - t0)
-    assert "tiled kernel" in info, info
+    assert "static-ownership kernel, 512 threads" in info, info
     assert inner == 5 * 30
     assert err < GATE, err
 
