@@ -3,6 +3,8 @@
 #include "../../include/admm_b200.h"
 #include "kernels.cuh"
 #include "sptrsv.cuh"
+#include "ldlt_blocks.hpp"
+#include "sptrsv_blocks.cuh"
 #include "uzawa.cuh"
 #include "mcgs_resident.cuh"
 #include "mcgs_resident_f32.cuh"
@@ -188,6 +190,13 @@ struct admm_b200_solver {
 	DevBuf<double> d_fwd_vals, d_bwd_vals, d_ld_D;
 	DevBuf<double4> d_ld_y;
 	int ld_levels_fwd = 0, ld_levels_bwd = 0, ld_grid = 0, ld_lanes = 4;
+	// block (supernodal) solve, sptrsv_blocks.cuh -- the default; the level-scheduled kernel above stays as ADMM_B200_LDLT_KERNEL=levels
+	bool ld_blocks = false;
+	int lb_levels_f = 0, lb_levels_b = 0;
+	DevBuf<int> lb_blk_of, lb_blk_c0, lb_f_lev_ptr, lb_f_rows, lb_f_rowptr, lb_f_cols, lb_f_lanes, lb_b_lev_ptr, lb_b_cols, lb_b_colptr, lb_b_rows, lb_b_lanes;
+	DevBuf<long long> lb_inv_off;
+	DevBuf<double> lb_inv, lb_invT, lb_f_vals, lb_b_vals;
+	DevBuf<double4> lb_t;
 
 	// settings
 	bool finalized = false;
@@ -494,6 +503,20 @@ void launch_ldlt(S *s, const double4 *rhs = nullptr, double4 *out = nullptr, con
 	P.bwd_level_ptr = s->d_bwd_level_ptr.p; P.bwd_rows = s->d_bwd_rows.p; P.bwd_rowptr = s->d_bwd_rowptr.p; P.bwd_cols = s->d_bwd_cols.p; P.bwd_vals = s->d_bwd_vals.p;
 	P.dinv_unused = nullptr; P.D = s->d_ld_D.p; P.y = s->d_ld_y.p; P.b = rhs ? rhs : s->b.p; P.x = out ? out : s->cx.p; P.barrier = s->barrier.p; P.active = active;
 	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
+	if (s->ld_blocks) {
+		LdltBlkParams B;
+		B.n = s->ld_n; B.n_levels_f = s->lb_levels_f; B.n_levels_b = s->lb_levels_b;
+		B.perm = s->d_ld_perm.p; B.blk_of = s->lb_blk_of.p; B.blk_c0 = s->lb_blk_c0.p; B.inv_off = s->lb_inv_off.p; B.inv = s->lb_inv.p; B.invT = s->lb_invT.p;
+		B.f_lev_ptr = s->lb_f_lev_ptr.p; B.f_rows = s->lb_f_rows.p; B.f_rowptr = s->lb_f_rowptr.p; B.f_cols = s->lb_f_cols.p; B.f_lanes = s->lb_f_lanes.p; B.f_vals = s->lb_f_vals.p;
+		B.b_lev_ptr = s->lb_b_lev_ptr.p; B.b_cols = s->lb_b_cols.p; B.b_colptr = s->lb_b_colptr.p; B.b_rows = s->lb_b_rows.p; B.b_lanes = s->lb_b_lanes.p; B.b_vals = s->lb_b_vals.p;
+		B.D = s->d_ld_D.p; B.t = s->lb_t.p; B.y = s->d_ld_y.p; B.b = P.b; B.x = P.x; B.barrier = s->barrier.p; B.active = active;
+		void *args[] = {&B};
+		fine_begin(s, 2);
+		CK(cudaLaunchCooperativeKernel((void *)ldlt_blocks_kernel, dim3(s->ld_grid), dim3(1024), args, 0, s->stream));
+		fine_end(s);
+		s->launches++;
+		return;
+	}
 	fine_begin(s, 2);
 	switch (s->ld_lanes) {
 	case 1: ldlt_launch_T<1>(s, P); break;
@@ -936,6 +959,36 @@ void build_ldlt(S *s)
 	for (int i = 0; i < n; ++i) require(s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 1] && s->h_m[3 * (size_t)i] == s->h_m[3 * (size_t)i + 2], "LDLT path needs equal x/y/z masses per node");
 	const std::vector<int> &Lp = s->ld_Lp, &Li = s->ld_Li;
 	const std::vector<double> &Lx = s->ld_Lx;
+	for (int j = 0; j < n; ++j) for (int q = Lp[j]; q < Lp[j + 1]; ++q) require(Li[q] > j && Li[q] < n && (q == Lp[j] || Li[q] > Li[q - 1]), "set_ldlt: L must be strictly lower, CSC, ascending rows");
+	{
+		const char *ek = getenv("ADMM_B200_LDLT_KERNEL");
+		s->ld_blocks = !(ek && std::string(ek) == "levels");
+	}
+	if (s->ld_blocks) {
+		LdltBlockPlan B = plan_ldlt_blocks(n, Lp.data(), Li.data(), Lx.data());
+		s->lb_levels_f = B.n_levels_f; s->lb_levels_b = B.n_levels_b;
+		s->d_ld_perm.upload(s->ld_perm, s->stream);
+		s->lb_blk_of.upload(B.blk_of, s->stream); s->lb_blk_c0.upload(B.blk_c0, s->stream); s->lb_inv_off.upload(B.inv_off, s->stream);
+		s->lb_inv.upload(B.inv, s->stream); s->lb_invT.upload(B.invT, s->stream);
+		auto nonempty_i = [](std::vector<int> &v) { if (v.empty()) v.push_back(0); };
+		auto nonempty_d = [](std::vector<double> &v) { if (v.empty()) v.push_back(0.0); };
+		nonempty_i(B.f_cols); nonempty_d(B.f_vals); nonempty_i(B.b_rows); nonempty_d(B.b_vals);
+		s->lb_f_lev_ptr.upload(B.f_lev_ptr, s->stream); s->lb_f_rows.upload(B.f_rows, s->stream); s->lb_f_rowptr.upload(B.f_rowptr, s->stream);
+		s->lb_f_cols.upload(B.f_cols, s->stream); s->lb_f_vals.upload(B.f_vals, s->stream); s->lb_f_lanes.upload(B.f_lanes, s->stream);
+		s->lb_b_lev_ptr.upload(B.b_lev_ptr, s->stream); s->lb_b_cols.upload(B.b_cols, s->stream); s->lb_b_colptr.upload(B.b_colptr, s->stream);
+		s->lb_b_rows.upload(B.b_rows, s->stream); s->lb_b_vals.upload(B.b_vals, s->stream); s->lb_b_lanes.upload(B.b_lanes, s->stream);
+		s->d_ld_D.upload(s->ld_D, s->stream);
+		s->d_ld_y.alloc(n); s->lb_t.alloc(n);
+		CK(cudaStreamSynchronize(s->stream));
+		int occ = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ldlt_blocks_kernel, 1024, 0));
+		require(occ >= 1, "ldlt block kernel does not fit on an SM");
+		s->ld_grid = s->n_sms;
+		char buf[320];
+		snprintf(buf, sizeof(buf), "ldlt blocks: n %d, nnz(L) %lld, %d blocks (largest %d), %lld entries outside + %lld in the inverted diagonal blocks, %d + %d levels, %d CTAs x 1024", n, (long long)Lp[n],
+			B.n_blocks, B.max_block, B.nnz_out, B.nnz_inv, B.n_levels_f, B.n_levels_b, s->ld_grid);
+		s->gs_info = buf;
+	} else {
 	// CSR of strictly lower L (row gather for the forward solve)
 	std::vector<int> rp(n + 1, 0);
 	for (int j = 0; j < n; ++j) for (int q = Lp[j]; q < Lp[j + 1]; ++q) { require(Li[q] > j && Li[q] < n, "set_ldlt: L must be strictly lower, CSC"); rp[Li[q] + 1]++; }
@@ -967,6 +1020,7 @@ void build_ldlt(S *s)
 	s->d_bwd_rowptr.upload(s->ld_Lp, s->stream); s->d_bwd_cols.upload(s->ld_Li, s->stream); s->d_bwd_vals.upload(s->ld_Lx, s->stream);
 	s->d_ld_D.upload(s->ld_D, s->stream);
 	s->d_ld_y.alloc(n);
+	} // level-scheduled structures
 	if (s->linsolver == ADMM_B200_UZAWA && !s->obstacles.empty()) {
 		// UzawaCG with passive collisions (uzawa.cuh): at most one constraint row per node
 		s->uz_hv.alloc(n); s->uz_hn.alloc(3 * (size_t)n); s->uz_hc.alloc(n); s->uz_y.alloc(n); s->uz_r.alloc(n); s->uz_d.alloc(n); s->uz_q3.alloc(n);
@@ -977,13 +1031,14 @@ void build_ldlt(S *s)
 		CK(cudaStreamSynchronize(s->stream));
 	}
 	CK(cudaStreamSynchronize(s->stream));
+	if (s->ld_blocks) return;
 	const char *env = getenv("ADMM_B200_LDLT_LANES");
 	int T = env ? atoi(env) : 4;
 	if (T != 1 && T != 2 && T != 4 && T != 8) T = 4;
 	s->ld_lanes = T;
 	s->ld_grid = s->n_sms;
 	char buf[256];
-	snprintf(buf, sizeof(buf), "ldlt: n %d, nnz(L) %lld, dependency levels %d forward + %d backward, %d lane(s)/row, %d CTAs", n, (long long)Lp[n], nlf, nlb, T, s->ld_grid);
+	snprintf(buf, sizeof(buf), "ldlt: n %d, nnz(L) %lld, dependency levels %d forward + %d backward, %d lane(s)/row, %d CTAs", n, (long long)Lp[n], s->ld_levels_fwd, s->ld_levels_bwd, T, s->ld_grid);
 	s->gs_info = buf;
 }
 
@@ -1806,6 +1861,22 @@ int admm_b200_plan_bank_stats(int n, const int *rowptr, const int *cols, const d
 		out[3] = (long long)R4.smem_bytes(n_colors, 4, 2); out[4] = (long long)R4.max_slices; out[5] = R4.entries ? (long long)(1000.0 * (double)R4.nnz / (double)R4.entries) : 0;
 		out[6] = (long long)R.smem_bytes(n_colors, 4, 1); out[7] = (long long)R4.max_rows;
 		{ long long c = 0; for (size_t r = 0; r < R4.entries / 32; ++r) c += detail::rowstep_cycles(&R4.col[r * 32]); out[8] = c; out[9] = 4 * (long long)(R4.entries / 32); }
+		return 0;
+	} catch (std::exception &e) {
+		g_create_error = e.what();
+		return 1;
+	}
+}
+
+// Host-only: plans the block solve for a factor (ldlt_blocks.hpp) and applies it on the host to one right-hand side
+// (n values), exactly as the device kernel walks it.  stats[6] = {blocks, largest block, forward levels, backward levels,
+// entries outside the diagonal blocks, entries of the inverted diagonal blocks}.
+int admm_b200_ldlt_blocks_check(int n, const int *perm, const int *Lp, const int *Li, const double *Lx, const double *D, const double *b, double *x, long long *stats)
+{
+	try {
+		LdltBlockPlan B = plan_ldlt_blocks(n, Lp, Li, Lx);
+		ldlt_blocks_solve_host(B, perm, D, b, x);
+		if (stats) { stats[0] = B.n_blocks; stats[1] = B.max_block; stats[2] = B.n_levels_f; stats[3] = B.n_levels_b; stats[4] = B.nnz_out; stats[5] = B.nnz_inv; }
 		return 0;
 	} catch (std::exception &e) {
 		g_create_error = e.what();

@@ -1,0 +1,155 @@
+// sptrsv_blocks.cuh -- prefactored L D L^T solve on the GPU by BLOCKS (supernodes), 3 right-hand sides at once.
+//
+// Replaces LDLTSolver::solve = Eigen SimplicialLDLT::solve (src/LinearSolver.hpp:87-90): x = P^T L^-T D^-1 L^-1 P b, and is
+// the inner solve of UzawaCG (src/UzawaCG.hpp:83-118).  Plan: ldlt_blocks.hpp -- the columns of L are cut into blocks whose
+// diagonal part is inverted on the host, so a level of the block tree costs
+//     gather:  t_i = b_i - sum_{j left of i's block} L_ij y_j        one item per row, lanes stride over the row (coalesced)
+//     dense:   y_i = t_i + sum_{k < i in the block} Linv_ik t_k      one item per row, the block's t is contiguous
+// with a grid barrier after each: ~2 x 15 barriers per direction instead of one per dependency level (2 415 on the cloth).
+// One persistent cooperative launch per solve; A = L_scalar (x) I3, so x, y, z go through together as double4.
+#pragma once
+#include "sptrsv.cuh"
+
+namespace admmb200 {
+
+struct LdltBlkParams {
+	int n, n_levels_f, n_levels_b;
+	const int *perm;                 // [n] perm[new] = old
+	const int *blk_of, *blk_c0;      // [n], [n_blocks + 1]
+	const long long *inv_off;        // [n_blocks]
+	const double *inv, *invT;        // packed strictly-lower inverse rows / transposed rows
+	const int *f_lev_ptr, *f_rows, *f_rowptr, *f_cols, *f_lanes;
+	const double *f_vals;
+	const int *b_lev_ptr, *b_cols, *b_colptr, *b_rows, *b_lanes;
+	const double *b_vals;
+	const double *D;
+	double4 *t, *y;                  // work, permuted numbering
+	const double4 *b;                // node order
+	double4 *x;                      // node order, out
+	unsigned int *barrier;
+	const int *active;               // NULL, or a device flag: 0 = skip this solve (uzawa.cuh: the CG loop has already ended)
+};
+
+__device__ __forceinline__ void blk_reduce(double &sx, double &sy, double &sz, int T)
+{
+	for (int o = T >> 1; o > 0; o >>= 1) {
+		sx += __shfl_xor_sync(0xffffffffu, sx, o);
+		sy += __shfl_xor_sync(0xffffffffu, sy, o);
+		sz += __shfl_xor_sync(0xffffffffu, sz, o);
+	}
+}
+
+__global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
+{
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+	unsigned int bar_target = 0;
+	if (P.active && *P.active == 0) return; // the same for every block: no barrier is left waiting
+
+	// ---------------- forward: y = L^-1 P b ----------------
+	for (int lv = 0; lv < P.n_levels_f; ++lv) {
+		const int k0 = P.f_lev_ptr[lv], k1 = P.f_lev_ptr[lv + 1];
+		{
+			const int T = P.f_lanes[2 * lv], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			for (int kb = k0; kb < k1; kb += n_groups) {
+				const int k = kb + group;
+				const bool act = k < k1;
+				const int i = act ? __ldg(&P.f_rows[k]) : 0;
+				double sx = 0, sy = 0, sz = 0;
+				if (act) {
+					const int q1 = __ldg(&P.f_rowptr[i + 1]);
+					for (int q = __ldg(&P.f_rowptr[i]) + sub; q < q1; q += T) {
+						const double a = __ldg(&P.f_vals[q]);
+						const double4 yj = ld_node_cg(&P.y[__ldg(&P.f_cols[q])]);
+						sx += a * yj.x; sy += a * yj.y; sz += a * yj.z;
+					}
+				}
+				blk_reduce(sx, sy, sz, T);
+				if (act && sub == 0) {
+					const double4 bi = P.b[__ldg(&P.perm[i])];
+					st_node(&P.t[i], bi.x - sx, bi.y - sy, bi.z - sz);
+				}
+			}
+		}
+		grid_barrier(P.barrier, bar_target, gridDim.x);
+		{
+			const int T = P.f_lanes[2 * lv + 1], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			for (int kb = k0; kb < k1; kb += n_groups) {
+				const int k = kb + group;
+				const bool act = k < k1;
+				const int i = act ? __ldg(&P.f_rows[k]) : 0;
+				double sx = 0, sy = 0, sz = 0;
+				if (act) {
+					const int bl = __ldg(&P.blk_of[i]), c0 = __ldg(&P.blk_c0[bl]), r = i - c0;
+					const double *inv = P.inv + __ldg(&P.inv_off[bl]) + (long long)r * (r - 1) / 2;
+					for (int c = sub; c < r; c += T) {
+						const double a = __ldg(&inv[c]);
+						const double4 tc = ld_node_cg(&P.t[c0 + c]);
+						sx += a * tc.x; sy += a * tc.y; sz += a * tc.z;
+					}
+				}
+				blk_reduce(sx, sy, sz, T);
+				if (act && sub == 0) {
+					const double4 ti = ld_node_cg(&P.t[i]);
+					st_node(&P.y[i], ti.x + sx, ti.y + sy, ti.z + sz);
+				}
+			}
+		}
+		grid_barrier(P.barrier, bar_target, gridDim.x);
+	}
+	// ---------------- backward: x = P^T L^-T D^-1 y ----------------
+	for (int lv = 0; lv < P.n_levels_b; ++lv) {
+		const int k0 = P.b_lev_ptr[lv], k1 = P.b_lev_ptr[lv + 1];
+		{
+			const int T = P.b_lanes[2 * lv], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			for (int kb = k0; kb < k1; kb += n_groups) {
+				const int k = kb + group;
+				const bool act = k < k1;
+				const int j = act ? __ldg(&P.b_cols[k]) : 0;
+				double sx = 0, sy = 0, sz = 0;
+				if (act) {
+					const int q1 = __ldg(&P.b_colptr[j + 1]);
+					for (int q = __ldg(&P.b_colptr[j]) + sub; q < q1; q += T) {
+						const double a = __ldg(&P.b_vals[q]);
+						const double4 xi = ld_node_cg(&P.y[__ldg(&P.b_rows[q])]); // rows below the block: already final
+						sx += a * xi.x; sy += a * xi.y; sz += a * xi.z;
+					}
+				}
+				blk_reduce(sx, sy, sz, T);
+				if (act && sub == 0) {
+					const double4 yj = ld_node_cg(&P.y[j]);
+					const double d = __ldg(&P.D[j]);
+					st_node(&P.t[j], yj.x / d - sx, yj.y / d - sy, yj.z / d - sz);
+				}
+			}
+		}
+		grid_barrier(P.barrier, bar_target, gridDim.x);
+		{
+			const int T = P.b_lanes[2 * lv + 1], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			for (int kb = k0; kb < k1; kb += n_groups) {
+				const int k = kb + group;
+				const bool act = k < k1;
+				const int j = act ? __ldg(&P.b_cols[k]) : 0;
+				double sx = 0, sy = 0, sz = 0;
+				if (act) {
+					const int bl = __ldg(&P.blk_of[j]), c0 = __ldg(&P.blk_c0[bl]), s = __ldg(&P.blk_c0[bl + 1]) - c0, r = j - c0;
+					const double *invT = P.invT + __ldg(&P.inv_off[bl]) + (long long)r * (s - 1) - (long long)r * (r - 1) / 2;
+					for (int c = r + 1 + sub; c < s; c += T) {
+						const double a = __ldg(&invT[c - r - 1]);
+						const double4 tc = ld_node_cg(&P.t[c0 + c]);
+						sx += a * tc.x; sy += a * tc.y; sz += a * tc.z;
+					}
+				}
+				blk_reduce(sx, sy, sz, T);
+				if (act && sub == 0) {
+					const double4 tj = ld_node_cg(&P.t[j]);
+					const double rx = tj.x + sx, ry = tj.y + sy, rz = tj.z + sz;
+					st_node(&P.y[j], rx, ry, rz);
+					st_node(&P.x[__ldg(&P.perm[j])], rx, ry, rz);
+				}
+			}
+		}
+		grid_barrier(P.barrier, bar_target, gridDim.x);
+	}
+}
+
+} // namespace admmb200

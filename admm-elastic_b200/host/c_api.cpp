@@ -215,4 +215,14 @@ int admmhost_ldlt_check(int n, const int *rowptr, const int *cols, const double 
 	} catch (std::exception &) { return 1; }
 }
 
+// The same factor walked by the device's block plan (csrc/ldlt_blocks.hpp) on the host; stats as admm_b200_ldlt_blocks_check
+int admmhost_ldlt_blocks_check(int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, const double *b, double *x, long long *stats) {
+	try {
+		sparse::Csr A; A.n = n; A.rowptr.assign(rowptr, rowptr + n + 1); A.cols.assign(cols, cols + rowptr[n]); A.vals.assign(vals, vals + rowptr[n]);
+		std::vector<int> perm = sparse::order_nested_dissection(A, pos3);
+		sparse::Ldlt f = sparse::factor_ldlt(A, perm);
+		return admm_b200_ldlt_blocks_check(n, f.perm.data(), f.Lp.data(), f.Li.data(), f.Lx.data(), f.D.data(), b, x, stats);
+	} catch (std::exception &) { return 1; }
+}
+
 } // extern "C"

@@ -240,6 +240,11 @@ int admm_b200_plan_check( int n, const int *rowptr, const int *cols, const doubl
 int admm_b200_plan_bank_stats( int n, const int *rowptr, const int *cols, const double *vals, int n_colors, const int *color_off, const int *color_nodes,
 	const double *pos3, int n_parts, long long *out );
 
+/* Host-only: the block (supernodal) plan of the L D L^T solve (csrc/ldlt_blocks.hpp) for the factor of admm_b200_set_ldlt's
+ * form, applied on the host to one right-hand side b (n values) exactly as the device kernel walks it.
+ * stats[6] = {blocks, largest block, forward levels, backward levels, entries outside / inside the inverted diagonal blocks}. */
+int admm_b200_ldlt_blocks_check( int n, const int *perm, const int *Lp, const int *Li, const double *Lx, const double *D, const double *b, double *x, long long *stats );
+
 /* One line describing which global-solve kernel finalize chose and why (diagnostics). */
 const char *admm_b200_solver_info( const admm_b200_solver *s );
 

@@ -223,3 +223,39 @@ def test_host_code_on_an_unstructured_mesh(pkg):
         assert err.value < 1e-12 and st[4] == A.nnz - n
     stats4 = (ctypes.c_longlong * 4)()
     assert pkg.cuda_lib.admm_b200_dataflow_check(n, ip(rp), ip(ci), dp(va), len(colors), ip(off), ip(nodes), dp(pos), 9, 4, 3, 2, stats4) == 0
+
+
+def test_ldlt_block_plan_host(pkg):
+    """The block (supernodal) plan of the device's L D L^T solve (csrc/ldlt_blocks.hpp), walked on the host exactly as
+    sptrsv_blocks.cuh walks it: solves A x = b to rounding, and the block tree is shallow (a level-scheduled solve of
+    the same factors needs one grid barrier per separator COLUMN: hundreds to thousands of levels)."""
+    import scipy.sparse as sp
+
+    def laplacian(n, elems):
+        k = elems.shape[1]
+        rows = np.repeat(elems, k, axis=1).ravel()
+        cols = np.tile(elems, (1, k)).ravel()
+        A = sp.coo_matrix((-np.ones(rows.size), (rows, cols)), shape=(n, n)).tocsr()
+        A.setdiag(0)
+        A.eliminate_zeros()
+        A = (A + sp.diags(-np.asarray(A.sum(1)).ravel() + 0.5)).tocsr()
+        A.sort_indices()
+        return A
+
+    for verts, elems, max_levels in ((pkg.meshes.make_tet_blocks(24, 8, 6) + (16,)), (pkg.meshes.make_plane_sym(48, 40) + (24,))):
+        A = laplacian(len(verts), elems)
+        b = np.random.RandomState(1).randn(len(verts))
+        x, st = pkg.ldlt_blocks_solve_host(A.indptr, A.indices, A.data, verts.astype(np.float64), b)
+        assert np.abs(A @ x - b).max() < 1e-11 * np.abs(b).max()
+        x_ref, nnz = pkg.ldlt_solve_host(A.indptr, A.indices, A.data, verts.astype(np.float64), b)
+        assert np.abs(x - x_ref).max() < 1e-11 * np.abs(x_ref).max()
+        assert st["levels_f"] <= max_levels and st["levels_b"] <= max_levels, st
+        assert st["nnz_out"] + st["nnz_inv"] >= nnz          # explicit zeros inside the diagonal blocks only ever add entries
+    # a path graph: one long chain of the elimination tree -- blocks are capped, the plan stays correct
+    n = 6000
+    A = sp.diags([-np.ones(n - 1), 2.5 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]).tocsr()
+    pos = np.zeros((n, 3))
+    pos[:, 0] = np.arange(n)
+    b = np.random.RandomState(2).randn(n)
+    x, st = pkg.ldlt_blocks_solve_host(A.indptr, A.indices, A.data, pos, b)
+    assert np.abs(A @ x - b).max() < 1e-11

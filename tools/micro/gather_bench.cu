@@ -145,37 +145,50 @@ int main()
 	std::vector<float> val(32 * (size_t)n_rows);
 	std::vector<uint16_t> col(32 * (size_t)n_rows);
 	for (size_t i = 0; i < val.size(); ++i) { val[i] = (float)(rand() % 1000) * 1e-3f; col[i] = (uint16_t)(rand() % n_loc); }
-	// a second column pattern with mesh-like locality: neighbours within +-64 of the node
-	std::vector<uint16_t> col_local(col.size());
+	// column patterns: what does one LDS.128 gather cost as a function of the bank pattern of its 32 addresses?
+	//   random      uniformly random nodes
+	//   local       neighbours within +-64 of the node (mesh-like)
+	//   linear      col = lane + 32 * row: 32 consecutive float4 = 512 contiguous bytes, conflict-free
+	//   samegroup   col = 8 * (lane + row): every lane of a quarter-warp in the same 16-byte bank group (8-way conflict)
+	//   broadcast   one word for all lanes
+	//   pairs       col = 4 * lane + row: 2 lanes of a quarter-warp per bank group (2-way conflict)
+	const char *pat_name[6] = {"random", "local", "linear", "samegroup", "broadcast", "pairs"};
+	std::vector<uint16_t> pats[6];
+	pats[0] = col;
+	for (int p = 1; p < 6; ++p) pats[p].resize(col.size());
 	for (int s = 0; s < n_slices; ++s) for (int r = srow[s]; r < srow[s + 1]; ++r) for (int l = 0; l < 32; ++l) {
+		const size_t at = (size_t)r * 32 + l;
 		int node = (s * 32 + l) % n_own;
 		int c = node + (rand() % 129) - 64; if (c < 0) c += n_loc; if (c >= n_loc) c -= n_loc;
-		col_local[(size_t)r * 32 + l] = (uint16_t)c;
+		pats[1][at] = (uint16_t)c;
+		pats[2][at] = (uint16_t)((l + 32 * r) % n_loc);
+		pats[3][at] = (uint16_t)((8 * (l + r)) % (n_loc & ~7));
+		pats[4][at] = (uint16_t)(r % n_loc);
+		pats[5][at] = (uint16_t)((4 * l + r) % n_loc);
 	}
-	float *d_val; uint16_t *d_col, *d_col2; int *d_srow; long long *d_out;
-	CK(cudaMalloc(&d_val, val.size() * 4)); CK(cudaMalloc(&d_col, col.size() * 2)); CK(cudaMalloc(&d_col2, col.size() * 2)); CK(cudaMalloc(&d_srow, srow.size() * 4)); CK(cudaMalloc(&d_out, 148 * 16 * 8));
+	float *d_val; uint16_t *d_col, *d_pat[6]; int *d_srow; long long *d_out;
+	CK(cudaMalloc(&d_val, val.size() * 4)); CK(cudaMalloc(&d_col, col.size() * 2)); for (int p = 0; p < 6; ++p) { CK(cudaMalloc(&d_pat[p], col.size() * 2)); CK(cudaMemcpy(d_pat[p], pats[p].data(), col.size() * 2, cudaMemcpyHostToDevice)); } CK(cudaMalloc(&d_srow, srow.size() * 4)); CK(cudaMalloc(&d_out, 148 * 16 * 8));
 	CK(cudaMemcpy(d_val, val.data(), val.size() * 4, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(d_col, col.data(), col.size() * 2, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(d_col2, col_local.data(), col.size() * 2, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(d_srow, srow.data(), srow.size() * 4, cudaMemcpyHostToDevice));
 	const size_t smem = 16 * (size_t)n_loc + 6 * 32 * (size_t)n_rows;
 	printf("part: %d local nodes, %d rows, %d slices, %zu B shared memory\n", n_loc, n_rows, n_slices, smem);
 	const void *kern[4] = {(const void *)bench_kernel<0>, (const void *)bench_kernel<1>, (const void *)bench_kernel<2>, (const void *)bench_kernel<3>};
 	for (int v = 0; v < 4; ++v) CK(cudaFuncSetAttribute(kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int reps = 200;
-	for (int pat = 0; pat < 2; ++pat)
-		for (int v = 0; v < 4; ++v)
-			for (int sync_mode = 0; sync_mode < 2; ++sync_mode)
-				for (int aw : {1, 2, 4, 8, 12, 16}) {
-					const uint16_t *dc = pat ? d_col2 : d_col;
+	for (int pat = 0; pat < 6; ++pat)
+		for (int v : {0, 2})
+			for (int sync_mode = 0; sync_mode < (pat < 2 ? 2 : 1); ++sync_mode)
+				for (int aw : {1, 4, 8, 16}) {
+					const uint16_t *dc = d_pat[pat];
 					int nl = n_loc, nr = n_rows, ns = n_slices, r = reps, sm = sync_mode;
 					void *args[] = {&d_val, &dc, &d_srow, &nl, &nr, &ns, &aw, &r, &sm, &d_out};
 					for (int w = 0; w < 2; ++w) CK(cudaLaunchKernel(kern[v], dim3(148), dim3(512), args, smem, 0));
 					CK(cudaDeviceSynchronize());
 					long long h[16];
 					CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
-					printf("columns %-6s v%d %-12s active warps %2d: %6.0f cycles per slice-step (warp 0), %6.0f cycles per slice of pipe time\n", pat ? "local" : "random", v,
-						sync_mode ? "syncthreads" : "free-running", aw, (double)h[0] / reps, (double)h[0] / reps / aw);
+					printf("columns %-9s v%d %-12s active warps %2d: %6.0f cycles per slice-step (warp 0), %6.0f cycles per slice of pipe time, %5.1f per row-step\n", pat_name[pat], v,
+						sync_mode ? "syncthreads" : "free-running", aw, (double)h[0] / reps, (double)h[0] / reps / aw, (double)h[0] / reps / aw / (v == 2 ? 16.0 : 18.0));
 				}
 	return 0;
 }
