@@ -40,10 +40,14 @@ struct LdltBlockPlan {
 	int max_block = 0;
 };
 
-inline int ldlt_pow2_lanes(double avg_len)
+// Threads per row of a phase: about 8 entries per thread (4 loads in flight, twice), but never fewer rows in flight than the
+// grid has room for -- the rows of the top separators hold thousands of entries while only a few hundred rows exist, so a
+// row gets up to a whole CTA (1024 threads, reduced through shared memory in sptrsv_blocks.cuh).
+inline int ldlt_pow2_lanes(double avg_len, int n_rows = 1 << 30, int grid_threads = 148 * 1024)
 {
 	int t = 1;
-	while (t < 32 && (double)t * 6.0 < avg_len) t <<= 1; // about 6 entries per lane
+	while (t < 1024 && (double)t * 8.0 < avg_len) t <<= 1;
+	while (t > 1 && (long long)n_rows * t > 2LL * grid_threads) t >>= 1; // keep at most two rounds of rows
 	return t;
 }
 
@@ -177,8 +181,8 @@ inline LdltBlockPlan plan_ldlt_blocks(int n, const int *Lp, const int *Li, const
 				out += itemptr[i + 1] - itemptr[i];
 				dense += 0.5 * (s - 1);
 			}
-			lanes[2 * l] = ldlt_pow2_lanes(cnt ? out / cnt : 0.0);
-			lanes[2 * l + 1] = ldlt_pow2_lanes(cnt ? dense / cnt : 0.0);
+			lanes[2 * l] = ldlt_pow2_lanes(cnt ? out / cnt : 0.0, cnt);
+			lanes[2 * l + 1] = ldlt_pow2_lanes(cnt ? dense / cnt : 0.0, cnt);
 		}
 	};
 	bucket(flev, P.n_levels_f, P.f_lev_ptr, P.f_rows, P.f_rowptr, P.f_lanes);

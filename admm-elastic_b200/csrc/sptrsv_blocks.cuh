@@ -30,18 +30,54 @@ struct LdltBlkParams {
 	const int *active;               // NULL, or a device flag: 0 = skip this solve (uzawa.cuh: the CG loop has already ended)
 };
 
-__device__ __forceinline__ void blk_reduce(double &sx, double &sy, double &sz, int T)
+// Sum over the T threads of a group (T a power of two, 1..1024; groups are aligned, so one never straddles a CTA).
+// T <= 32: shuffles.  T > 32: every warp reduces, lane 0 leaves its partial sum in shared memory, the group's first warp
+// adds them up (two CTA barriers -- every thread of the CTA calls this the same number of times).  Valid in sub == 0.
+__device__ __forceinline__ void blk_reduce(double &sx, double &sy, double &sz, int T, double *s_part)
 {
-	for (int o = T >> 1; o > 0; o >>= 1) {
+	const int w = T < 32 ? T : 32;
+	for (int o = w >> 1; o > 0; o >>= 1) {
 		sx += __shfl_xor_sync(0xffffffffu, sx, o);
 		sy += __shfl_xor_sync(0xffffffffu, sy, o);
 		sz += __shfl_xor_sync(0xffffffffu, sz, o);
+	}
+	if (T <= 32) return;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpg = T >> 5; // warps per group
+	__syncthreads();
+	if (lane == 0) { s_part[3 * warp] = sx; s_part[3 * warp + 1] = sy; s_part[3 * warp + 2] = sz; }
+	__syncthreads();
+	if ((warp & (wpg - 1)) == 0 && lane == 0) {
+		for (int k = 1; k < wpg; ++k) { sx += s_part[3 * (warp + k)]; sy += s_part[3 * (warp + k) + 1]; sz += s_part[3 * (warp + k) + 2]; }
+	}
+}
+
+// dot product of a sparse / dense row with double4 vectors: 4 independent loads in flight per lane (the rows of the top
+// separators have thousands of entries and every gather is an L2 round trip)
+template <bool INDEXED>
+__device__ __forceinline__ void blk_row_dot(const double *__restrict__ vals, const int *__restrict__ idx, const double4 *vec, int q0, int q1, int sub, int T,
+	double &sx, double &sy, double &sz)
+{
+	int q = q0 + sub;
+	for (; q + 3 * T < q1; q += 4 * T) {
+		double a[4]; int c[4]; double4 v[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) { a[u] = __ldg(&vals[q + u * T]); c[u] = INDEXED ? __ldg(&idx[q + u * T]) : q + u * T; }
+#pragma unroll
+		for (int u = 0; u < 4; ++u) v[u] = ld_node_cg(&vec[c[u]]);
+#pragma unroll
+		for (int u = 0; u < 4; ++u) { sx += a[u] * v[u].x; sy += a[u] * v[u].y; sz += a[u] * v[u].z; }
+	}
+	for (; q < q1; q += T) {
+		const double a = __ldg(&vals[q]);
+		const double4 v = ld_node_cg(&vec[INDEXED ? __ldg(&idx[q]) : q]);
+		sx += a * v.x; sy += a * v.y; sz += a * v.z;
 	}
 }
 
 __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 {
-	const int tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+	__shared__ double s_part[3 * 32];
 	unsigned int bar_target = 0;
 	if (P.active && *P.active == 0) return; // the same for every block: no barrier is left waiting
 
@@ -49,21 +85,14 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 	for (int lv = 0; lv < P.n_levels_f; ++lv) {
 		const int k0 = P.f_lev_ptr[lv], k1 = P.f_lev_ptr[lv + 1];
 		{
-			const int T = P.f_lanes[2 * lv], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			const int T = P.f_lanes[2 * lv], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
 			for (int kb = k0; kb < k1; kb += n_groups) {
 				const int k = kb + group;
 				const bool act = k < k1;
 				const int i = act ? __ldg(&P.f_rows[k]) : 0;
 				double sx = 0, sy = 0, sz = 0;
-				if (act) {
-					const int q1 = __ldg(&P.f_rowptr[i + 1]);
-					for (int q = __ldg(&P.f_rowptr[i]) + sub; q < q1; q += T) {
-						const double a = __ldg(&P.f_vals[q]);
-						const double4 yj = ld_node_cg(&P.y[__ldg(&P.f_cols[q])]);
-						sx += a * yj.x; sy += a * yj.y; sz += a * yj.z;
-					}
-				}
-				blk_reduce(sx, sy, sz, T);
+				if (act) blk_row_dot<true>(P.f_vals, P.f_cols, P.y, __ldg(&P.f_rowptr[i]), __ldg(&P.f_rowptr[i + 1]), sub, T, sx, sy, sz);
+				blk_reduce(sx, sy, sz, T, s_part);
 				if (act && sub == 0) {
 					const double4 bi = P.b[__ldg(&P.perm[i])];
 					st_node(&P.t[i], bi.x - sx, bi.y - sy, bi.z - sz);
@@ -72,7 +101,7 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 		}
 		grid_barrier(P.barrier, bar_target, gridDim.x);
 		{
-			const int T = P.f_lanes[2 * lv + 1], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			const int T = P.f_lanes[2 * lv + 1], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
 			for (int kb = k0; kb < k1; kb += n_groups) {
 				const int k = kb + group;
 				const bool act = k < k1;
@@ -81,13 +110,9 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 				if (act) {
 					const int bl = __ldg(&P.blk_of[i]), c0 = __ldg(&P.blk_c0[bl]), r = i - c0;
 					const double *inv = P.inv + __ldg(&P.inv_off[bl]) + (long long)r * (r - 1) / 2;
-					for (int c = sub; c < r; c += T) {
-						const double a = __ldg(&inv[c]);
-						const double4 tc = ld_node_cg(&P.t[c0 + c]);
-						sx += a * tc.x; sy += a * tc.y; sz += a * tc.z;
-					}
+					blk_row_dot<false>(inv, nullptr, P.t + c0, 0, r, sub, T, sx, sy, sz);
 				}
-				blk_reduce(sx, sy, sz, T);
+				blk_reduce(sx, sy, sz, T, s_part);
 				if (act && sub == 0) {
 					const double4 ti = ld_node_cg(&P.t[i]);
 					st_node(&P.y[i], ti.x + sx, ti.y + sy, ti.z + sz);
@@ -100,21 +125,14 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 	for (int lv = 0; lv < P.n_levels_b; ++lv) {
 		const int k0 = P.b_lev_ptr[lv], k1 = P.b_lev_ptr[lv + 1];
 		{
-			const int T = P.b_lanes[2 * lv], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			const int T = P.b_lanes[2 * lv], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
 			for (int kb = k0; kb < k1; kb += n_groups) {
 				const int k = kb + group;
 				const bool act = k < k1;
 				const int j = act ? __ldg(&P.b_cols[k]) : 0;
 				double sx = 0, sy = 0, sz = 0;
-				if (act) {
-					const int q1 = __ldg(&P.b_colptr[j + 1]);
-					for (int q = __ldg(&P.b_colptr[j]) + sub; q < q1; q += T) {
-						const double a = __ldg(&P.b_vals[q]);
-						const double4 xi = ld_node_cg(&P.y[__ldg(&P.b_rows[q])]); // rows below the block: already final
-						sx += a * xi.x; sy += a * xi.y; sz += a * xi.z;
-					}
-				}
-				blk_reduce(sx, sy, sz, T);
+				if (act) blk_row_dot<true>(P.b_vals, P.b_rows, P.y, __ldg(&P.b_colptr[j]), __ldg(&P.b_colptr[j + 1]), sub, T, sx, sy, sz); // rows below the block: already final
+				blk_reduce(sx, sy, sz, T, s_part);
 				if (act && sub == 0) {
 					const double4 yj = ld_node_cg(&P.y[j]);
 					const double d = __ldg(&P.D[j]);
@@ -124,7 +142,7 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 		}
 		grid_barrier(P.barrier, bar_target, gridDim.x);
 		{
-			const int T = P.b_lanes[2 * lv + 1], sub = lane & (T - 1), group = tid / T, n_groups = n_threads / T;
+			const int T = P.b_lanes[2 * lv + 1], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
 			for (int kb = k0; kb < k1; kb += n_groups) {
 				const int k = kb + group;
 				const bool act = k < k1;
@@ -133,13 +151,9 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 				if (act) {
 					const int bl = __ldg(&P.blk_of[j]), c0 = __ldg(&P.blk_c0[bl]), s = __ldg(&P.blk_c0[bl + 1]) - c0, r = j - c0;
 					const double *invT = P.invT + __ldg(&P.inv_off[bl]) + (long long)r * (s - 1) - (long long)r * (r - 1) / 2;
-					for (int c = r + 1 + sub; c < s; c += T) {
-						const double a = __ldg(&invT[c - r - 1]);
-						const double4 tc = ld_node_cg(&P.t[c0 + c]);
-						sx += a * tc.x; sy += a * tc.y; sz += a * tc.z;
-					}
+					blk_row_dot<false>(invT, nullptr, P.t + c0 + r + 1, 0, s - r - 1, sub, T, sx, sy, sz);
 				}
-				blk_reduce(sx, sy, sz, T);
+				blk_reduce(sx, sy, sz, T, s_part);
 				if (act && sub == 0) {
 					const double4 tj = ld_node_cg(&P.t[j]);
 					const double rx = tj.x + sx, ry = tj.y + sy, rz = tj.z + sz;
