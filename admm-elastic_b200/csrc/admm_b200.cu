@@ -151,7 +151,7 @@ struct admm_b200_solver {
 	DevBuf<PartDesc> res_parts;
 	DevBuf<uint16_t> res_col;
 	DevBuf<char> res_val;
-	DevBuf<int> res_gid, res_slice_row, res_slice_mid, res_color_slice, res_nbr, res_halo_color;
+	DevBuf<int> res_gid, res_slice_row, res_color_slice, res_nbr, res_halo_color;
 	DevBuf<float4> res_nodebuf;
 	DevBuf<uint2> res_dglob;
 	DevBuf<int> res_dest_off; DevBuf<unsigned int> res_dest_slot; int res_total_slots = 0; // mailboxes (plan_mailboxes)
@@ -427,7 +427,7 @@ void launch_mcgs_resident(S *s)
 	} else {
 		R32.parts = s->res_parts.p; R32.col = s->res_col.p; R32.val = (const float *)s->res_val.p; R32.gid = s->res_gid.p;
 		R32.slice_row = s->res_slice_row.p; R32.color_slice = s->res_color_slice.p; R32.slice_node = s->res_slice_node.p; R32.nbr = s->res_nbr.p;
-		R32.halo_color = s->res_halo_color.p; R32.slice_mid = s->res_slice_mid.p;
+		R32.halo_color = s->res_halo_color.p;
 		R32.part_epoch = part_epoch; R32.sweep_flag = sweep_flag; R32.sweep_arrive = sweep_arrive; R32.prof = s->res_prof.p;
 		R32.dglob = s->res_dglob.p; R32.nodebuf = s->res_nodebuf.p; R32.val64 = s->res_val64.p;
 		R32.dest_off = s->res_dest_off.p; R32.dest_slot = s->res_dest_slot.p; R32.total_slots = s->res_total_slots;
@@ -776,7 +776,6 @@ void build_mcgs_resident(S *s)
 	s->res_col.upload(R.col, s->stream);
 	s->res_gid.upload(R.gid, s->stream);
 	s->res_slice_row.upload(R.slice_row, s->stream);
-	s->res_slice_mid.upload(R.slice_mid, s->stream);
 	s->res_color_slice.upload(R.color_slice, s->stream);
 	s->res_slice_node.upload(R.slice_node, s->stream);
 	s->res_nbr.upload(R.nbr.empty() ? std::vector<int>(1, 0) : R.nbr, s->stream);

@@ -36,7 +36,6 @@ namespace admmb200 {
 struct OwnedSlice {   // registers; everything but l / rb / ia / dst0 / dst1 is warp-uniform
 	int meta;         // -1: none; else colour | boundary << 8 | pinned << 9 | readers << 10 (pinned, readers: per lane)
 	int r0, r1;       // ELL rows [r0, r1)
-	int rm;           // boundary slice: rows [r0, rm) read no halo value of the previous colour (gathered before the halo arrives)
 	int l;            // local node id of this lane, -1: padding lane
 	unsigned int dst0, dst1; // first two mailbox slots this node is published to (slot | rank << 27); count in meta bits 10..15
 	float rb[3];      // r0 = b - A x_ref
@@ -46,18 +45,10 @@ struct OwnedSlice {   // registers; everything but l / rb / ia / dst0 / dst1 is 
 // One lane's row of the sliced ELL: rows [r0, r1) in batches of 8 with all 24 loads of a batch in flight.
 // The last batch is padded by re-reading row r1 - 1 with a zero coefficient instead of a serial tail loop
 // (a tail of up to 7 dependent col -> d loads used to cost as much as the three full batches before it).
-__device__ __forceinline__ void owned_gather_acc(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
-	int r0, int r1, int lane, float &sx, float &sy, float &sz);
 __device__ __forceinline__ void owned_gather(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
 	int r0, int r1, int lane, float &sx, float &sy, float &sz)
 {
 	sx = 0.f; sy = 0.f; sz = 0.f;
-	owned_gather_acc(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
-}
-// adds rows [r0, r1) to (sx, sy, sz)
-__device__ __forceinline__ void owned_gather_acc(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
-	int r0, int r1, int lane, float &sx, float &sy, float &sz)
-{
 	const float *v = s_val + r0 * 32 + lane;
 	const uint16_t *c = s_col + r0 * 32 + lane;
 	const int n = r1 - r0;
@@ -87,10 +78,8 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ double red[32];
 	__shared__ __align__(8) uint64_t tma_bar;
-	// pass of colour c, warp w: -1 = only interior work (skips the halo barrier); >= 0 = polls the halo, rank among the
-	// pollers; -2 = owns a boundary slice but leaves the polling to the idle warps (it gathers its early rows meanwhile)
-	__shared__ short s_role[ADMMB200_OWNED_MAX_COLORS * NW];
-	__shared__ short s_npoll[ADMMB200_OWNED_MAX_COLORS], s_npart[ADMMB200_OWNED_MAX_COLORS];
+	__shared__ short s_role[ADMMB200_OWNED_MAX_COLORS * NW]; // rank of warp w among the pollers of colour c, -1: not a poller
+	__shared__ short s_npoll[ADMMB200_OWNED_MAX_COLORS];
 	__shared__ int s_decision;
 	const McgsParams &P = R.base;
 	const long long t_kernel = PROF ? clock64() : 0;
@@ -148,7 +137,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 	OwnedSlice S[KMAX];
 #pragma unroll
 	for (int k = 0; k < KMAX; ++k) {
-		S[k].meta = -1; S[k].r0 = 0; S[k].r1 = 0; S[k].rm = 0; S[k].l = -1; S[k].dst0 = 0u; S[k].dst1 = 0u;
+		S[k].meta = -1; S[k].r0 = 0; S[k].r1 = 0; S[k].l = -1; S[k].dst0 = 0u; S[k].dst1 = 0u;
 		S[k].rb[0] = S[k].rb[1] = S[k].rb[2] = 0.f; S[k].ia[0] = S[k].ia[1] = S[k].ia[2] = 0.f;
 		int c, sl; bool bnd;
 		if (locate(k * NW + warp, c, bnd, sl)) {
@@ -158,7 +147,6 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 			for (int j = 0; j < k; ++j) if (bnd && S[j].meta >= 0 && (S[j].meta & 0x1ff) == (c | 0x100)) S[k].meta |= 0x10000;
 			S[k].r0 = __ldg(&R.slice_row[d.slice_off + sl]);
 			S[k].r1 = __ldg(&R.slice_row[d.slice_off + sl + 1]);
-			S[k].rm = bnd ? __ldg(&R.slice_mid[d.slice_off + sl]) : S[k].r1;
 			S[k].l = (int)__ldg(&R.slice_node[d.snode_off + sl * 32 + lane]);
 		}
 	}
@@ -171,27 +159,15 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 			int cc, sl; bool bnd;
 			if (locate(k * NW + w, cc, bnd, sl) && cc == c) { if (bnd) has_b = true; else has_i = true; }
 		}
-		s_role[t] = has_b ? 2 : (!has_i ? 1 : 0); // 2: boundary owner, 1: idle in this colour, 0: interior only
+		s_role[t] = (has_b || !has_i) ? 1 : 0;
 	}
 	if (d.n_rows > 0) mbar_wait(&tma_bar, 0);
 	__syncthreads();
 	if (tid < C) {
-		// the idle warps poll; without idle warps the boundary owners do (after their early rows)
-		int n_idle = 0, n_bown = 0;
-		for (int w = 0; w < NW; ++w) { n_idle += s_role[tid * NW + w] == 1; n_bown += s_role[tid * NW + w] == 2; }
 		short rank = 0;
-		for (int w = 0; w < NW; ++w) {
-			short &q = s_role[tid * NW + w];
-			if (q == 1 || (q == 2 && n_idle == 0)) q = rank++;
-			else if (q == 2) q = (short)-2;
-			else q = (short)-1;
-		}
-		short n_part = (short)(n_idle + n_bown);
-		if (rank == 0) { // nobody polls yet: warp 0 has to keep the halo current
-			if (s_role[tid * NW] == -1) ++n_part;
-			s_role[tid * NW] = 0; rank = 1;
-		}
-		s_npoll[tid] = rank; s_npart[tid] = n_part;
+		for (int w = 0; w < NW; ++w) { short &q = s_role[tid * NW + w]; q = q ? rank++ : (short)-1; }
+		if (rank == 0) { s_role[tid * NW] = 0; rank = 1; } // somebody has to keep the halo current
+		s_npoll[tid] = rank;
 	}
 
 	const long long t_staged = PROF ? clock64() : 0;
@@ -306,24 +282,16 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 					if (cnt > 3) pre3 = __ldg(&R.dest_slot[pre_e0 + 3]);
 				}
 			}
-			// early rows of this warp's boundary slice: they read no halo value of the previous colour, so they run while
-			// those values are still in flight (the chain the neighbours wait for is only rows [rm, r1) + update + publish)
-			float esx = 0.f, esy = 0.f, esz = 0.f;
-#pragma unroll
-			for (int k = 0; k < KMAX; ++k) {
-				if (S[k].meta < 0 || (S[k].meta & 0x101ff) != (color | 0x100)) continue;
-				owned_gather_acc(s_val, s_col, s_d, S[k].r0, S[k].rm, lane, esx, esy, esz);
-			}
-			if (role != -1) {
+			if (role >= 0) {
 				const int n_poll = 32 * (int)s_npoll[color];
-				if (role >= 0 && pass > 0 && !(PROF && (R.dbg & 2))) {
+				if (pass > 0 && !(PROF && (R.dbg & 2))) {
 					// what the neighbours changed in the previous pass: the halo nodes of that pass's colour
 					const int cp = (color + C - 1) % C;
 					const int it_prev = color > 0 ? it : it - 1;
 					refresh(cp, R.dglob + (size_t)(it_prev & 1) * buf_stride, R.tag_base | pass, 32 * role + lane, n_poll);
 				}
 				if (PROF) TR(1);
-				named_sync(1, 32 * (int)s_npart[color]);
+				named_sync(1, n_poll);
 				if (PROF && pass > 0 && role == 0 && lane == 0) {
 					// when did the neighbours publish what has just arrived?  (global timer; single GPU only)
 					const unsigned long long now = gtime_ns();
@@ -343,11 +311,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				if ((S[k].meta & 0xff) != color || S[k].meta < 0) continue;
 				if (PROF && (R.dbg & 4) && !(S[k].meta & 0x100)) continue; // timing experiment: no interior work
 				float sx, sy, sz;
-				if ((S[k].meta & 0x10100) == 0x100) {
-					// the warp's first boundary slice of this colour: its early rows are already in (esx, esy, esz)
-					sx = esx; sy = esy; sz = esz;
-					owned_gather_acc(s_val, s_col, s_d, S[k].rm, (PROF && (R.dbg & 32)) ? S[k].rm : S[k].r1, lane, sx, sy, sz);
-				} else owned_gather(s_val, s_col, s_d, S[k].r0, (PROF && (R.dbg & 32)) ? S[k].r0 : S[k].r1, lane, sx, sy, sz);
+				owned_gather(s_val, s_col, s_d, S[k].r0, (PROF && (R.dbg & 32)) ? S[k].r0 : S[k].r1, lane, sx, sy, sz);
 				const int l = S[k].l;
 				if (l < 0) continue;
 				const float4 dold = s_d[l];

@@ -30,7 +30,6 @@ struct McgsRes32Params {
 	const float *val;     // swept in shared memory
 	const double *val64;  // same entries in full precision, streamed once per solve for r0 = b - A x_ref
 	const int *gid, *slice_row, *color_slice, *nbr, *halo_color;
-	const int *slice_mid;   // static-ownership kernel: first row of a boundary slice that may read a halo value of the previous colour
 	const short *slice_node;
 	unsigned int *part_epoch, *sweep_flag, *sweep_arrive;
 	unsigned long long *prof;

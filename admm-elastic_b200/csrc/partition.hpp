@@ -15,7 +15,6 @@
 #include <cstring>
 #include <functional>
 #include <numeric>
-#include <utility>
 #include <stdexcept>
 #include <vector>
 
@@ -51,10 +50,6 @@ struct ResidentPlan {
 	std::vector<uint16_t> col;     // local index: < n_own -> shared-memory x, else halo (gid[col])
 	std::vector<double> val;       // converted to the storage precision at upload
 	std::vector<int> gid, slice_row, color_slice, nbr, halo_color;
-	// T = 1: per slice the first row-step (relative to the part, like slice_row) that may hold a "late" entry -- a halo
-	// node of the PREVIOUS colour, the only values a boundary slice has to wait for in its pass (all other neighbours were
-	// final when the pass began).  Rows [slice_row, slice_mid) can be gathered before the halo has arrived.
-	std::vector<int> slice_mid;
 	std::vector<short> slice_node;
 	std::vector<int> part_of;      // node -> part (for tests / diagnostics)
 	// Mailboxes (mcgs_owned_f32.cuh): every part has one slot per halo node, in its own halo order, so the
@@ -298,21 +293,11 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 	// and inside a colour the interior nodes first: they are updated while the neighbours' flags of
 	// the previous pass are still in flight
 	std::vector<int> owner_local(n, 0); // position of a node in its owner's order
-	// late entries of a node: neighbours of the previous colour owned by another part
-	std::vector<int> n_late(n, 0);
-	for (int i = 0; i < n; ++i) {
-		const int cp = (color_of[i] + n_colors - 1) % n_colors;
-		for (int q = rowptr[i]; q < rowptr[i + 1]; ++q)
-			if (cols[q] != i && vals[q] != 0.0 && R.part_of[cols[q]] != R.part_of[i] && color_of[cols[q]] == cp) ++n_late[i];
-	}
 	for (int p = 0; p < n_parts; ++p) {
 		std::vector<int> &nodes = own[p];
 		std::sort(nodes.begin(), nodes.end(), [&](int a, int b) {
 			if (color_of[a] != color_of[b]) return color_of[a] < color_of[b];
 			if (boundary[a] != boundary[b]) return boundary[a] < boundary[b];
-			// boundary nodes: similar numbers of early entries (row length minus late entries) share a slice, so the
-			// part of a slice that can run before the halo arrives is as long as possible
-			if (T == 1 && boundary[a] && (rowlen[a] - n_late[a]) != (rowlen[b] - n_late[b])) return (rowlen[a] - n_late[a]) > (rowlen[b] - n_late[b]);
 			if (rowlen[a] != rowlen[b]) return rowlen[a] > rowlen[b];
 			return a < b;
 		});
@@ -390,27 +375,7 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 					}
 					for (; j < width * T; ++j) R.col[base + (size_t)(j / T) * 32 + g * T + (j % T)] = (uint16_t)self;
 				}
-				int mid = width; // T > 1 and interior slices: no late part
-				if (T == 1 && bnd && width > 0) {
-					// early entries first (own nodes and halo nodes of colours other than the previous one), late entries last
-					const int cp = (c + n_colors - 1) % n_colors;
-					mid = width;
-					for (int g = 0; g < 32; ++g) {
-						const int node = (k + g < k1) ? nodes[k + g] : -1;
-						if (node < 0) continue;
-						std::vector<std::pair<uint16_t, double>> early, late;
-						for (int j = 0; j < rowlen[node]; ++j) {
-							const uint16_t li = R.col[base + (size_t)j * 32 + g];
-							const double v = R.val[base + (size_t)j * 32 + g];
-							const bool is_late = li >= d.n_own && color_of[halo[li - d.n_own]] == cp;
-							(is_late ? late : early).push_back({li, v});
-						}
-						int j = 0;
-						for (auto &e : early) { R.col[base + (size_t)j * 32 + g] = e.first; R.val[base + (size_t)j * 32 + g] = e.second; ++j; }
-						for (auto &e : late) { R.col[base + (size_t)j * 32 + g] = e.first; R.val[base + (size_t)j * 32 + g] = e.second; ++j; }
-						mid = std::min(mid, (int)early.size());
-					}
-				} else if (T == 1 && R.schedule_banks && width > 0) {
+				if (T == 1 && R.schedule_banks && width > 0) {
 					// re-order the entries of every lane's row so that the quarter-warp phases of the float4 gather hit distinct
 					// shared-memory bank groups (detail::schedule_slice)
 					std::vector<detail::SliceEntry> lane_rows[32];
@@ -421,11 +386,10 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 						if (node < 0) continue;
 						for (int j = 0; j < rowlen[node]; ++j) lane_rows[g].push_back({R.col[base + (size_t)j * 32 + g], R.val[base + (size_t)j * 32 + g]});
 					}
-					R.cycles_before += [&]() { long long c2 = 0; for (int j = 0; j < width; ++j) c2 += detail::rowstep_cycles(&R.col[base + (size_t)j * 32]); return c2; }();
+					R.cycles_before += [&]() { long long c = 0; for (int j = 0; j < width; ++j) c += detail::rowstep_cycles(&R.col[base + (size_t)j * 32]); return c; }();
 					detail::schedule_slice(lane_rows, width, self, d.n_own + (int)halo.size(), &R.col[base], &R.val[base]);
-					R.cycles_after += [&]() { long long c2 = 0; for (int j = 0; j < width; ++j) c2 += detail::rowstep_cycles(&R.col[base + (size_t)j * 32]); return c2; }();
+					R.cycles_after += [&]() { long long c = 0; for (int j = 0; j < width; ++j) c += detail::rowstep_cycles(&R.col[base + (size_t)j * 32]); return c; }();
 				}
-				R.slice_mid.push_back(rows + mid);
 				rows += width;
 				++slices;
 				R.slice_row.push_back(rows);
@@ -433,7 +397,6 @@ inline ResidentPlan plan_resident(int n, const int *rowptr, const int *cols, con
 			k = k1;
 		}
 		R.color_slice.push_back(slices);
-		R.slice_mid.push_back(rows); // keeps slice_mid indexed like slice_row (n_slices + 1 entries per part)
 		d.n_halo = (int)halo.size();
 		d.n_slices = slices;
 		d.n_rows = rows;
