@@ -52,7 +52,10 @@ LIMITS = (0.95, 1.05)      # :50-51
 DENSITY = 1522.0           # samples/utils/AddMeshes.hpp:104-106
 MODEL_NAMES = {0: "linear", 1: "neohookean", 2: "stvk"}
 SOLVER_NAMES = {0: "LDLT", 1: "NodalMultiColorGS 30 sweeps omega=1.9", 2: "UzawaCG (pins as SpringPin energy terms, LDLT inside)"}
-PARITY_TOL = 2e-6          # metres: N ranks vs one GPU after the same steps (same colours; only summation orders differ)
+# N ranks vs one GPU after the same steps (same colours; only the summation order of a vertex's element shares and the
+# fp32 rounding inside the sweeps differ): max |dx| / bounding-box diagonal.  fp32 has 6e-8; W + 2K + 2 steps x 20 ADMM
+# iterations amplify it (measured at N = 2 after 25 steps: 4.7e-7); the fp32 gate of SURVEY.md 8d is 1e-4.
+PARITY_TOL_REL = 2e-6
 
 
 def parse_args():
@@ -464,11 +467,12 @@ def run_b200(args):
             if n_el <= 2000000:
                 one = measure(pkg, args, scene, torch, dist, stream, 0, 1, local_rank, K, W)
                 diff = float(np.abs(one["x"].reshape(-1, 3) - x_n).max())
-                parity = {"max_abs": diff, "tol": PARITY_TOL, "unit": "m", "steps_compared": W + 2 * K + 2,
+                bbox = float(np.linalg.norm(scene["verts"].max(0) - scene["verts"].min(0)))
+                parity = {"max_abs": diff, "max_over_bbox": diff / bbox, "tol_over_bbox": PARITY_TOL_REL, "bbox_diagonal_m": bbox, "unit": "m", "steps_compared": W + 2 * K + 2,
                           "what": "owned nodes of all %d ranks merged vs a single-GPU run of the same %d steps on rank 0 (same colours)" % (world, W + 2 * K + 2),
                           "single_gpu_value": iters * K / (one["ms_res"] * 1e-3)}
             else:
-                parity = {"max_abs": None, "tol": PARITY_TOL, "skipped": "the single-GPU run of this mesh is not part of the default bench (see tests/test_multi_gpu.py)"}
+                parity = {"max_abs": None, "max_over_bbox": None, "tol_over_bbox": PARITY_TOL_REL, "skipped": "the single-GPU run of this mesh is not part of the default bench (see tests/test_multi_gpu.py)"}
         dist.barrier()
 
     # N > 1: ONE mesh sharded over the ranks (strong scaling) -- the job's ADMM iterations, not a sum
@@ -574,7 +578,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": None, "error": str(e)}
     if rank == 0:
         print(json.dumps(line))
-    bad_parity = bool(parity and parity.get("max_abs") is not None and not (parity["max_abs"] <= PARITY_TOL))
+    bad_parity = bool(parity and parity.get("max_over_bbox") is not None and not (parity["max_over_bbox"] <= PARITY_TOL_REL))
     if world > 1:
         flag = torch.tensor([1.0 if bad_parity else 0.0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
@@ -584,7 +588,7 @@ def run_b200(args):
     if not finite:
         raise SystemExit("bench.py: non-finite positions")
     if bad_parity:
-        raise SystemExit("bench.py: the %d-GPU positions differ from the single-GPU run by more than %g m" % (world, PARITY_TOL))
+        raise SystemExit("bench.py: the %d-GPU positions differ from the single-GPU run by more than %g x the bounding-box diagonal" % (world, PARITY_TOL_REL))
 
 
 def load_traffic():
