@@ -304,6 +304,12 @@ class Solver(object):
                 self._ck(_host.admmhost_mgpu_import(self.h, r, ctypes.create_string_buffer(b, IPC_BYTES)))
         self._ck(_host.admmhost_mgpu_ready(self.h))
 
+    def mgpu_nodes(self):
+        """(owned, ghost) node counts of this rank: what step() moves per step is owned + ghost up, owned down."""
+        out = (ctypes.c_int * 2)()
+        self._ck(_host.admmhost_mgpu_nodes(self.h, out))
+        return int(out[0]), int(out[1])
+
     def node_owner(self):
         out = np.zeros(self.dof // 3, dtype=np.int32)
         n = _host.admmhost_get_node_owner(self.h, _ip(out))

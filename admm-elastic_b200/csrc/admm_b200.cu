@@ -178,6 +178,10 @@ struct admm_b200_solver {
 	double4 *peer_x[ADMMB200_MAX_RANKS] = {nullptr};
 	unsigned int *peer_flags[ADMMB200_MAX_RANKS] = {nullptr};
 	std::vector<void *> ipc_opened;
+	// multi-GPU step_host: only the nodes this rank touches travel -- owned + ghost nodes up, owned nodes down
+	std::vector<int> mg_local, mg_owned;     // node ids, ascending
+	DevBuf<int> d_mg_local, d_mg_owned;
+	double *mg_pinned = nullptr;             // pinned host staging: [x local | v local]
 	bool mg_ready = false;
 	unsigned int mg_epoch = 0;
 
@@ -214,6 +218,7 @@ struct admm_b200_solver {
 
 	~admm_b200_solver() {
 		for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
+		if (mg_pinned) cudaFreeHost(mg_pinned);
 		for (auto t : tets) delete t;
 		for (auto t : tris) delete t;
 		for (auto e : events) cudaEventDestroy(e);
@@ -783,6 +788,19 @@ void build_mcgs_resident(S *s)
 	if (s->world > 1) {
 		s->mg_dest_mask.upload(dest_masks(R, s->n_nodes, s->gs_parts, s->rank), s->stream);
 		s->mg_flags.alloc(8 * ADMMB200_MAX_RANKS); s->mg_flags.zero(s->stream);
+		// nodes this rank owns, and owned + ghost nodes (halo nodes of its parts that another rank owns)
+		std::vector<char> loc((size_t)s->n_nodes, 0);
+		for (int i = 0; i < s->n_nodes; ++i) if (R.part_of[i] / s->gs_parts == s->rank) loc[i] = 1;
+		for (int p = s->rank * s->gs_parts; p < (s->rank + 1) * s->gs_parts; ++p) {
+			const PartDesc &d = R.parts[p];
+			for (int h = 0; h < d.n_halo; ++h) { const int g = R.gid[d.gid_off + d.n_own + h]; if (!loc[g]) loc[g] = 2; }
+		}
+		s->mg_local.clear(); s->mg_owned.clear();
+		for (int i = 0; i < s->n_nodes; ++i) { if (loc[i]) s->mg_local.push_back(i); if (loc[i] == 1) s->mg_owned.push_back(i); }
+		s->d_mg_local.upload(s->mg_local.empty() ? std::vector<int>(1, 0) : s->mg_local, s->stream);
+		s->d_mg_owned.upload(s->mg_owned.empty() ? std::vector<int>(1, 0) : s->mg_owned, s->stream);
+		if (s->mg_pinned) { cudaFreeHost(s->mg_pinned); s->mg_pinned = nullptr; }
+		CK(cudaMallocHost((void **)&s->mg_pinned, sizeof(double) * 6 * std::max<size_t>(s->mg_local.size(), 1)));
 	}
 	if (val_bytes == 4) {
 		require((long long)s->gs_iters * s->n_colors < 4094, "resident fp32 MCGS: sweeps x colours must stay below 4094 (12-bit pass tags)");
@@ -1164,6 +1182,57 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 	}
 }
 
+__global__ void scatter3_to4_kernel(int n, const int *__restrict__ idx, const double *__restrict__ in3, double4 *__restrict__ out4)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	st_node(&out4[idx[i]], in3[3 * i], in3[3 * i + 1], in3[3 * i + 2]);
+}
+__global__ void gather4_to3_kernel(int n, const int *__restrict__ idx, const double4 *__restrict__ in4, double *__restrict__ out3)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double4 v = in4[idx[i]];
+	out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z;
+}
+
+// Multi-GPU variants of upload_state / download_state: a rank computes on its owned nodes and reads its ghost nodes, so
+// only those travel.  Host arrays keep the full 3n layout: entries of nodes this rank does not own are left untouched by
+// the download (a caller merges the ranks' results by admm_b200_mgpu_nodes / Solver::node_owner()).
+void upload_state_local(S *s, const double *x, const double *v)
+{
+	const int nl = (int)s->mg_local.size();
+	if (!nl) return;
+	double *hx = s->mg_pinned, *hv = s->mg_pinned + 3 * (size_t)nl;
+	for (int i = 0; i < nl; ++i) {
+		const size_t g = 3 * (size_t)s->mg_local[i];
+		hx[3 * i] = x[g]; hx[3 * i + 1] = x[g + 1]; hx[3 * i + 2] = x[g + 2];
+		hv[3 * i] = v[g]; hv[3 * i + 1] = v[g + 1]; hv[3 * i + 2] = v[g + 2];
+	}
+	CK(cudaMemcpyAsync(s->stage3.p, s->mg_pinned, sizeof(double) * 6 * nl, cudaMemcpyHostToDevice, s->stream));
+	scatter3_to4_kernel<<<(nl + 255) / 256, 256, 0, s->stream>>>(nl, s->d_mg_local.p, s->stage3.p, s->x.p);
+	scatter3_to4_kernel<<<(nl + 255) / 256, 256, 0, s->stream>>>(nl, s->d_mg_local.p, s->stage3.p + 3 * (size_t)nl, s->v.p);
+	CK(cudaGetLastError());
+	s->launches += 2;
+}
+void download_state_local(S *s, double *x, double *v)
+{
+	const int no = (int)s->mg_owned.size();
+	if (!no) return;
+	gather4_to3_kernel<<<(no + 255) / 256, 256, 0, s->stream>>>(no, s->d_mg_owned.p, s->x.p, s->stage3.p);
+	gather4_to3_kernel<<<(no + 255) / 256, 256, 0, s->stream>>>(no, s->d_mg_owned.p, s->v.p, s->stage3.p + 3 * (size_t)no);
+	CK(cudaGetLastError());
+	s->launches += 2;
+	CK(cudaMemcpyAsync(s->mg_pinned, s->stage3.p, sizeof(double) * 6 * no, cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	const double *hx = s->mg_pinned, *hv = s->mg_pinned + 3 * (size_t)no;
+	for (int i = 0; i < no; ++i) {
+		const size_t g = 3 * (size_t)s->mg_owned[i];
+		x[g] = hx[3 * i]; x[g + 1] = hx[3 * i + 1]; x[g + 2] = hx[3 * i + 2];
+		v[g] = hv[3 * i]; v[g + 1] = hv[3 * i + 1]; v[g + 2] = hv[3 * i + 2];
+	}
+}
+
 void upload_state(S *s, const double *x, const double *v)
 {
 	const int n = s->n_nodes;
@@ -1335,7 +1404,7 @@ int admm_b200_set_nodes(admm_b200_solver *s, int n_nodes, const double *x, const
 		s->h_m.assign(m, m + (size_t)3 * n_nodes);
 		s->h_x0.assign(x, x + (size_t)3 * n_nodes);
 		s->x.alloc(n_nodes); s->v.alloc(n_nodes); s->cx.alloc(n_nodes); s->mxbar.alloc(n_nodes); s->b.alloc(n_nodes); s->m.alloc(n_nodes);
-		s->stage3.alloc((size_t)3 * n_nodes); s->stage3b.alloc(std::max<size_t>((size_t)3 * n_nodes, 4096));
+		s->stage3.alloc((size_t)6 * n_nodes); s->stage3b.alloc(std::max<size_t>((size_t)3 * n_nodes, 4096));
 		s->v.zero(s->stream); s->b.zero(s->stream); s->mxbar.zero(s->stream);
 		upload_state(s, x, v);
 		CK(cudaStreamSynchronize(s->stream));
@@ -1490,6 +1559,14 @@ int admm_b200_set_rank(admm_b200_solver *s, int rank, int world)
 
 int admm_b200_device_sms(const admm_b200_solver *s) { return s ? s->n_sms : 0; }
 
+int admm_b200_mgpu_nodes(const admm_b200_solver *s, int *n_owned, int *n_ghost)
+{
+	if (!s) return 1;
+	if (n_owned) *n_owned = s->world > 1 ? (int)s->mg_owned.size() : s->n_nodes;
+	if (n_ghost) *n_ghost = s->world > 1 ? (int)(s->mg_local.size() - s->mg_owned.size()) : 0;
+	return 0;
+}
+
 int admm_b200_gs_parts(const admm_b200_solver *s) { return s ? s->gs_parts : 0; }
 
 int admm_b200_set_gs_parts(admm_b200_solver *s, int n_parts)
@@ -1611,12 +1688,20 @@ int admm_b200_step(admm_b200_solver *s, int admm_iters, double gravity, admm_b20
 
 int admm_b200_upload_state(admm_b200_solver *s, const double *x, const double *v)
 {
-	return guard(s, [&]() { require(s->n_nodes > 0, "no nodes"); upload_state(s, x, v); CK(cudaStreamSynchronize(s->stream)); });
+	return guard(s, [&]() {
+		require(s->n_nodes > 0, "no nodes");
+		if (s->world > 1 && s->finalized && x && v && !s->mg_local.empty()) upload_state_local(s, x, v); else upload_state(s, x, v);
+		CK(cudaStreamSynchronize(s->stream));
+	});
 }
 
 int admm_b200_download_state(admm_b200_solver *s, double *x, double *v)
 {
-	return guard(s, [&]() { require(s->n_nodes > 0, "no nodes"); download_state(s, x, v); });
+	return guard(s, [&]() {
+		require(s->n_nodes > 0, "no nodes");
+		// several ranks: only the nodes this rank owns are written (the rest of the device arrays carries no elastic forces)
+		if (s->world > 1 && s->finalized && x && v && !s->mg_owned.empty()) download_state_local(s, x, v); else download_state(s, x, v);
+	});
 }
 
 int admm_b200_pin_host(admm_b200_solver *s, void *ptr, unsigned long long bytes)
@@ -1636,6 +1721,12 @@ int admm_b200_step_host(admm_b200_solver *s, int admm_iters, double gravity, dou
 {
 	return guard(s, [&]() {
 		require(x && v, "step_host: null state");
+		if (s->world > 1 && !s->mg_local.empty()) {
+			upload_state_local(s, x, v);
+			do_step(s, admm_iters, gravity, runtime);
+			download_state_local(s, x, v);
+			return;
+		}
 		upload_state(s, x, v);
 		do_step(s, admm_iters, gravity, runtime);
 		download_state(s, x, v);

@@ -359,6 +359,9 @@ public:
 	void mgpu_import(int peer_rank, const void *blob) { check(admm_b200_mgpu_import(handle, peer_rank, blob), "mgpu_import"); }
 	void mgpu_ready() { check(admm_b200_mgpu_ready(handle), "mgpu_ready"); }
 	const std::vector<int> &node_owner() const { return m_node_owner; } // rank owning each node (empty when world == 1)
+	// With several ranks step() moves only this rank's nodes: owned + ghost nodes up, owned nodes down.  m_x / m_v entries of
+	// nodes owned by other ranks are left as they were: merge the ranks' arrays by node_owner().
+	void mgpu_nodes(int &n_owned, int &n_ghost) { check(admm_b200_mgpu_nodes(handle, &n_owned, &n_ghost), "mgpu_nodes"); }
 	const sparse::Csr &system_matrix() const { return scalarL; }
 	const std::vector<std::vector<int>> &colors() const { return m_colors; }
 	int n_reduction_rows() const { return n_D_rows; }
@@ -541,7 +544,7 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 	const int world = device_options.world, rank = device_options.rank;
 	if (world > 1) {
 		if (m_settings.linsolver != 1) throw std::runtime_error("**admm_b200::Solver Error: multi-GPU needs the NodalMultiColorGS solver (-ls 1)");
-		if (!rgroups.empty() || !p_idx.empty()) throw std::runtime_error("**admm_b200::Solver Error: multi-GPU supports tet meshes only");
+		if (!p_idx.empty()) throw std::runtime_error("**admm_b200::Solver Error: multi-GPU has no energy-based pins (they belong to LDLT / UzawaCG)");
 		check(admm_b200_set_rank(handle, rank, world), "set_rank");
 		const int sms = admm_b200_gs_parts(handle);
 		std::vector<int> part(n_nodes);
@@ -563,9 +566,23 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 			}
 			g.idx.resize(4 * keep); g.dminv.resize(9 * keep); g.w.resize(keep); g.row.resize(keep);
 		}
+		for (auto &g : rgroups) {
+			size_t keep = 0;
+			const size_t n_e = g.w.size();
+			for (size_t e = 0; e < n_e; ++e) {
+				bool mine = false;
+				for (int c = 0; c < 3; ++c) mine = mine || m_node_owner[g.idx[3 * e + c]] == rank;
+				if (!mine) continue;
+				for (int c = 0; c < 3; ++c) g.idx[3 * keep + c] = g.idx[3 * e + c];
+				for (int k = 0; k < 4; ++k) g.rest[4 * keep + k] = g.rest[4 * e + k];
+				g.w[keep] = g.w[e]; g.row[keep] = g.row[e];
+				++keep;
+			}
+			g.idx.resize(3 * keep); g.rest.resize(4 * keep); g.w.resize(keep); g.row.resize(keep);
+		}
 	}
 	for (auto &g : tgroups) if (!g.w.empty()) check(admm_b200_add_tets(handle, (int)g.w.size(), g.idx.data(), g.dminv.data(), g.w.data(), g.model, g.mu, g.lambda, g.kappa, g.row.data()), "add_tets");
-	for (auto &g : rgroups) check(admm_b200_add_tris(handle, (int)g.w.size(), g.idx.data(), g.rest.data(), g.w.data(), g.lmin, g.lmax, g.row.data()), "add_tris");
+	for (auto &g : rgroups) if (!g.w.empty()) check(admm_b200_add_tris(handle, (int)g.w.size(), g.idx.data(), g.rest.data(), g.w.data(), g.lmin, g.lmax, g.row.data()), "add_tris");
 	if (!p_idx.empty()) check(admm_b200_add_pins(handle, (int)p_idx.size(), p_idx.data(), p_pos.data(), p_w.data(), p_row.data()), "add_pins");
 
 	for (auto &o : passive_objs) { double p[4]; o->params(p); check(admm_b200_add_obstacle(handle, o->kind(), p), "add_obstacle"); }

@@ -93,6 +93,7 @@ int admmhost_set_rank(void *h_, int rank, int world) {
 int admmhost_mgpu_export(void *h_, void *blob) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.mgpu_export(blob); }); }
 int admmhost_mgpu_import(void *h_, int peer, const void *blob) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.mgpu_import(peer, blob); }); }
 int admmhost_mgpu_ready(void *h_) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.mgpu_ready(); }); }
+int admmhost_mgpu_nodes(void *h_, int *out2) { Host *h = (Host *)h_; return guarded(h, [&]() { h->solver.mgpu_nodes(out2[0], out2[1]); }); }
 int admmhost_get_node_owner(void *h_, int *out) {
 	const std::vector<int> &o = ((Host *)h_)->solver.node_owner();
 	for (size_t i = 0; i < o.size(); ++i) out[i] = o[i];

@@ -353,6 +353,7 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
     sol, init_s = build_solver(pkg, args, scene, local_rank, stream, rank, world)
     n_el, n_verts = len(scene["elems"]), len(scene["verts"])
     n_el_rank, n_verts_rank, owner = n_el, n_verts, None
+    n_owned, n_ghost = n_verts, 0
     if world > 1:
         def all_gather_bytes(b):
             out = [None] * world
@@ -362,6 +363,8 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
         owner = sol.node_owner()
         n_el_rank = int((owner[scene["elems"]] == rank).any(axis=1).sum())   # cut elements are computed on both sides
         n_verts_rank = int((owner == rank).sum())
+        n_owned, n_ghost = sol.mgpu_nodes()
+        assert n_owned == n_verts_rank
     sol.set_x(scene["x0"].ravel())
     dev = sol.device()
     rp, _, _ = sol.system_matrix()
@@ -416,7 +419,7 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
     clk = clocks.stop() if clocks is not None else None
     x_final = sol.get_x()
     out = dict(ms_res=ms_res, ms_e2e=ms_e2e, acc=acc, launches=launches, clk=clk, x=x_final, owner=owner, init_s=init_s, info=dev.info(),
-               nnz_L=nnz_L, n_colors=n_colors, n_el_rank=n_el_rank, n_verts_rank=n_verts_rank)
+               nnz_L=nnz_L, n_colors=n_colors, n_el_rank=n_el_rank, n_verts_rank=n_verts_rank, h2d=2 * 3 * 8 * (n_owned + n_ghost), d2h=2 * 3 * 8 * n_owned)
     sol.close()
     return out
 
@@ -451,8 +454,8 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     iters = args.admm_iters
     stream = torch.cuda.Stream()
-    if world > 1 and (scene["kind"] != "tet" or args.linsolver != 1 or args.floor):
-        raise SystemExit("bench.py: only the pinned tet beams with the NodalMultiColorGS solve shard over several GPUs (DESIGN.md 7); "
+    if world > 1 and args.linsolver != 1:
+        raise SystemExit("bench.py: only the NodalMultiColorGS solve shards over several GPUs (DESIGN.md 7); "
                          "LDLT / UzawaCG configurations are single-GPU (SURVEY.md 8e: replicas only)")
 
     m = measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W, ClockSampler(local_rank) if rank == 0 else None)
@@ -478,7 +481,12 @@ def run_b200(args):
     # N > 1: ONE mesh sharded over the ranks (strong scaling) -- the job's ADMM iterations, not a sum
     value = iters * K / (ms_res * 1e-3)
     e2e = iters * K / (ms_e2e * 1e-3)
-    state_bytes = 2 * 3 * n_verts * 8
+    # bytes per step of Solver::step(): x and v, owned + ghost nodes up, owned nodes down, summed over the ranks
+    h2d_bytes, d2h_bytes = m["h2d"], m["d2h"]
+    if world > 1:
+        t = torch.tensor([float(h2d_bytes), float(d2h_bytes)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_bytes, d2h_bytes = int(t[0].item()), int(t[1].item())
 
     # ---- roofline: algorithmic bytes / CUDA-event durations from the timed region ----
     peak, peak_src = measured_peaks()
@@ -547,7 +555,7 @@ def run_b200(args):
                     "multi_gpu": ("one mesh sharded by node ownership over %d ranks; cut elements computed on both sides; neighbour values and solved cut positions pushed into peer memory by the solve kernel (CUDA IPC over NVLink), no NCCL call in the data path" % world) if world > 1 else "single GPU",
                     "n_elements_this_rank": n_el_rank, "n_verts_this_rank": n_verts_rank, "init_s": m["init_s"], "global_solve_kernel": info},
         "elem_prox_per_s": n_el / (acc["local_ms"] / n_launch * 1e-3),  # whole local phase (kernel + helpers), all ranks' elements
-        "e2e": {"value": e2e, "unit": "ADMM iters/s", "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
+        "e2e": {"value": e2e, "unit": "ADMM iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / K, "api": "admm_b200::Solver::step() -> admm_b200_step_host"},
         "gpu_launches": int(m["launches"]),
         "roofline": roofline, "kernels": kernels,

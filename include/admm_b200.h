@@ -201,7 +201,9 @@ long long admm_b200_launch_count( const admm_b200_solver *s );
  * values inside the Gauss-Seidel sweeps and the solved positions of cut nodes -- is done by the solve
  * kernel itself with stores into the peers' memory (CUDA IPC mappings of their buffers); the 256-byte
  * blobs are moved between the processes by the caller (e.g. torch.distributed.all_gather).
- * Restrictions: NodalMultiColorGS, precision FP32, the reference's convergence test is off. */
+ * Restrictions: NodalMultiColorGS, precision FP32; the reference's convergence test (which never fires)
+ * is off, the sweep count is returned.  admm_b200_step_host / _upload_state / _download_state move only this rank's
+ * nodes (see admm_b200_mgpu_nodes). */
 #define ADMM_B200_IPC_BYTES 256
 int admm_b200_set_rank( admm_b200_solver *s, int rank, int world );                /* before finalize */
 int admm_b200_device_sms( const admm_b200_solver *s );
@@ -212,6 +214,10 @@ int admm_b200_device_sms( const admm_b200_solver *s );
 int admm_b200_set_gs_parts( admm_b200_solver *s, int n_parts );
 int admm_b200_gs_parts( const admm_b200_solver *s );
 int admm_b200_plan_parts( int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, int n_parts, int *part_of );
+/* After finalize: how many nodes this rank owns and how many it reads from other ranks (ghosts).  With several ranks
+ * admm_b200_step_host moves only those: owned + ghost nodes host -> device, owned nodes device -> host; the entries of the
+ * caller's x / v arrays that belong to nodes of other ranks are left untouched (merge the ranks' arrays by owner). */
+int admm_b200_mgpu_nodes( const admm_b200_solver *s, int *n_owned, int *n_ghost );
 int admm_b200_mgpu_export( admm_b200_solver *s, void *blob );                      /* after finalize */
 int admm_b200_mgpu_import( admm_b200_solver *s, int peer_rank, const void *blob );
 int admm_b200_mgpu_ready( admm_b200_solver *s );

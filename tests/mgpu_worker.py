@@ -82,35 +82,58 @@ def main():
         if rank == 0:
             print(json.dumps({"ok": True, "elements_per_rank": counts, "duplicated_fraction": dup, "ghosts": [int(a[1].sum()) for a in allr]}))
     elif mode == "step":
+        # variants: beam (pinned cantilever), floor (StVK beam dropped on a Floor handled inside the sweep, no pins),
+        # cloth (triangles + Gauss-Seidel pins): each sharded over the ranks and compared with a single-GPU run
         torch.cuda.set_device(rank)
-        dims = tuple(int(a) for a in sys.argv[2:5]) if len(sys.argv) >= 5 else (48, 6, 6)
-        scene = scenes.beam(pkg.meshes, *dims)
-        x0 = scenes.bend(scene[0]).ravel()
+        variant = sys.argv[2] if len(sys.argv) >= 3 else "beam"
+        if variant == "cloth":
+            scene = scenes.cloth(pkg.meshes, 40)
+            x0 = scene[0].ravel().copy()
+        else:
+            scene = scenes.beam(pkg.meshes, 48, 6, 6)
+            x0 = scenes.bend(scene[0]).ravel()
+        floor_y = float(scene[0][:, 1].min() - 0.03)
 
         def build(r, w):
             s = pkg.Solver()
             s.set_options(device=rank, precision=pkg.FP32, timers=False)
             if w > 1:
                 s.set_rank(r, w)
-            scenes.build_tet_scene(s, scene, 1, linsolver=1, iters=8)
+            if variant == "cloth":
+                s.add_nodes(scene[0], scene[2])
+                s.add_tris(scene[0], scene[1], 100.0 / 2.2, 100.0 * 0.1 / (1.1 * 0.8), 0.95, 1.05)
+                s.set_pins(scene[3])
+                assert s.initialize(dt=1.0 / 24, admm_iters=8, gravity=-9.8, linsolver=1)
+            elif variant == "floor":
+                scenes.build_tet_scene(s, scene, 2, linsolver=1, iters=8, floor=floor_y, pin=False)
+            else:
+                scenes.build_tet_scene(s, scene, 1, linsolver=1, iters=8)
             return s
 
+        n_steps = 6 if variant == "floor" else 3
         s = build(rank, world)
         s.mgpu_connect(all_gather)
         s.set_x(x0)
-        for _ in range(3):
+        for _ in range(n_steps):
             s.step()
         owner = s.node_owner()
+        n_owned, n_ghost = s.mgpu_nodes()
+        assert n_owned == int((owner == rank).sum()) and 0 < n_ghost < len(owner)
         x = s.get_x().reshape(-1, 3)
+        # step() moves only this rank's nodes: what it does not own still holds the start values
+        assert (x[owner != rank] == x0.reshape(-1, 3)[owner != rank]).all()
         xm = torch.from_numpy(np.where((owner == rank)[:, None], x, 0.0))
         dist.all_reduce(xm)
         if rank == 0:
             ref = build(0, 1)
             ref.set_x(x0)
-            for _ in range(3):
+            for _ in range(n_steps):
                 ref.step()
-            err = float(np.abs(ref.get_x().reshape(-1, 3) - xm.numpy()).max())
-            print(json.dumps({"ok": bool(err < 2e-6), "err": err, "n_nodes": int(len(owner)), "owned": [int((owner == r).sum()) for r in range(world)]}))
+            xr = ref.get_x().reshape(-1, 3)
+            err = float(np.abs(xr - xm.numpy()).max())
+            landed = bool(variant != "floor" or np.abs(xr[:, 1] - floor_y).min() < 1e-9)
+            print(json.dumps({"ok": bool(err < 2e-6 and landed), "err": err, "variant": variant, "landed": landed, "n_nodes": int(len(owner)),
+                              "owned": [int((owner == r).sum()) for r in range(world)], "info": s.device().info()}))
     dist.barrier()
     dist.destroy_process_group()
 

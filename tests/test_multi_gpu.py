@@ -44,9 +44,14 @@ def test_exchange_plans_fit_together(pkg, world):
 
 
 @pytest.mark.gpu
-def test_sharded_steps_match_single_gpu(pkg):
+@pytest.mark.parametrize("variant", ["beam", "floor", "cloth"])
+def test_sharded_steps_match_single_gpu(pkg, variant):
+    """A scene sharded over 2 ranks reproduces the single-GPU positions: pinned Neo-Hookean beam; StVK beam dropped on a
+    Floor handled inside the sweep (no pins); cloth (triangles) with Gauss-Seidel pins.  step() moves only each rank's own
+    (+ ghost) nodes."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    res = launch(2, ["step"])
+    res = launch(2, ["step", variant])
+    print(json.dumps(res))
     assert res["ok"], res
