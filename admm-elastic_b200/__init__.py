@@ -305,7 +305,7 @@ class Solver(object):
         self._ck(_host.admmhost_mgpu_ready(self.h))
 
     def mgpu_nodes(self):
-        """(owned, ghost) node counts of this rank: what step() moves per step is owned + ghost up, owned down."""
+        """(owned, ghost) node counts of this rank: step() moves owned + ghost nodes up and down."""
         out = (ctypes.c_int * 2)()
         self._ck(_host.admmhost_mgpu_nodes(self.h, out))
         return int(out[0]), int(out[1])

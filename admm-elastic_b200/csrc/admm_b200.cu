@@ -1197,8 +1197,8 @@ __global__ void gather4_to3_kernel(int n, const int *__restrict__ idx, const dou
 }
 
 // Multi-GPU variants of upload_state / download_state: a rank computes on its owned nodes and reads its ghost nodes, so
-// only those travel.  Host arrays keep the full 3n layout: entries of nodes this rank does not own are left untouched by
-// the download (a caller merges the ranks' results by admm_b200_mgpu_nodes / Solver::node_owner()).
+// only those travel, in both directions.  Host arrays keep the full 3n layout: entries of nodes this rank neither owns nor
+// reads are left untouched (a caller merges the ranks' results by Solver::node_owner()).
 void upload_state_local(S *s, const double *x, const double *v)
 {
 	const int nl = (int)s->mg_local.size();
@@ -1217,17 +1217,19 @@ void upload_state_local(S *s, const double *x, const double *v)
 }
 void download_state_local(S *s, double *x, double *v)
 {
-	const int no = (int)s->mg_owned.size();
+	// owned AND ghost nodes come back: the next upload sends the ghosts up again, so the host must hold the values the
+	// owners pushed into this rank's arrays at the end of the solve (they equal the owners' own values)
+	const int no = (int)s->mg_local.size();
 	if (!no) return;
-	gather4_to3_kernel<<<(no + 255) / 256, 256, 0, s->stream>>>(no, s->d_mg_owned.p, s->x.p, s->stage3.p);
-	gather4_to3_kernel<<<(no + 255) / 256, 256, 0, s->stream>>>(no, s->d_mg_owned.p, s->v.p, s->stage3.p + 3 * (size_t)no);
+	gather4_to3_kernel<<<(no + 255) / 256, 256, 0, s->stream>>>(no, s->d_mg_local.p, s->x.p, s->stage3.p);
+	gather4_to3_kernel<<<(no + 255) / 256, 256, 0, s->stream>>>(no, s->d_mg_local.p, s->v.p, s->stage3.p + 3 * (size_t)no);
 	CK(cudaGetLastError());
 	s->launches += 2;
 	CK(cudaMemcpyAsync(s->mg_pinned, s->stage3.p, sizeof(double) * 6 * no, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	const double *hx = s->mg_pinned, *hv = s->mg_pinned + 3 * (size_t)no;
 	for (int i = 0; i < no; ++i) {
-		const size_t g = 3 * (size_t)s->mg_owned[i];
+		const size_t g = 3 * (size_t)s->mg_local[i];
 		x[g] = hx[3 * i]; x[g + 1] = hx[3 * i + 1]; x[g + 2] = hx[3 * i + 2];
 		v[g] = hv[3 * i]; v[g + 1] = hv[3 * i + 1]; v[g + 2] = hv[3 * i + 2];
 	}
@@ -1700,7 +1702,7 @@ int admm_b200_download_state(admm_b200_solver *s, double *x, double *v)
 	return guard(s, [&]() {
 		require(s->n_nodes > 0, "no nodes");
 		// several ranks: only the nodes this rank owns are written (the rest of the device arrays carries no elastic forces)
-		if (s->world > 1 && s->finalized && x && v && !s->mg_owned.empty()) download_state_local(s, x, v); else download_state(s, x, v);
+		if (s->world > 1 && s->finalized && x && v && !s->mg_local.empty()) download_state_local(s, x, v); else download_state(s, x, v);
 	});
 }
 

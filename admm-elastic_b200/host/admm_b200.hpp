@@ -359,8 +359,8 @@ public:
 	void mgpu_import(int peer_rank, const void *blob) { check(admm_b200_mgpu_import(handle, peer_rank, blob), "mgpu_import"); }
 	void mgpu_ready() { check(admm_b200_mgpu_ready(handle), "mgpu_ready"); }
 	const std::vector<int> &node_owner() const { return m_node_owner; } // rank owning each node (empty when world == 1)
-	// With several ranks step() moves only this rank's nodes: owned + ghost nodes up, owned nodes down.  m_x / m_v entries of
-	// nodes owned by other ranks are left as they were: merge the ranks' arrays by node_owner().
+	// With several ranks step() moves only this rank's nodes (owned + ghost) up and down.  m_x / m_v entries of all other
+	// nodes are left as they were: merge the ranks' arrays by node_owner().
 	void mgpu_nodes(int &n_owned, int &n_ghost) { check(admm_b200_mgpu_nodes(handle, &n_owned, &n_ghost), "mgpu_nodes"); }
 	const sparse::Csr &system_matrix() const { return scalarL; }
 	const std::vector<std::vector<int>> &colors() const { return m_colors; }

@@ -419,7 +419,7 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
     clk = clocks.stop() if clocks is not None else None
     x_final = sol.get_x()
     out = dict(ms_res=ms_res, ms_e2e=ms_e2e, acc=acc, launches=launches, clk=clk, x=x_final, owner=owner, init_s=init_s, info=dev.info(),
-               nnz_L=nnz_L, n_colors=n_colors, n_el_rank=n_el_rank, n_verts_rank=n_verts_rank, h2d=2 * 3 * 8 * (n_owned + n_ghost), d2h=2 * 3 * 8 * n_owned)
+               nnz_L=nnz_L, n_colors=n_colors, n_el_rank=n_el_rank, n_verts_rank=n_verts_rank, h2d=2 * 3 * 8 * (n_owned + n_ghost), d2h=2 * 3 * 8 * (n_owned + n_ghost))
     sol.close()
     return out
 
@@ -481,7 +481,7 @@ def run_b200(args):
     # N > 1: ONE mesh sharded over the ranks (strong scaling) -- the job's ADMM iterations, not a sum
     value = iters * K / (ms_res * 1e-3)
     e2e = iters * K / (ms_e2e * 1e-3)
-    # bytes per step of Solver::step(): x and v, owned + ghost nodes up, owned nodes down, summed over the ranks
+    # bytes per step of Solver::step(): x and v of every rank's owned + ghost nodes, up and down, summed over the ranks
     h2d_bytes, d2h_bytes = m["h2d"], m["d2h"]
     if world > 1:
         t = torch.tensor([float(h2d_bytes), float(d2h_bytes)], device="cuda", dtype=torch.float64)

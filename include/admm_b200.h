@@ -215,8 +215,8 @@ int admm_b200_set_gs_parts( admm_b200_solver *s, int n_parts );
 int admm_b200_gs_parts( const admm_b200_solver *s );
 int admm_b200_plan_parts( int n, const int *rowptr, const int *cols, const double *vals, const double *pos3, int n_parts, int *part_of );
 /* After finalize: how many nodes this rank owns and how many it reads from other ranks (ghosts).  With several ranks
- * admm_b200_step_host moves only those: owned + ghost nodes host -> device, owned nodes device -> host; the entries of the
- * caller's x / v arrays that belong to nodes of other ranks are left untouched (merge the ranks' arrays by owner). */
+ * admm_b200_step_host moves only those, in both directions (a ghost's value is the copy its owner pushed); the entries of
+ * the caller's x / v arrays of all other nodes are left untouched (merge the ranks' arrays by owner). */
 int admm_b200_mgpu_nodes( const admm_b200_solver *s, int *n_owned, int *n_ghost );
 int admm_b200_mgpu_export( admm_b200_solver *s, void *blob );                      /* after finalize */
 int admm_b200_mgpu_import( admm_b200_solver *s, int peer_rank, const void *blob );
