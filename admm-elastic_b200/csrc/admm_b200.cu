@@ -180,6 +180,7 @@ struct admm_b200_solver {
 	std::vector<void *> ipc_opened;
 	// multi-GPU step_host: only the nodes this rank touches travel -- owned + ghost nodes up, owned nodes down
 	std::vector<int> mg_local, mg_owned;     // node ids, ascending
+	std::vector<int> mg_runs;                // mg_local as runs of consecutive ids: {first id, length, offset in mg_local} x n_runs
 	DevBuf<int> d_mg_local, d_mg_owned;
 	double *mg_pinned = nullptr;             // pinned host staging: [x local | v local]
 	bool mg_ready = false;
@@ -797,6 +798,13 @@ void build_mcgs_resident(S *s)
 		}
 		s->mg_local.clear(); s->mg_owned.clear();
 		for (int i = 0; i < s->n_nodes; ++i) { if (loc[i]) s->mg_local.push_back(i); if (loc[i] == 1) s->mg_owned.push_back(i); }
+		s->mg_runs.clear();
+		for (size_t i = 0; i < s->mg_local.size();) {
+			size_t j = i + 1;
+			while (j < s->mg_local.size() && s->mg_local[j] == s->mg_local[j - 1] + 1) ++j;
+			s->mg_runs.push_back(s->mg_local[i]); s->mg_runs.push_back((int)(j - i)); s->mg_runs.push_back((int)i);
+			i = j;
+		}
 		s->d_mg_local.upload(s->mg_local.empty() ? std::vector<int>(1, 0) : s->mg_local, s->stream);
 		s->d_mg_owned.upload(s->mg_owned.empty() ? std::vector<int>(1, 0) : s->mg_owned, s->stream);
 		if (s->mg_pinned) { cudaFreeHost(s->mg_pinned); s->mg_pinned = nullptr; }
@@ -1203,13 +1211,22 @@ void upload_state_local(S *s, const double *x, const double *v)
 {
 	const int nl = (int)s->mg_local.size();
 	if (!nl) return;
-	double *hx = s->mg_pinned, *hv = s->mg_pinned + 3 * (size_t)nl;
-	for (int i = 0; i < nl; ++i) {
-		const size_t g = 3 * (size_t)s->mg_local[i];
-		hx[3 * i] = x[g]; hx[3 * i + 1] = x[g + 1]; hx[3 * i + 2] = x[g + 2];
-		hv[3 * i] = v[g]; hv[3 * i + 1] = v[g + 1]; hv[3 * i + 2] = v[g + 2];
+	if (s->mg_runs.size() <= 3 * 64) {
+		// a spatially compact rank of a mesh numbered along an axis is a handful of id ranges: copy them where they lie
+		for (size_t r = 0; r < s->mg_runs.size(); r += 3) {
+			const size_t first = (size_t)s->mg_runs[r], len = (size_t)s->mg_runs[r + 1], off = (size_t)s->mg_runs[r + 2];
+			CK(cudaMemcpyAsync(s->stage3.p + 3 * off, x + 3 * first, sizeof(double) * 3 * len, cudaMemcpyHostToDevice, s->stream));
+			CK(cudaMemcpyAsync(s->stage3.p + 3 * ((size_t)nl + off), v + 3 * first, sizeof(double) * 3 * len, cudaMemcpyHostToDevice, s->stream));
+		}
+	} else {
+		double *hx = s->mg_pinned, *hv = s->mg_pinned + 3 * (size_t)nl;
+		for (int i = 0; i < nl; ++i) {
+			const size_t g = 3 * (size_t)s->mg_local[i];
+			hx[3 * i] = x[g]; hx[3 * i + 1] = x[g + 1]; hx[3 * i + 2] = x[g + 2];
+			hv[3 * i] = v[g]; hv[3 * i + 1] = v[g + 1]; hv[3 * i + 2] = v[g + 2];
+		}
+		CK(cudaMemcpyAsync(s->stage3.p, s->mg_pinned, sizeof(double) * 6 * nl, cudaMemcpyHostToDevice, s->stream));
 	}
-	CK(cudaMemcpyAsync(s->stage3.p, s->mg_pinned, sizeof(double) * 6 * nl, cudaMemcpyHostToDevice, s->stream));
 	scatter3_to4_kernel<<<(nl + 255) / 256, 256, 0, s->stream>>>(nl, s->d_mg_local.p, s->stage3.p, s->x.p);
 	scatter3_to4_kernel<<<(nl + 255) / 256, 256, 0, s->stream>>>(nl, s->d_mg_local.p, s->stage3.p + 3 * (size_t)nl, s->v.p);
 	CK(cudaGetLastError());
@@ -1225,6 +1242,15 @@ void download_state_local(S *s, double *x, double *v)
 	gather4_to3_kernel<<<(no + 255) / 256, 256, 0, s->stream>>>(no, s->d_mg_local.p, s->v.p, s->stage3.p + 3 * (size_t)no);
 	CK(cudaGetLastError());
 	s->launches += 2;
+	if (s->mg_runs.size() <= 3 * 64) {
+		for (size_t r = 0; r < s->mg_runs.size(); r += 3) {
+			const size_t first = (size_t)s->mg_runs[r], len = (size_t)s->mg_runs[r + 1], off = (size_t)s->mg_runs[r + 2];
+			CK(cudaMemcpyAsync(x + 3 * first, s->stage3.p + 3 * off, sizeof(double) * 3 * len, cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaMemcpyAsync(v + 3 * first, s->stage3.p + 3 * ((size_t)no + off), sizeof(double) * 3 * len, cudaMemcpyDeviceToHost, s->stream));
+		}
+		CK(cudaStreamSynchronize(s->stream));
+		return;
+	}
 	CK(cudaMemcpyAsync(s->mg_pinned, s->stage3.p, sizeof(double) * 6 * no, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	const double *hx = s->mg_pinned, *hv = s->mg_pinned + 3 * (size_t)no;
