@@ -121,11 +121,11 @@ class DeviceSolver(object):
         v = _f64(v).ravel() if v is not None else None
         self._ck(_cuda.admm_b200_set_nodes(self.h, x.size // 3, _dp(x), _dp(v), _dp(m)))
 
-    def add_tets(self, idx, dminv, weight, model, mu, lam, kappa=0.0, row_offset=None):
+    def add_tets(self, idx, dminv, weight, model, mu, lam, kappa=0.0, row_offset=None, bulk_modulus=0.0):
         idx, dminv, weight = _i32(idx).ravel(), _f64(dminv).ravel(), _f64(weight).ravel()
         ro = _i32(row_offset).ravel() if row_offset is not None else None
         self._ck(_cuda.admm_b200_add_tets(self.h, weight.size, _ip(idx), _dp(dminv), _dp(weight), int(model),
-                                          ctypes.c_double(mu), ctypes.c_double(lam), ctypes.c_double(kappa), _ip(ro)))
+                                          ctypes.c_double(mu), ctypes.c_double(lam), ctypes.c_double(kappa), ctypes.c_double(bulk_modulus), _ip(ro)))
 
     def set_system(self, rowptr, cols, vals):
         rowptr, cols, vals = _i32(rowptr), _i32(cols), _f64(vals)
@@ -167,11 +167,12 @@ class DeviceSolver(object):
         self._ck(_cuda.admm_b200_download_state(self.h, _dp(x), _dp(v)))
         return x, v
 
-    def prox_tets(self, model, mu, lam, z, kappa=0.0, precision=FP32):
+    def prox_tets(self, model, mu, lam, z, kappa=0.0, precision=FP32, bulk_modulus=0.0):
+        """bulk_modulus: K of the prox penalty (the element's Lame); 0 = lambda + 2/3 mu of the model constants."""
         z = _f64(z).reshape(-1, 9)
         out = np.empty_like(z)
         self._ck(_cuda.admm_b200_prox_tets(self.h, int(model), ctypes.c_double(mu), ctypes.c_double(lam),
-                                           ctypes.c_double(kappa), int(precision), z.shape[0], _dp(z), _dp(out)))
+                                           ctypes.c_double(kappa), ctypes.c_double(bulk_modulus), int(precision), z.shape[0], _dp(z), _dp(out)))
         return out
 
     def prox_tris(self, z, limit_min=-100.0, limit_max=100.0, precision=FP32):
@@ -264,6 +265,13 @@ class Solver(object):
         self._ck(_host.admmhost_add_tets(self.h, _dp(verts), _ip(inds), inds.size // 4, int(model),
                                          ctypes.c_double(mu), ctypes.c_double(lam), ctypes.c_double(kappa), int(vertex_offset)))
 
+    def add_spline_tets(self, verts, inds, spline_type, mu, lam, spline, vertex_offset=0):
+        """SplineTet(tet, verts, Lame(mu, lam), spline) with spline = (mu, lambda, kappa) of its own
+        (src/TetEnergyTerm.hpp:200-205); spline_type 0 NeoHookean, 1 StVK, 2 CoRotated."""
+        verts, inds = _f64(verts).ravel(), _i32(inds).ravel()
+        self._ck(_host.admmhost_add_spline_tets(self.h, _dp(verts), _ip(inds), inds.size // 4, int(spline_type), ctypes.c_double(mu), ctypes.c_double(lam),
+                                                ctypes.c_double(spline[0]), ctypes.c_double(spline[1]), ctypes.c_double(spline[2]), int(vertex_offset)))
+
     def add_tris(self, verts, inds, mu, lam, limit_min=-100.0, limit_max=100.0, vertex_offset=0):
         verts, inds = _f64(verts).ravel(), _i32(inds).ravel()
         self._ck(_host.admmhost_add_tris(self.h, _dp(verts), _ip(inds), inds.size // 3, ctypes.c_double(mu),
@@ -280,6 +288,11 @@ class Solver(object):
     def add_sphere(self, center, radius):
         c = _f64(center)
         self._ck(_host.admmhost_add_sphere(self.h, _dp(c), ctypes.c_double(radius)))
+
+    def set_surface_inds(self, inds):
+        """Solver::surface_inds: the vertices UzawaCG's collision detection tests, in that order (empty: all nodes)."""
+        inds = _i32(inds).ravel()
+        _host.admmhost_set_surface_inds(self.h, _ip(inds), inds.size)
 
     def set_options(self, **kw):
         for k in kw:

@@ -6,6 +6,7 @@
 #include "ldlt_blocks.hpp"
 #include "sptrsv_blocks.cuh"
 #include "uzawa.cuh"
+#include "uzawa_blocks.cuh"
 #include "mcgs_resident.cuh"
 #include "mcgs_resident_f32.cuh"
 #include "mcgs_owned_f32.cuh"
@@ -58,7 +59,7 @@ inline int pad32(int n) { return (n + 31) & ~31; }
 
 struct TetBatchH {
 	int n = 0, n_pad = 0, model = 0;
-	double mu = 0, lambda = 0, kappa = 0;
+	double mu = 0, lambda = 0, kappa = 0, bulk = 0; // bulk: K of the prox penalty (<= 0: from mu, lambda)
 	std::vector<int> idx;      // 4n
 	std::vector<double> dminv; // 9n
 	std::vector<double> w;     // n
@@ -139,6 +140,9 @@ struct admm_b200_solver {
 	// UzawaCG with passive collisions (uzawa.cuh)
 	DevBuf<int> uz_hv, uz_ctl; DevBuf<double> uz_hn, uz_hc, uz_y, uz_r, uz_d, uz_q3, uz_scal; DevBuf<double4> uz_q1, uz_q2;
 	int uz_max_iters = 20; double uz_tol = 1e-10; // src/UzawaCG.hpp:45-46
+	std::vector<int> surface_inds;   // Solver::surface_inds: the vertices Collider::detect tests, in that order (empty: all)
+	double constraint_w = 1.0;       // ConstraintSet::constraint_w of the UzawaCG path (src/Solver.cpp:239,245)
+	DevBuf<int> uz_cand, uz_cta_cnt; DevBuf<double> uz_red;
 	int gs_grid = 0;
 	size_t gs_nnz = 0, gs_ell_entries = 0;
 	// mcgs, shared-memory-resident variant (mcgs_resident.cuh)
@@ -273,7 +277,7 @@ template <typename E, int MODEL> void launch_tet_model(S *s, TetBatchH *t)
 	tb.z = (E *)t->d_z.p;
 	tb.q = (E *)t->d_q.p;
 	tb.f = (typename Vec4<E>::type *)s->f.p + t->slot_base;
-	tb.mat = Material<E>::make(t->mu, t->lambda, t->kappa);
+	tb.mat = Material<E>::make(t->mu, t->lambda, t->kappa, t->bulk);
 	tb.defer_count = t->d_defer.p; tb.defer_list = t->d_defer.p + 1; tb.defer_done = t->d_defer.p + 1 + t->n;
 	const int threads = 128;
 	int blocks = (t->n + threads - 1) / threads;
@@ -568,6 +572,28 @@ void launch_uzawa(S *s)
 	U.n = n; U.n_obstacles = (int)s->obstacles.size(); U.obs = s->d_obstacles.p;
 	U.hv = s->uz_hv.p; U.hn = s->uz_hn.p; U.hc = s->uz_hc.p; U.y = s->uz_y.p; U.r = s->uz_r.p; U.d = s->uz_d.p; U.q3 = s->uz_q3.p;
 	U.ctl = s->uz_ctl.p; U.scal = s->uz_scal.p; U.tol2 = s->uz_tol * s->uz_tol;
+	if (s->ld_blocks) {
+		// one persistent cooperative launch: detection, the conjugate-gradient loop and every A^-1 inside (uzawa_blocks.cuh)
+		UzBlkParams Z;
+		LdltBlkParams &B = Z.L;
+		B.n = s->ld_n; B.n_levels_f = s->lb_levels_f; B.n_levels_b = s->lb_levels_b;
+		B.perm = s->d_ld_perm.p; B.blk_of = s->lb_blk_of.p; B.blk_c0 = s->lb_blk_c0.p; B.inv_off = s->lb_inv_off.p; B.inv = s->lb_inv.p; B.invT = s->lb_invT.p;
+		B.f_lev_ptr = s->lb_f_lev_ptr.p; B.f_rows = s->lb_f_rows.p; B.f_rowptr = s->lb_f_rowptr.p; B.f_cols = s->lb_f_cols.p; B.f_lanes = s->lb_f_lanes.p; B.f_vals = s->lb_f_vals.p;
+		B.b_lev_ptr = s->lb_b_lev_ptr.p; B.b_cols = s->lb_b_cols.p; B.b_colptr = s->lb_b_colptr.p; B.b_rows = s->lb_b_rows.p; B.b_lanes = s->lb_b_lanes.p; B.b_vals = s->lb_b_vals.p;
+		B.D = s->d_ld_D.p; B.t = s->lb_t.p; B.y = s->d_ld_y.p; B.b = nullptr; B.x = nullptr; B.barrier = s->barrier.p; B.active = nullptr;
+		Z.U = U;
+		Z.cand = s->surface_inds.empty() ? nullptr : s->uz_cand.p; Z.n_cand = (int)s->surface_inds.size();
+		Z.ck = std::sqrt(std::max(0.0, s->constraint_w)); Z.max_iters = s->uz_max_iters;
+		Z.x = s->cx.p; Z.b = s->b.p; Z.q1 = s->uz_q1.p; Z.q2 = s->uz_q2.p; Z.cta_cnt = s->uz_cta_cnt.p; Z.red = s->uz_red.p; Z.iters_done = s->gs_iters_done.p;
+		CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
+		void *args[] = {&Z};
+		fine_begin(s, 2);
+		CK(cudaLaunchCooperativeKernel((void *)uzawa_blocks_kernel, dim3(s->ld_grid), dim3(1024), args, 0, s->stream));
+		fine_end(s);
+		s->launches++;
+		return;
+	}
+	require(s->surface_inds.empty() && s->constraint_w == 1.0, "surface_inds / constraint_w need the block UzawaCG kernel (unset ADMM_B200_LDLT_KERNEL=levels)");
 	const int *active = s->uz_ctl.p + 2;
 	// hits at the current iterate (Solver::step, src/Solver.cpp:87-90), then x = A^-1 (b - C^T y) (:83-84)
 	uz_detect_kernel<<<1, 1024, 0, s->stream>>>(U, s->cx.p);
@@ -1052,6 +1078,10 @@ void build_ldlt(S *s)
 		s->uz_hv.alloc(n); s->uz_hn.alloc(3 * (size_t)n); s->uz_hc.alloc(n); s->uz_y.alloc(n); s->uz_r.alloc(n); s->uz_d.alloc(n); s->uz_q3.alloc(n);
 		s->uz_q1.alloc(n); s->uz_q2.alloc(n); s->uz_ctl.alloc(8); s->uz_scal.alloc(2);
 		s->uz_y.zero(s->stream); s->uz_ctl.zero(s->stream); s->uz_scal.zero(s->stream);
+		s->uz_q1.zero(s->stream); // uzawa_blocks.cuh keeps it all zero between its scatters
+		s->uz_cta_cnt.alloc(std::max(s->n_sms, 1)); s->uz_red.alloc(4 * (size_t)std::max(s->n_sms, 1));
+		for (int v : s->surface_inds) require(v >= 0 && v < n, "set_surface_inds: vertex out of range");
+		if (!s->surface_inds.empty()) s->uz_cand.upload(s->surface_inds, s->stream);
 		if (!s->gs_iters_done.p) s->gs_iters_done.alloc(1);
 		s->d_obstacles.upload(s->obstacles, s->stream);
 		CK(cudaStreamSynchronize(s->stream));
@@ -1294,13 +1324,13 @@ void download_state(S *s, double *x, double *v)
 	CK(cudaStreamSynchronize(s->stream));
 }
 
-template <typename E> void prox_tets_impl(S *s, int model, double mu, double lambda, double kappa, int n, const double *z_in, double *z_out)
+template <typename E> void prox_tets_impl(S *s, int model, double mu, double lambda, double kappa, double bulk, int n, const double *z_in, double *z_out)
 {
 	int n_pad = pad32(n);
 	std::vector<E> tmp((size_t)9 * n_pad, E(0));
 	for (int e = 0; e < n; ++e) for (int k = 0; k < 9; ++k) tmp[(size_t)k * n_pad + e] = E(z_in[(size_t)9 * e + k]);
 	DevBuf<E> d; d.upload(tmp, s->stream);
-	Material<E> mat = Material<E>::make(mu, lambda, kappa);
+	Material<E> mat = Material<E>::make(mu, lambda, kappa, bulk);
 	int threads = 128, blocks = (n + threads - 1) / threads;
 	DevBuf<int> defer; defer.alloc((size_t)n + 1); defer.zero(s->stream);
 #define ADMMB200_PROX_ONLY(M) \
@@ -1444,7 +1474,7 @@ int admm_b200_set_nodes(admm_b200_solver *s, int n_nodes, const double *x, const
 }
 
 int admm_b200_add_tets(admm_b200_solver *s, int n, const int *idx, const double *dminv, const double *weight,
-	int model, double mu, double lambda, double kappa, const int *row_offset)
+	int model, double mu, double lambda, double kappa, double bulk_modulus, const int *row_offset)
 {
 	return guard(s, [&]() {
 		require(!s->finalized, "add_tets after finalize");
@@ -1454,7 +1484,7 @@ int admm_b200_add_tets(admm_b200_solver *s, int n, const int *idx, const double 
 		for (int i = 0; i < 4 * n; ++i) require(idx[i] >= 0 && idx[i] < s->n_nodes, "add_tets: vertex index out of range (call set_nodes first)");
 		for (int e = 0; e < n; ++e) require(weight[e] > 0.0, "**EnergyTerm::get_reduction Error: Some weight leq 0");
 		TetBatchH *t = new TetBatchH();
-		t->n = n; t->model = model; t->mu = mu; t->lambda = lambda; t->kappa = kappa;
+		t->n = n; t->model = model; t->mu = mu; t->lambda = lambda; t->kappa = kappa; t->bulk = bulk_modulus;
 		t->idx.assign(idx, idx + (size_t)4 * n);
 		t->dminv.assign(dminv, dminv + (size_t)9 * n);
 		t->w.assign(weight, weight + n);
@@ -1523,6 +1553,23 @@ int admm_b200_set_gs_pins(admm_b200_solver *s, int n, const int *idx, const doub
 		s->gs_pin_idx.assign(idx, idx + n);
 		s->gs_pin_pos.assign(pos, pos + (size_t)3 * n);
 		if (s->finalized && s->linsolver == ADMM_B200_MCGS) upload_gs_pins(s);
+	});
+}
+
+int admm_b200_set_surface_inds(admm_b200_solver *s, int n, const int *idx)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_surface_inds after finalize");
+		require(n >= 0 && (n == 0 || idx), "set_surface_inds: null input");
+		s->surface_inds.assign(idx, idx + n);
+	});
+}
+
+int admm_b200_set_constraint_weight(admm_b200_solver *s, double constraint_w)
+{
+	return guard(s, [&]() {
+		require(!s->finalized, "set_constraint_weight after finalize");
+		s->constraint_w = constraint_w;
 	});
 }
 
@@ -1761,13 +1808,13 @@ int admm_b200_step_host(admm_b200_solver *s, int admm_iters, double gravity, dou
 	});
 }
 
-int admm_b200_prox_tets(admm_b200_solver *s, int model, double mu, double lambda, double kappa, int precision, int n, const double *z_in, double *z_out)
+int admm_b200_prox_tets(admm_b200_solver *s, int model, double mu, double lambda, double kappa, double bulk_modulus, int precision, int n, const double *z_in, double *z_out)
 {
 	return guard(s, [&]() {
 		require(n >= 0 && (n == 0 || (z_in && z_out)), "prox_tets: null input");
 		if (n == 0) return;
-		if (precision == ADMM_B200_FP64) prox_tets_impl<double>(s, model, mu, lambda, kappa, n, z_in, z_out);
-		else prox_tets_impl<float>(s, model, mu, lambda, kappa, n, z_in, z_out);
+		if (precision == ADMM_B200_FP64) prox_tets_impl<double>(s, model, mu, lambda, kappa, bulk_modulus, n, z_in, z_out);
+		else prox_tets_impl<float>(s, model, mu, lambda, kappa, bulk_modulus, n, z_in, z_out);
 	});
 }
 

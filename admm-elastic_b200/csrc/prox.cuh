@@ -227,12 +227,15 @@ ADMMB200_FN void usvt(const T *U, const T *s, const T *V, T *Z)
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct Material {
 	T a, l, kap;              // mu/K, lambda/K, kappa/K (the Newton path works on the objective divided by K)
-	double mu, lambda, kappa; // raw constants, only read by the reference-faithful path (prox_lbfgs_reference)
-	static Material make(double mu_, double lambda_, double kappa_) {
+	double mu, lambda, kappa, k; // raw constants, only read by the reference-faithful path (prox_lbfgs_reference)
+	// K = stiffness of the prox penalty K/2 |sigma - sigma0|^2: the bulk modulus of the ELEMENT's Lame
+	// (src/TetEnergyTerm.hpp:125-128, 193-200), which for a SplineTet may differ from the spline's own constants;
+	// K_ <= 0: lambda + 2/3 mu of the model constants (Lame::bulk_modulus, src/EnergyTerm.hpp:41)
+	static Material make(double mu_, double lambda_, double kappa_, double K_ = 0.0) {
 		Material m;
-		double K = lambda_ + (2.0 / 3.0) * mu_; // Lame::bulk_modulus (src/EnergyTerm.hpp:41)
+		const double K = K_ > 0.0 ? K_ : lambda_ + (2.0 / 3.0) * mu_;
 		m.a = T(mu_ / K); m.l = T(lambda_ / K); m.kap = T(kappa_ / K);
-		m.mu = mu_; m.lambda = lambda_; m.kappa = kappa_;
+		m.mu = mu_; m.lambda = lambda_; m.kappa = kappa_; m.k = K;
 		return m;
 	}
 };
@@ -470,11 +473,11 @@ template <int MODEL> struct RefProblem {
 };
 
 template <int MODEL>
-ADMMB200_SLOWPATH void prox_lbfgs_reference(double mu, double lambda, double kappa, const double *x0, double *x)
+ADMMB200_SLOWPATH void prox_lbfgs_reference(double mu, double lambda, double kappa, double bulk, const double *x0, double *x)
 {
 	RefProblem<MODEL> P;
 	P.m.a = mu; P.m.l = lambda; P.m.kap = kappa; P.m.mu = mu; P.m.lambda = lambda; P.m.kappa = kappa;
-	P.k = lambda + (2.0 / 3.0) * mu;
+	P.k = bulk;
 	P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
 	const int M = 8;
 	double s[M][3], y[M][3], alpha[M], rho[M];
@@ -605,7 +608,7 @@ ADMMB200_FN bool prox_tet_mode(const Material<T> &m, T *z, T *q = nullptr)
 		if (MODE == PROX_FAST) return true;
 		// minimiser on the bound (or no convergence): walk the reference optimiser's own path in fp64
 		double xs[3] = {double(S[0]), double(S[1]), double(S[2])}, xc[3] = {double(x0[0]), double(x0[1]), double(x0[2])};
-		if (MODEL != TET_LINEAR) prox_lbfgs_reference<MODEL == TET_LINEAR ? TET_STVK : MODEL>(m.mu, m.lambda, m.kappa, xc, xs);
+		if (MODEL != TET_LINEAR) prox_lbfgs_reference<MODEL == TET_LINEAR ? TET_STVK : MODEL>(m.mu, m.lambda, m.kappa, m.k, xc, xs);
 		S[0] = T(xs[0]); S[1] = T(xs[1]); S[2] = T(xs[2]);
 	}
 	usvt(U, S, V, z);

@@ -74,12 +74,11 @@ __device__ __forceinline__ void blk_row_dot(const double *__restrict__ vals, con
 	}
 }
 
-__global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
+// The whole solve x = P^T L^-T D^-1 L^-1 P b as a device function: the standalone kernel below and the persistent UzawaCG
+// kernel (uzawa.cuh) call it.  Every thread of the (cooperative) grid must call it; it ends with a grid barrier.
+__device__ __forceinline__ void ldlt_blocks_solve(const LdltBlkParams &P, const double4 *b, double4 *x, unsigned int &bar_target, double *s_part)
 {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
-	__shared__ double s_part[3 * 32];
-	unsigned int bar_target = 0;
-	if (P.active && *P.active == 0) return; // the same for every block: no barrier is left waiting
 
 	// ---------------- forward: y = L^-1 P b ----------------
 	for (int lv = 0; lv < P.n_levels_f; ++lv) {
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 				if (act) blk_row_dot<true>(P.f_vals, P.f_cols, P.y, __ldg(&P.f_rowptr[i]), __ldg(&P.f_rowptr[i + 1]), sub, T, sx, sy, sz);
 				blk_reduce(sx, sy, sz, T, s_part);
 				if (act && sub == 0) {
-					const double4 bi = P.b[__ldg(&P.perm[i])];
+					const double4 bi = ld_node_cg(&b[__ldg(&P.perm[i])]);
 					st_node(&P.t[i], bi.x - sx, bi.y - sy, bi.z - sz);
 				}
 			}
@@ -158,12 +157,20 @@ __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
 					const double4 tj = ld_node_cg(&P.t[j]);
 					const double rx = tj.x + sx, ry = tj.y + sy, rz = tj.z + sz;
 					st_node(&P.y[j], rx, ry, rz);
-					st_node(&P.x[__ldg(&P.perm[j])], rx, ry, rz);
+					st_node(&x[__ldg(&P.perm[j])], rx, ry, rz);
 				}
 			}
 		}
 		grid_barrier(P.barrier, bar_target, gridDim.x);
 	}
+}
+
+__global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
+{
+	__shared__ double s_part[3 * 32];
+	unsigned int bar_target = 0;
+	if (P.active && *P.active == 0) return; // the same for every block: no barrier is left waiting
+	ldlt_blocks_solve(P, P.b, P.x, bar_target, s_part);
 }
 
 } // namespace admmb200

@@ -126,6 +126,8 @@ public:
 	virtual double kappa() const { return 0.0; }
 	virtual double model_mu() const { return lame.mu; }
 	virtual double model_lambda() const { return lame.lambda; }
+	// K of the prox penalty: always the ELEMENT's Lame (problem.k = lame_.bulk_modulus(), src/TetEnergyTerm.hpp:193-200)
+	double prox_bulk_modulus() const { return lame.bulk_modulus(); }
 	const Vec4i &indices() const { return tet; }
 	const Lame &material() const { return lame; }
 	const double *rest_inverse() const { return edges_inv; }
@@ -489,7 +491,7 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 	// scalar system matrix L = dt^2 sum_e w_e^2 d_e^T d_e  (A = L (x) I3 + M).
 	const double dt2 = m_settings.timestep_s * m_settings.timestep_s;
 	std::vector<sparse::Entry> entries;
-	struct TetGroup { int model; double mu, lambda, kappa; std::vector<int> idx, row; std::vector<double> dminv, w; };
+	struct TetGroup { int model; double mu, lambda, kappa, bulk; std::vector<int> idx, row; std::vector<double> dminv, w; };
 	struct TriGroup { double lmin, lmax; std::vector<int> idx, row; std::vector<double> rest, w; };
 	std::vector<TetGroup> tgroups; std::vector<TriGroup> rgroups;
 	std::vector<int> p_idx, p_row; std::vector<double> p_pos, p_w;
@@ -498,8 +500,8 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 		case EnergyTerm::TET: {
 			TetEnergyTerm *t = static_cast<TetEnergyTerm *>(term.get());
 			TetGroup *g = nullptr;
-			if (!tgroups.empty()) { TetGroup &b = tgroups.back(); if (b.model == t->model() && b.mu == t->model_mu() && b.lambda == t->model_lambda() && b.kappa == t->kappa()) g = &b; }
-			if (!g) { tgroups.emplace_back(); g = &tgroups.back(); g->model = t->model(); g->mu = t->model_mu(); g->lambda = t->model_lambda(); g->kappa = t->kappa(); }
+			if (!tgroups.empty()) { TetGroup &b = tgroups.back(); if (b.model == t->model() && b.mu == t->model_mu() && b.lambda == t->model_lambda() && b.kappa == t->kappa() && b.bulk == t->prox_bulk_modulus()) g = &b; }
+			if (!g) { tgroups.emplace_back(); g = &tgroups.back(); g->model = t->model(); g->mu = t->model_mu(); g->lambda = t->model_lambda(); g->kappa = t->kappa(); g->bulk = t->prox_bulk_modulus(); }
 			const double *bi = t->rest_inverse();
 			for (int c = 0; c < 4; ++c) g->idx.push_back(t->indices()[c]);
 			for (int k = 0; k < 9; ++k) g->dminv.push_back(bi[k]);
@@ -581,11 +583,17 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 			g.idx.resize(3 * keep); g.rest.resize(4 * keep); g.w.resize(keep); g.row.resize(keep);
 		}
 	}
-	for (auto &g : tgroups) if (!g.w.empty()) check(admm_b200_add_tets(handle, (int)g.w.size(), g.idx.data(), g.dminv.data(), g.w.data(), g.model, g.mu, g.lambda, g.kappa, g.row.data()), "add_tets");
+	for (auto &g : tgroups) if (!g.w.empty()) check(admm_b200_add_tets(handle, (int)g.w.size(), g.idx.data(), g.dminv.data(), g.w.data(), g.model, g.mu, g.lambda, g.kappa, g.bulk, g.row.data()), "add_tets");
 	for (auto &g : rgroups) if (!g.w.empty()) check(admm_b200_add_tris(handle, (int)g.w.size(), g.idx.data(), g.rest.data(), g.w.data(), g.lmin, g.lmax, g.row.data()), "add_tris");
 	if (!p_idx.empty()) check(admm_b200_add_pins(handle, (int)p_idx.size(), p_idx.data(), p_pos.data(), p_w.data(), p_row.data()), "add_pins");
 
 	for (auto &o : passive_objs) { double p[4]; o->params(p); check(admm_b200_add_obstacle(handle, o->kind(), p), "add_obstacle"); }
+	if (m_settings.linsolver == 2) {
+		// what UzawaCG's collision rows depend on: the candidate vertices and their order (src/Solver.cpp:93), and
+		// constraint_w = 1 unless -ck overrides it (src/Solver.cpp:239,245)
+		if (!surface_inds.empty()) check(admm_b200_set_surface_inds(handle, (int)surface_inds.size(), surface_inds.data()), "set_surface_inds");
+		check(admm_b200_set_constraint_weight(handle, m_settings.constraint_w > 0.0 ? m_settings.constraint_w : 1.0), "set_constraint_weight");
+	}
 
 	// Linear solver (src/Solver.cpp:229-246)
 	switch (m_settings.linsolver) {

@@ -54,6 +54,22 @@ int admmhost_add_tets(void *h_, const double *verts, const int *inds, int n_tets
 	});
 }
 
+// SplineTet with a spline whose constants differ from the element's Lame (src/TetEnergyTerm.hpp:200-205)
+int admmhost_add_spline_tets(void *h_, const double *verts, const int *inds, int n_tets, int spline_type, double mu, double lambda, double sp_mu, double sp_lambda, double sp_kappa, int vertex_offset) {
+	Host *h = (Host *)h_;
+	return guarded(h, [&]() {
+		Lame lame = make_lame(mu, lambda, -100.0, 100.0);
+		std::shared_ptr<xu::Spline> sp = std::make_shared<xu::Spline>((xu::Spline::Type)spline_type, sp_mu, sp_lambda, sp_kappa);
+		for (int i = 0; i < n_tets; ++i) {
+			Vec4i tet(inds[i * 4], inds[i * 4 + 1], inds[i * 4 + 2], inds[i * 4 + 3]);
+			std::vector<Vec3> tv;
+			for (int c = 0; c < 4; ++c) tv.emplace_back(verts[tet[c] * 3], verts[tet[c] * 3 + 1], verts[tet[c] * 3 + 2]);
+			for (int c = 0; c < 4; ++c) tet[c] += vertex_offset;
+			h->solver.energyterms.emplace_back(std::make_shared<SplineTet>(tet, tv, lame, sp));
+		}
+	});
+}
+
 int admmhost_add_tris(void *h_, const double *verts, const int *inds, int n_tris, double mu, double lambda, double limit_min, double limit_max, int vertex_offset) {
 	Host *h = (Host *)h_;
 	return guarded(h, [&]() {
@@ -83,6 +99,7 @@ int admmhost_set_options(void *h_, int device, int precision, int gs_max_iters, 
 	return 0;
 }
 
+int admmhost_set_surface_inds(void *h_, const int *idx, int n) { ((Host *)h_)->solver.surface_inds.assign(idx, idx + n); return 0; }
 int admmhost_set_gs_parts(void *h_, int n_parts) { ((Host *)h_)->solver.device_options.gs_parts = n_parts; return 0; }
 
 int admmhost_set_rank(void *h_, int rank, int world) {

@@ -92,9 +92,13 @@ int admm_b200_set_nodes( admm_b200_solver *s, int n_nodes, const double *x, cons
  *   weight[e]          get_weight() = sqrt(K*vol)
  *   row_offset[e]      g_index, the first of the tet's 9 rows of D (src/EnergyTerm.hpp:117);
  *                      only used to lay out debug_get("z"/"u") like the reference; may be NULL
- *   mu, lambda         Lame parameters; kappa: compression term of the spline models. */
+ *   mu, lambda         constants of the constitutive model (for the spline models: the xu::Spline's own);
+ *                      kappa: compression term of the spline models
+ *   bulk_modulus       K of the prox penalty K/2 |sigma - sigma0|^2 = Lame::bulk_modulus() of the ELEMENT's Lame
+ *                      (problem.k, src/TetEnergyTerm.hpp:125-128, 154-157, 193-200) -- it differs from the model constants
+ *                      only for a SplineTet built with a spline of other constants; <= 0: lambda + 2/3 mu. */
 int admm_b200_add_tets( admm_b200_solver *s, int n, const int *idx, const double *dminv, const double *weight,
-	int model, double mu, double lambda, double kappa, const int *row_offset );
+	int model, double mu, double lambda, double kappa, double bulk_modulus, const int *row_offset );
 
 /* A batch of n triangles (TriEnergyTerm, src/TriEnergyTerm.cpp:29-101):
  *   idx[3e+c]; restpose[4e+2c+r] = rest_pose(c,r) (2x2, F = [x1-x0, x2-x0] * rest_pose);
@@ -117,6 +121,15 @@ int admm_b200_set_gs_pins( admm_b200_solver *s, int n, const int *idx, const dou
 /* Passive obstacles tested per node inside the sweep, Collider::detect_passive
  * (src/Collider.hpp:137-150); order of calls = order of passive_objs. */
 int admm_b200_add_obstacle( admm_b200_solver *s, int kind, const double *params );
+
+/* UzawaCG only.  The vertices Collider::detect tests for passive hits, in that order: Solver::surface_inds
+ * (src/Solver.hpp:69, src/Solver.cpp:93, src/Collider.hpp:152-212; filled by binding::add_tetmesh,
+ * samples/utils/AddMeshes.hpp:130-136).  n = 0 (the default): every node, in node order.  The order fixes the row order of
+ * the constraint matrix and with it which multiplier a warm start hands to which row (src/UzawaCG.hpp:69-74). */
+int admm_b200_set_surface_inds( admm_b200_solver *s, int n, const int *idx );
+/* UzawaCG only.  ConstraintSet::constraint_w: C and c are scaled by sqrt(max(0, w)) (src/ConstraintSet.hpp:66,84-88);
+ * 1 unless Settings::constraint_w > 0 (-ck) overrides it (src/Solver.cpp:239,245). */
+int admm_b200_set_constraint_weight( admm_b200_solver *s, double constraint_w );
 
 /* The constant global matrix A = M + dt^2 D^T W^2 D (src/Solver.cpp:226).  Every get_reduction of
  * the reference couples x-x, y-y, z-z only, so A = L (x) I3 plus a diagonal: the host passes the
@@ -157,7 +170,7 @@ int admm_b200_download_state( admm_b200_solver *s, double *x, double *v );
 
 /* prox() alone on n deformation gradients, column-major 9 doubles each, in the chosen precision:
  * TetEnergyTerm::prox / HyperElasticTet::prox (src/TetEnergyTerm.cpp:73-92, 114-136). */
-int admm_b200_prox_tets( admm_b200_solver *s, int model, double mu, double lambda, double kappa,
+int admm_b200_prox_tets( admm_b200_solver *s, int model, double mu, double lambda, double kappa, double bulk_modulus,
 	int precision, int n, const double *z_in, double *z_out );
 /* TriEnergyTerm::prox (src/TriEnergyTerm.cpp:73-101), 6 doubles each. */
 int admm_b200_prox_tris( admm_b200_solver *s, double limit_min, double limit_max,

@@ -51,7 +51,7 @@ public:
 	bool keep_z;     // keep z on the device (debug_get)
 
 	// What initialize() harvested, in energyterms order per kind (public: the parity tests compare it with the mirror's)
-	struct TetBatch { int model; double mu, lambda, kappa; std::vector<int> idx, row; std::vector<double> dminv, w; };
+	struct TetBatch { int model; double mu, lambda, kappa, bulk; std::vector<int> idx, row; std::vector<double> dminv, w; };
 	struct TriBatch { double limit_min, limit_max; std::vector<int> idx, row; std::vector<double> rest, w; };
 	std::vector<TetBatch> tet_batches;
 	std::vector<TriBatch> tri_batches;
@@ -122,10 +122,12 @@ inline void GpuSolver::harvest_terms(){
 		if( TetEnergyTerm *tet = dynamic_cast<TetEnergyTerm*>(t) ){
 			// 36 triplets, index (r*4+c)*3+j: row g+3r+j, column 3*tet[c]+j, value (S*edges_inv)(c,r)  (src/TetEnergyTerm.cpp:50-71)
 			if( nt != 36 || tet->get_dim() != 9 ){ throw std::runtime_error("**GpuSolver Error: unknown tet term layout"); }
-			int model = ADMM_B200_TET_LINEAR; double mu=0, lambda=0, kappa=0;
-			if( NeoHookeanTet *nh = dynamic_cast<NeoHookeanTet*>(t) ){ model = ADMM_B200_TET_NEOHOOKEAN; mu = nh->problem.mu; lambda = nh->problem.lambda; }
-			else if( StVKTet *sv = dynamic_cast<StVKTet*>(t) ){ model = ADMM_B200_TET_STVK; mu = sv->problem.mu; lambda = sv->problem.lambda; }
+			// bulk: K of the prox penalty = problem.k, the bulk modulus of the element's own Lame (src/TetEnergyTerm.hpp:125-128,193-200)
+			int model = ADMM_B200_TET_LINEAR; double mu=0, lambda=0, kappa=0, bulk=0;
+			if( NeoHookeanTet *nh = dynamic_cast<NeoHookeanTet*>(t) ){ model = ADMM_B200_TET_NEOHOOKEAN; mu = nh->problem.mu; lambda = nh->problem.lambda; bulk = nh->problem.k; }
+			else if( StVKTet *sv = dynamic_cast<StVKTet*>(t) ){ model = ADMM_B200_TET_STVK; mu = sv->problem.mu; lambda = sv->problem.lambda; bulk = sv->problem.k; }
 			else if( SplineTet *sp = dynamic_cast<SplineTet*>(t) ){
+				bulk = sp->problem.k;
 				xu::Spline *s = sp->problem.spline.get();
 				if( xu::NeoHookean *a = dynamic_cast<xu::NeoHookean*>(s) ){ model = ADMM_B200_TET_SPLINE_NH; mu = a->mu; lambda = a->lambda; kappa = a->kappa; }
 				else if( xu::StVK *b = dynamic_cast<xu::StVK*>(s) ){ model = ADMM_B200_TET_SPLINE_STVK; mu = b->mu; lambda = b->lambda; kappa = b->kappa; }
@@ -134,8 +136,8 @@ inline void GpuSolver::harvest_terms(){
 			}
 			else if( dynamic_cast<HyperElasticTet*>(t) ){ throw std::runtime_error("**GpuSolver Error: custom HyperElasticTet subclasses cannot run on the GPU"); }
 			if( tet_batches.empty() || tet_batches.back().model != model || tet_batches.back().mu != mu ||
-				tet_batches.back().lambda != lambda || tet_batches.back().kappa != kappa ){
-				TetBatch nb; nb.model = model; nb.mu = mu; nb.lambda = lambda; nb.kappa = kappa;
+				tet_batches.back().lambda != lambda || tet_batches.back().kappa != kappa || tet_batches.back().bulk != bulk ){
+				TetBatch nb; nb.model = model; nb.mu = mu; nb.lambda = lambda; nb.kappa = kappa; nb.bulk = bulk;
 				tet_batches.push_back( nb );
 			}
 			TetBatch &b = tet_batches.back();
@@ -194,7 +196,7 @@ inline bool GpuSolver::initialize( const Settings &settings_ ){
 	harvest_terms();
 	for( size_t b=0; b<tet_batches.size(); ++b ){
 		TetBatch &t = tet_batches[b];
-		ck( admm_b200_add_tets( h, t.w.size(), t.idx.data(), t.dminv.data(), t.w.data(), t.model, t.mu, t.lambda, t.kappa, t.row.data() ), "add_tets" );
+		ck( admm_b200_add_tets( h, t.w.size(), t.idx.data(), t.dminv.data(), t.w.data(), t.model, t.mu, t.lambda, t.kappa, t.bulk, t.row.data() ), "add_tets" );
 	}
 	for( size_t b=0; b<tri_batches.size(); ++b ){
 		TriBatch &t = tri_batches[b];
@@ -233,6 +235,11 @@ inline bool GpuSolver::initialize( const Settings &settings_ ){
 		rowptr[i+1] = cols.size();
 	}
 
+	if( m_settings.linsolver == 2 ){
+		// what UzawaCG's collision rows depend on (src/Solver.cpp:93,239,245; src/ConstraintSet.hpp:66)
+		if( surface_inds.size() ){ ck( admm_b200_set_surface_inds( h, surface_inds.size(), surface_inds.data() ), "set_surface_inds" ); }
+		ck( admm_b200_set_constraint_weight( h, m_constraints->constraint_w ), "set_constraint_weight" );
+	}
 	if( m_settings.linsolver == 1 ){
 		ck( admm_b200_set_system( h, n, rowptr.data(), cols.data(), vals.data() ), "set_system" );
 		// Replace the CPU solver by one whose colour lists can be read: GPU and cpu_step() then sweep the SAME colours

@@ -385,6 +385,8 @@ typedef struct oracle_solver {
 	/* LDL^T of A, natural ordering */
 	int *Lp, *Li; double *Lx, *Dg; int have_ldlt;
 	double *uz_y; int uz_rows;
+	int *surf; int n_surf;   /* Solver::surface_inds (src/Solver.hpp:69): the vertices Collider::detect tests, in order; none = all */
+	double uz_ck;            /* sqrt(max(0, constraint_w)), ConstraintSet::make_matrix (src/ConstraintSet.hpp:66) */
 	double global_ms, local_ms; int inner_iters;
 	int initialized;
 	char err[256];
@@ -604,17 +606,20 @@ static int mcgs_solve(oracle_solver *s, double *x, const double *b)
 }
 
 /* UzawaCG::solve (src/UzawaCG.hpp:57-125) with ConstraintSet::make_matrix (src/ConstraintSet.hpp:59-116)
- * for passive hits only (Collider::detect with_passive, src/Collider.hpp:152-212); constraint_w = 1
- * (src/Solver.cpp:239) => ck = 1. */
+ * for passive hits only (Collider::detect over Solver::surface_inds with_passive, src/Collider.hpp:152-212); rows are
+ * scaled by ck = sqrt(constraint_w), constraint_w = 1 unless -ck overrides it (src/Solver.cpp:239,245). */
 static int uzawa_solve(oracle_solver *s, double *x, const double *b, const double *curr_x)
 {
-	int dof = s->A.n, n = s->n_nodes, i, rows = 0, iter;
-	int *hv = (int *)malloc(n * sizeof(int));
-	double *hn = (double *)malloc((size_t)3 * n * sizeof(double)), *hc = (double *)malloc(n * sizeof(double));
+	int dof = s->A.n, n = s->n_nodes, i, rows = 0, iter, c;
+	const int n_cand = s->n_surf > 0 ? s->n_surf : n;
+	const double ck = s->uz_ck;
+	int *hv = (int *)malloc((size_t)(n > s->n_surf ? n : s->n_surf) * sizeof(int));
+	double *hn = (double *)malloc((size_t)3 * (n > s->n_surf ? n : s->n_surf) * sizeof(double)), *hc = (double *)malloc((size_t)(n > s->n_surf ? n : s->n_surf) * sizeof(double));
 	double *q1, *q2, *r, *d, *q3;
 	const double tol2 = s->uz_tol * s->uz_tol;
-	for (i = 0; i < n && s->n_obs > 0; ++i) {
+	for (c = 0; c < n_cand && s->n_obs > 0; ++c) {
 		/* Collider::detect: every passive object lowers the payload, hit if dx < 0 */
+		i = s->n_surf > 0 ? s->surf[c] : c;
 		double dx = DBL_MAX, nn[3] = {0, 0, 0}, pp[3] = {0, 0, 0}; int j;
 		const double *xi = curr_x + 3 * i;
 		for (j = 0; j < s->n_obs; ++j) {
@@ -622,7 +627,7 @@ static int uzawa_solve(oracle_solver *s, double *x, const double *b, const doubl
 			if (o->kind == 0) { double dd = xi[1] - o->p[0]; if (!(dd > dx)) { dx = dd; pp[0] = xi[0]; pp[1] = o->p[0]; pp[2] = xi[2]; nn[0] = 0; nn[1] = 1; nn[2] = 0; } }
 			else { double dir[3] = {xi[0] - o->p[0], xi[1] - o->p[1], xi[2] - o->p[2]}, len = norm3(dir), dd = len - o->p[3]; if (!(dd > dx)) { int k; dx = dd; for (k = 0; k < 3; ++k) { dir[k] /= len; pp[k] = o->p[k] + dir[k] * o->p[3]; nn[k] = dir[k]; } } }
 		}
-		if (dx < 0) { hv[rows] = i; memcpy(hn + 3 * rows, nn, sizeof(nn)); hc[rows] = dot3(nn, pp); rows++; }
+		if (dx < 0) { hv[rows] = i; hn[3 * rows] = ck * nn[0]; hn[3 * rows + 1] = ck * nn[1]; hn[3 * rows + 2] = ck * nn[2]; hc[rows] = ck * dot3(nn, pp); rows++; }
 	}
 	if (s->uz_rows != rows) { free(s->uz_y); s->uz_y = (double *)calloc(rows > 0 ? rows : 1, sizeof(double)); s->uz_rows = rows; }
 	if (rows == 0) { ldlt_solve(s, b, x); free(hv); free(hn); free(hc); return 1; }
@@ -668,6 +673,7 @@ oracle_solver *oracle_create(void)
 	oracle_solver *s = (oracle_solver *)calloc(1, sizeof(oracle_solver));
 	s->gs_max_iters = 30; s->gs_tol = 1e-10; s->gs_omega = 1.9; /* src/NodalMultiColorGS.hpp:45-46 */
 	s->uz_max_iters = 20; s->uz_tol = 1e-10;                     /* src/UzawaCG.hpp:45-46 */
+	s->uz_ck = 1.0; s->surf = NULL; s->n_surf = 0;
 	return s;
 }
 void oracle_destroy(oracle_solver *s)
@@ -717,6 +723,18 @@ int oracle_add_tets(oracle_solver *s, const double *verts, const int *inds, int 
 		t->weight = sqrt(t->k * vol);
 		for (c = 0; c < 4; ++c) t->idx[c] = inds[4 * i + c] + vertex_offset;
 	}
+	return 0;
+}
+
+/* SplineTet(tet, verts, lame, spline) with a spline whose constants differ from the element's Lame
+ * (src/TetEnergyTerm.hpp:200-205): the weight and the prox penalty K come from the Lame, the energy from the spline. */
+int oracle_add_spline_tets(oracle_solver *s, const double *verts, const int *inds, int n_tets, int model, double mu, double lambda,
+	double sp_mu, double sp_lambda, double sp_kappa, int vertex_offset)
+{
+	const int first = s->n_terms;
+	int i, rc = oracle_add_tets(s, verts, inds, n_tets, model, mu, lambda, sp_kappa, vertex_offset);
+	if (rc) return rc;
+	for (i = first; i < s->n_terms; ++i) { s->terms[i].mu = sp_mu; s->terms[i].lambda = sp_lambda; } /* k and weight stay the Lame's */
 	return 0;
 }
 
@@ -784,6 +802,15 @@ void oracle_gs_params(oracle_solver *s, int max_iters, double tol, double omega)
 
 /* Solver::initialize (src/Solver.cpp:167-261).  Pins become SpringPin terms for linsolver 0/2, in
  * the order they were given (the reference iterates an unordered_map; tests read g_index back). */
+/* Solver::surface_inds and Settings::constraint_w (-ck) for the UzawaCG path; call before oracle_initialize */
+int oracle_set_uzawa(oracle_solver *s, int n_surf, const int *surf, double constraint_w)
+{
+	free(s->surf); s->surf = NULL; s->n_surf = 0;
+	if (n_surf > 0) { s->surf = (int *)malloc((size_t)n_surf * sizeof(int)); memcpy(s->surf, surf, (size_t)n_surf * sizeof(int)); s->n_surf = n_surf; }
+	s->uz_ck = constraint_w > 0.0 ? sqrt(constraint_w) : 1.0;
+	return 0;
+}
+
 int oracle_initialize(oracle_solver *s, double dt, int admm_iters, double gravity, int linsolver)
 {
 	int t, i, rows = 0;
@@ -891,6 +918,19 @@ int oracle_prox_tets(int model, double mu, double lambda, double kappa, int n, c
 		double z[9]; memcpy(z, z_in + 9 * i, sizeof(z));
 		if (model == TET_LINEAR) prox_tet_linear(z);
 		else { prox_problem p; memset(&p, 0, sizeof(p)); p.model = model; p.mu = mu; p.lambda = lambda; p.kappa = kappa; p.k = lambda + (2.0 / 3.0) * mu; bad += prox_tet_hyper(&p, z); }
+		memcpy(z_out + 9 * i, z, sizeof(z));
+	}
+	return bad;
+}
+/* the same with the prox penalty K given separately (a SplineTet whose spline constants differ from its Lame) */
+int oracle_prox_tets_k(int model, double mu, double lambda, double kappa, double K, int n, const double *z_in, double *z_out)
+{
+	int i, bad = 0;
+	#pragma omp parallel for reduction(+:bad)
+	for (i = 0; i < n; ++i) {
+		double z[9]; memcpy(z, z_in + 9 * i, sizeof(z));
+		if (model == TET_LINEAR) prox_tet_linear(z);
+		else { prox_problem p; memset(&p, 0, sizeof(p)); p.model = model; p.mu = mu; p.lambda = lambda; p.kappa = kappa; p.k = K; bad += prox_tet_hyper(&p, z); }
 		memcpy(z_out + 9 * i, z, sizeof(z));
 	}
 	return bad;

@@ -166,6 +166,23 @@ int ref_add_tets( void *h_, const double *verts, const int *inds, int n_tets, in
 	});
 }
 
+// SplineTet whose spline has constants of its own (src/TetEnergyTerm.hpp:200-205); spline_type 0 NeoHookean, 1 StVK, 2 CoRotated
+int ref_add_spline_tets( void *h_, const double *verts, const int *inds, int n_tets, int spline_type,
+	double mu, double lambda, double sp_mu, double sp_lambda, double sp_kappa, int vertex_offset ){
+	Handle *h = (Handle*)h_;
+	return guarded( h, [&](){
+		typedef Eigen::Matrix<int,4,1> Vec4i; typedef Eigen::Vector3d Vec3;
+		Lame lame = make_lame( mu, lambda, -100.0, 100.0 );
+		for( int i=0; i<n_tets; ++i ){
+			Vec4i tet( inds[i*4], inds[i*4+1], inds[i*4+2], inds[i*4+3] );
+			std::vector<Vec3> tv;
+			for( int c=0; c<4; ++c ){ tv.emplace_back( verts[tet[c]*3], verts[tet[c]*3+1], verts[tet[c]*3+2] ); }
+			tet += Vec4i(1,1,1,1)*vertex_offset;
+			h->solver.energyterms.emplace_back( std::make_shared<admm::SplineTet>( tet, tv, lame, make_spline( spline_type, sp_mu, sp_lambda, sp_kappa ) ) );
+		}
+	});
+}
+
 int ref_add_tris( void *h_, const double *verts, const int *inds, int n_tris,
 	double mu, double lambda, double limit_min, double limit_max, int vertex_offset ){
 	Handle *h = (Handle*)h_;
@@ -185,6 +202,9 @@ int ref_set_pins( void *h_, const int *inds, const double *points, int n ){
 		h->solver.set_pins( i, p );
 	});
 }
+
+// Solver::surface_inds (src/Solver.hpp:69): the vertices Collider::detect tests (src/Solver.cpp:93)
+void ref_set_surface_inds( void *h_, const int *inds, int n ){ ((Handle*)h_)->solver.surface_inds.assign( inds, inds+n ); }
 
 int ref_add_floor( void *h_, double y ){
 	Handle *h = (Handle*)h_;
@@ -303,6 +323,22 @@ int ref_prox_tets( int model, double mu, double lambda, double kappa, int n, con
 			std::memcpy( z_out+9*i, zi.data(), sizeof(double)*9 );
 		}
 	} catch( std::exception &e ){ fprintf( stderr, "ref_prox_tets: %s\n", e.what() ); return 1; }
+	return 0;
+}
+
+// SplineTet::prox with the element's Lame (mu, lambda -> the penalty K) and a spline of other constants
+int ref_prox_spline_tets( int spline_type, double mu, double lambda, double sp_mu, double sp_lambda, double sp_kappa, int n, const double *z_in, double *z_out ){
+	typedef Eigen::Matrix<int,4,1> Vec4i; typedef Eigen::Vector3d Vec3;
+	try {
+		Lame lame = make_lame( mu, lambda, -100.0, 100.0 );
+		std::vector<Vec3> tv = { Vec3(0,0,0), Vec3(0,1,0), Vec3(0,0,1), Vec3(1,0,0) };
+		admm::SplineTet t( Vec4i(0,1,2,3), tv, lame, make_spline( spline_type, sp_mu, sp_lambda, sp_kappa ) );
+		for( int i=0; i<n; ++i ){
+			VecX zi = Eigen::Map<const VecX>( z_in+9*i, 9 );
+			t.prox( zi );
+			std::memcpy( z_out+9*i, zi.data(), sizeof(double)*9 );
+		}
+	} catch( std::exception &e ){ fprintf( stderr, "ref_prox_spline_tets: %s\n", e.what() ); return 1; }
 	return 0;
 }
 

@@ -52,7 +52,7 @@ def oracle_lib():
                    "oracle_set_colors", "oracle_gs_params", "oracle_initialize", "oracle_step", "oracle_step_traced", "oracle_dof",
                    "oracle_n_rows", "oracle_n_terms", "oracle_get_x", "oracle_get_v", "oracle_set_x", "oracle_set_v", "oracle_set_admm_iters",
                    "oracle_runtime", "oracle_get_row_offsets", "oracle_get_weights", "oracle_A_shape", "oracle_A_get", "oracle_linsolve",
-                   "oracle_apply_D", "oracle_term_energy"):
+                   "oracle_apply_D", "oracle_term_energy", "oracle_set_uzawa", "oracle_add_spline_tets", "oracle_prox_tets_k"):
             getattr(L, fn).argtypes = None
         _oracle = L
     return _oracle
@@ -269,6 +269,14 @@ class CpuSolver(object):
         verts, inds = f64(verts).ravel(), i32(inds).ravel()
         self._ck(self._f("add_tets")(self.h, dp(verts), ip(inds), inds.size // 4, int(model), D(mu), D(lam), D(kappa), int(vertex_offset)))
 
+    def add_spline_tets(self, verts, inds, spline_type, mu, lam, spline, vertex_offset=0):
+        """SplineTet(tet, verts, Lame(mu, lam), spline = (mu, lambda, kappa) of its own); type 0 NeoHookean, 1 StVK, 2 CoRotated."""
+        verts, inds = f64(verts).ravel(), i32(inds).ravel()
+        if self.kind == "oracle":
+            self._ck(self.L.oracle_add_spline_tets(self.h, dp(verts), ip(inds), inds.size // 4, 3 + int(spline_type), D(mu), D(lam), D(spline[0]), D(spline[1]), D(spline[2]), int(vertex_offset)))
+        else:
+            self._ck(self.L.ref_add_spline_tets(self.h, dp(verts), ip(inds), inds.size // 4, int(spline_type), D(mu), D(lam), D(spline[0]), D(spline[1]), D(spline[2]), int(vertex_offset)))
+
     def add_tris(self, verts, inds, mu, lam, limit_min=-100.0, limit_max=100.0, vertex_offset=0):
         verts, inds = f64(verts).ravel(), i32(inds).ravel()
         self._ck(self._f("add_tris")(self.h, dp(verts), ip(inds), inds.size // 3, D(mu), D(lam), D(limit_min), D(limit_max), int(vertex_offset)))
@@ -292,6 +300,16 @@ class CpuSolver(object):
         else:
             cc = f64(c)
             self._ck(self.L.ref_add_sphere(self.h, dp(cc), D(r)))
+
+    def set_surface_inds(self, inds, constraint_w=-1.0):
+        """Solver::surface_inds (+ Settings::constraint_w for the oracle, which takes both through one call; the reference
+        gets constraint_w through initialize).  Call before initialize."""
+        inds = i32(inds).ravel()
+        self._surf = inds
+        if self.kind == "oracle":
+            self.L.oracle_set_uzawa(self.h, inds.size, ip(inds), D(constraint_w))
+        else:
+            self.L.ref_set_surface_inds(self.h, ip(inds), inds.size)
 
     def set_colors(self, colors):
         off = np.zeros(len(colors) + 1, dtype=np.int32)
@@ -395,6 +413,18 @@ def prox_tets(kind, model, mu, lam, z, kappa=0.0):
         rc = oracle_lib().oracle_prox_tets(int(model), D(mu), D(lam), D(kappa), z.shape[0], dp(z), dp(out))
     else:
         rc = ref_lib().ref_prox_tets(int(model), D(mu), D(lam), D(kappa), z.shape[0], dp(z), dp(out))
+    return out, rc
+
+
+def prox_spline_tets(kind, spline_type, mu, lam, spline, z):
+    """SplineTet::prox of an element with Lame (mu, lam) and a spline (mu, lambda, kappa) of its own."""
+    z = f64(z).reshape(-1, 9)
+    out = np.empty_like(z)
+    if kind == "oracle":
+        K = lam + (2.0 / 3.0) * mu
+        rc = oracle_lib().oracle_prox_tets_k(3 + int(spline_type), D(spline[0]), D(spline[1]), D(spline[2]), D(K), z.shape[0], dp(z), dp(out))
+    else:
+        rc = ref_lib().ref_prox_spline_tets(int(spline_type), D(mu), D(lam), D(spline[0]), D(spline[1]), D(spline[2]), z.shape[0], dp(z), dp(out))
     return out, rc
 
 

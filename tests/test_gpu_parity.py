@@ -107,6 +107,35 @@ def test_prox_spline_compression_term(pkg, dev, model):
     assert np.abs(out - base).max() < 1e-4
 
 
+@pytest.mark.parametrize("spline_type", [0, 1, 2])
+def test_spline_tet_with_its_own_constants(pkg, dev, cpu, spline_type):
+    """SplineTet whose spline constants differ from the element's Lame: the prox penalty K is the Lame's bulk modulus
+    (src/TetEnergyTerm.hpp:193-205), handed over separately (admm_b200_add_tets: bulk_modulus)."""
+    spline = (0.6 * MU, 1.7 * LAM, 0.0)
+    K = LAM + (2.0 / 3.0) * MU
+    z = checkers.random_F(2000 + 5, 0.15, seed=60 + spline_type)
+    ref, _ = checkers.prox_spline_tets("oracle", spline_type, MU, LAM, spline, z)
+    for precision, tol in ((1, TOL_Z64), (0, TOL_Z32)):
+        out = dev.prox_tets(3 + spline_type, spline[0], spline[1], z, precision=precision, bulk_modulus=K)
+        e = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref))).max()
+        record("prox_spline_own_constants", spline=spline_type, precision=precision, err=e)
+        assert e < tol, (precision, e)
+    # whole steps through the host mirror (SplineTet descriptor carries the Lame and the spline)
+    scene = scenes.beam(pkg.meshes, 6, 2, 2)
+    gpu = gpu_solver(pkg, 1)
+    orc = CpuSolver("oracle")
+    for s in (gpu, orc):
+        s.add_nodes(scene[0], scene[2])
+        s.add_spline_tets(scene[0], scene[1], spline_type, MU, LAM, spline)
+        s.set_pins(scene[3])
+        assert s.initialize(dt=1.0 / 24, admm_iters=8, gravity=-9.8, linsolver=0)
+        s.set_x(scenes.bend(scene[0]).ravel())
+    for _ in range(3):
+        gpu.step()
+        orc.step()
+    assert np.abs(gpu.get_x() - orc.get_x()).max() < TOL_X64
+
+
 def test_prox_tets_inverted_collapsed_and_rest(pkg, dev, cpu):
     z = checkers.random_F(96, 0.2, seed=7)
     z[:32, 6:9] *= -1.0           # inverted (det F < 0), src/TetEnergyTerm.cpp:122,131
@@ -467,6 +496,48 @@ def test_uzawa_with_collisions_matches_oracle(pkg, cpu):
         gpu.step()
     rd = gpu.runtime_data()
     assert np.isfinite(gpu.get_x()).all() and rd["inner_iters"] >= 8
+
+
+def test_uzawa_surface_inds_and_constraint_weight(pkg, cpu):
+    """Solver::surface_inds (candidate vertices of the hit detection, in that order) and Settings::constraint_w (-ck) on
+    the device's UzawaCG (csrc/uzawa_blocks.cuh) against the oracle, solve by solve with warm-started multipliers."""
+    scene = scenes.beam(pkg.meshes, 6, 2, 2)
+    v = scene[0]
+    floor_y = v[:, 1].min() + 0.15
+    surf = np.nonzero((np.abs(v - v.min(0)) < 1e-9).any(axis=1) | (np.abs(v - v.max(0)) < 1e-9).any(axis=1))[0].astype(np.int32)[::-1].copy()
+    cw = 9.0
+    gpu = gpu_solver(pkg, 1)
+    gpu.set_surface_inds(surf)
+    scenes.build_tet_scene(gpu, scene, 1, linsolver=2, iters=4, floor=floor_y, pin=False, constraint_w=cw)
+    orc = CpuSolver("oracle")
+    orc.set_surface_inds(surf, cw)
+    scenes.build_tet_scene(orc, scene, 1, linsolver=2, iters=4, floor=floor_y, pin=False)
+    rp, ci, va = gpu.system_matrix()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((va, ci, rp), shape=(len(v), len(v)))
+    rng = np.random.RandomState(7)
+    x0 = scenes.bend(v).ravel()
+    counts = []
+    for k in range(6):
+        x_in = x0 + (0.0 if k % 2 else 0.02) * rng.randn(x0.size)
+        b = (A @ (x_in.reshape(-1, 3) + 0.01 * rng.randn(len(v), 3))).ravel()
+        xg, itg = gpu.device().linsolve(x_in, b)
+        xo, ito = orc.linsolve(x_in, b)
+        err = np.abs(xg - xo).max() / np.abs(xo).max()
+        record("uzawa_surface_ck", solve=k, err=err, iters=itg)
+        assert err < 1e-8, (k, err)
+        assert abs(itg - ito) <= 1, (itg, ito)
+        counts.append(itg)
+    assert min(counts) > 2
+    # an interior vertex below the floor is NOT a candidate: it stays below
+    inner = np.setdiff1d(np.arange(len(v)), surf)
+    if len(inner):
+        x_in = x0.copy().reshape(-1, 3)
+        x_in[inner[0], 1] = floor_y - 0.5
+        b = (A @ x_in).ravel()
+        xg, _ = gpu.device().linsolve(x_in.ravel(), b)
+        xo, _ = orc.linsolve(x_in.ravel(), b)
+        assert np.abs(xg - xo).max() / np.abs(xo).max() < 1e-8
 
 
 def test_uzawa_with_floor_golden(pkg):

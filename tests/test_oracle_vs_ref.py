@@ -225,3 +225,61 @@ def test_moving_pins_match_reference(pkg, cpu):
             s.set_pins(allp, pts)
             s.step()
     assert np.abs(sol[0].get_x() - sol[1].get_x()).max() < 2e-7
+
+
+def test_uzawa_surface_inds_and_constraint_weight_match_reference(pkg, cpu):
+    """Solver::surface_inds (only those vertices are tested for hits, and in that order, src/Solver.cpp:93) and
+    Settings::constraint_w (-ck: C and c scaled by sqrt(w), src/ConstraintSet.hpp:66,84-88, which moves the r^2 < tol^2
+    exit of the conjugate gradients): the oracle solve by solve on the reference's own (x_in, b)."""
+    scene = scenes.beam(pkg.meshes, 4, 2, 2)
+    v = scene[0]
+    floor_y = v[:, 1].min() - 0.02
+    # "surface": every vertex of the outer faces, deliberately NOT in node order
+    surf = np.nonzero((np.abs(v - v.min(0)) < 1e-9).any(axis=1) | (np.abs(v - v.max(0)) < 1e-9).any(axis=1))[0].astype(np.int32)[::-1].copy()
+    assert 0 < len(surf) < len(v)
+    cw = 9.0
+    ref, orc = CpuSolver("ref"), CpuSolver("oracle")
+    for s in (ref, orc):
+        s.set_surface_inds(surf, cw)
+    scenes.build_tet_scene(ref, scene, 1, linsolver=2, iters=8, floor=floor_y, pin=False, constraint_w=cw)
+    scenes.build_tet_scene(orc, scene, 1, linsolver=2, iters=8, floor=floor_y, pin=False)
+    n_constrained = 0
+    for step in range(4):
+        x_prev = ref.get_x() + (1.0 / 24) * (ref.get_v() + np.tile([0, (1.0 / 24) * -9.8, 0], ref.dof // 3))
+        z, u, b, x = ref.traced_step(8)
+        for it in range(8):
+            x_in = x_prev if it == 0 else x[it - 1]
+            xo, iters = orc.linsolve(x_in, b[it])
+            assert np.abs(xo - x[it]).max() < 1e-10
+            n_constrained += int((x_in.reshape(-1, 3)[surf, 1] < floor_y).any())
+    assert n_constrained > 5
+
+
+@pytest.mark.parametrize("spline_type", [0, 1, 2])
+def test_spline_tet_with_its_own_constants_matches_reference(pkg, cpu, spline_type):
+    """SplineTet(tet, verts, lame, spline) with spline constants different from the element's Lame
+    (src/TetEnergyTerm.hpp:200-205): the prox penalty K and the weight come from the Lame, the energy from the spline."""
+    mu, lam = scenes.lame(*scenes.LAME_SOFT)
+    spline = (0.6 * mu, 1.7 * lam, 0.0)
+    z = checkers.random_F(600, 0.15, seed=40 + spline_type)
+    zr, rc = checkers.prox_spline_tets("ref", spline_type, mu, lam, spline, z)
+    zo, _ = checkers.prox_spline_tets("oracle", spline_type, mu, lam, spline, z)
+    assert rc == 0 and np.abs(zr - zo).max() < 5e-6
+    # and it is NOT what the same spline gives with K taken from its own constants (the bug this test pins)
+    zw, _ = checkers.prox_tets("oracle", 3 + spline_type, spline[0], spline[1], z)
+    assert np.abs(zw - zr).max() > 1e-3
+    # whole steps
+    scene = scenes.beam(pkg.meshes, 5, 2, 2)
+    sol = []
+    for kind in ("ref", "oracle"):
+        s = CpuSolver(kind)
+        s.add_nodes(scene[0], scene[2])
+        s.add_spline_tets(scene[0], scene[1], spline_type, mu, lam, spline)
+        s.set_pins(scene[3])
+        assert s.initialize(dt=1.0 / 24, admm_iters=8, gravity=-9.8, linsolver=0)
+        s.set_x(scenes.bend(scene[0]).ravel())
+        sol.append(s)
+    for _ in range(3):
+        for s in sol:
+            s.step()
+    assert np.abs(sol[0].get_x() - sol[1].get_x()).max() < 5e-7
