@@ -108,15 +108,87 @@ def cloth_corner_pins(verts):
 
 
 def lumped_masses_tets(verts, tets, density=1522.0):
-    """float32 lumped vertex masses, a quarter of each tet's mass per corner."""
+    """float32 lumped vertex masses, a quarter of each tet's mass per corner, accumulated tet by tet and corner by corner
+    like TetMesh::weighted_masses (deps/mclscene/include/MCL/TetMesh.hpp:297-315)."""
     v = verts.astype(np.float32)
     e1, e2, e3 = v[tets[:, 1]] - v[tets[:, 0]], v[tets[:, 2]] - v[tets[:, 0]], v[tets[:, 3]] - v[tets[:, 0]]
     vol = np.abs(np.einsum("ij,ij->i", e1, np.cross(e2, e3)).astype(np.float32) / np.float32(6.0))
-    tm = (np.float32(density) * vol / np.float32(4.0)).astype(np.float32)
+    tm = ((np.float32(density) * vol).astype(np.float32) / np.float32(4.0)).astype(np.float32)
     m = np.zeros(len(v), dtype=np.float32)
-    for c in range(4):
-        np.add.at(m, tets[:, c], tm)
+    np.add.at(m, np.asarray(tets).ravel(), np.repeat(tm, 4))   # unbuffered, in (tet, corner) order
     return m
+
+
+def load_elenode(prefix):
+    """TetGen .ele / .node pair -> (float32 verts [n,3], int32 tets [m,4]) with the semantics of mcl::meshio::load_elenode
+    (deps/mclscene/include/MCL/MeshIO.hpp:180-311): the first line holds the count; every further line is `id a b c d` /
+    `id x y z`; ids are 1-based when the first one is 1; a record is stored AT its id; every id must occur; vertices are
+    rounded to float; tets with negative float32 volume get their corners 1 and 2 swapped."""
+    def read(path, n_cols, dtype):
+        with open(path) as f:
+            header = f.readline().split()
+            n = int(header[0]) if header else 0
+            rows = []
+            for _ in range(n):
+                rows.append(f.readline().split()[:1 + n_cols])
+        ids = np.array([int(r[0]) for r in rows], dtype=np.int64)
+        vals = np.array([[float(t) for t in r[1:1 + n_cols]] for r in rows], dtype=np.float64).reshape(n, n_cols)
+        one = n > 0 and ids[0] == 1
+        if one:
+            ids = ids - 1
+        if n == 0 or ids.min() < 0 or ids.max() >= n or len(np.unique(ids)) != n:
+            raise RuntimeError("**TetMesh Error: Your indices are bad for file %s" % path)
+        out = np.zeros((n, n_cols), dtype=np.float64)
+        out[ids] = vals
+        return out.astype(dtype), one
+    tets, one = read(prefix + ".ele", 4, np.int64)
+    if one:
+        tets = tets - 1
+    verts, _ = read(prefix + ".node", 3, np.float32)
+    if len(verts) == 0 or len(tets) == 0:
+        raise RuntimeError("**TetMesh Error: Problem loading files")
+    tets = fix_inverted_tets(verts, tets.astype(np.int32))
+    return verts, tets
+
+
+def fix_inverted_tets(verts, tets):
+    """Swaps corners 1 and 2 of every tet whose float32 signed volume is negative (MeshIO.hpp:291-303)."""
+    v = np.asarray(verts, dtype=np.float32)
+    t = np.array(tets, dtype=np.int32, copy=True)
+    a = v[t[:, 0]]
+    vol = (np.einsum("ij,ij->i", v[t[:, 1]] - a, np.cross(v[t[:, 2]] - a, v[t[:, 3]] - a)).astype(np.float32) / np.float32(6.0))
+    flip = vol < 0
+    t[flip, 1], t[flip, 2] = tets[flip, 2], tets[flip, 1]
+    return t
+
+
+def tile_mesh(verts, tets, counts, gap=0.05):
+    """counts = (cx, cy, cz) translated copies of a mesh on a grid (spacing = bounding box + gap x its largest side), vertex
+    ids offset copy by copy -- how a 50k-tet bunny becomes a 1M- or 8M-tet scene (20 / 146 tiled copies)."""
+    v = np.asarray(verts, dtype=np.float32)
+    t = np.asarray(tets, dtype=np.int32)
+    ext = v.max(0) - v.min(0)
+    pitch = (ext + np.float32(gap) * ext.max()).astype(np.float32)
+    vs, ts = [], []
+    k = 0
+    for ix in range(counts[0]):
+        for iy in range(counts[1]):
+            for iz in range(counts[2]):
+                vs.append((v + pitch * np.array([ix, iy, iz], dtype=np.float32)).astype(np.float32))
+                ts.append(t + np.int32(k * len(v)))
+                k += 1
+    return np.concatenate(vs, axis=0), np.concatenate(ts, axis=0).astype(np.int32)
+
+
+def surface_vertices(tets):
+    """Vertices of the boundary faces (faces that belong to exactly one tet), ascending: the set TetMesh::surface_inds
+    returns (deps/mclscene/include/MCL/TetMesh.hpp:317-342; the reference's ORDER is that of an unordered_map)."""
+    t = np.asarray(tets, dtype=np.int64)
+    faces = np.concatenate([t[:, [0, 1, 2]], t[:, [0, 1, 3]], t[:, [0, 2, 3]], t[:, [1, 2, 3]]], axis=0)
+    key = np.sort(faces, axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    boundary = faces[cnt[inv.ravel()] == 1]
+    return np.unique(boundary).astype(np.int32)
 
 
 def lumped_masses_tris(verts, tris, density=1.0):

@@ -22,6 +22,8 @@
 #include "NodalMultiColorGS.hpp"
 #include "UzawaCG.hpp"
 #include "PassiveObject.hpp"
+#include "MCL/TetMesh.hpp"
+#include "MCL/MeshIO.hpp"
 #include <cstring>
 #include <chrono>
 
@@ -372,6 +374,30 @@ double ref_tet_energy( int model, double mu, double lambda, const double *verts1
 	SparseMat D( 9, 12 ); D.setFromTriplets( trips.begin(), trips.end() );
 	VecX x = Eigen::Map<const VecX>( x12, 12 );
 	return t->energy( D, x );
+}
+
+// mcl::meshio::load_elenode (deps/mclscene/include/MCL/MeshIO.hpp:180-311) + TetMesh::weighted_masses / surface_inds:
+// what the mesh loader of the package is checked against.  Returns a mesh handle (NULL on failure).
+void *ref_mesh_load_elenode( const char *prefix ){
+	mcl::TetMesh *m = new mcl::TetMesh();
+	try { if( !mcl::meshio::load_elenode( m, std::string(prefix) ) ){ delete m; return NULL; } }
+	catch( std::exception & ){ delete m; return NULL; }
+	return m;
+}
+void ref_mesh_free( void *m ){ delete (mcl::TetMesh*)m; }
+int ref_mesh_n_verts( void *m ){ return ((mcl::TetMesh*)m)->vertices.size(); }
+int ref_mesh_n_tets( void *m ){ return ((mcl::TetMesh*)m)->tets.size(); }
+void ref_mesh_get( void *m_, float *verts, int *tets, float *masses, float density ){
+	mcl::TetMesh *m = (mcl::TetMesh*)m_;
+	for( size_t i=0; i<m->vertices.size(); ++i ){ for( int j=0; j<3; ++j ){ verts[3*i+j] = m->vertices[i][j]; } }
+	for( size_t i=0; i<m->tets.size(); ++i ){ for( int j=0; j<4; ++j ){ tets[4*i+j] = m->tets[i][j]; } }
+	std::vector<float> w; m->weighted_masses( w, density );
+	for( size_t i=0; i<w.size(); ++i ){ masses[i] = w[i]; }
+}
+int ref_mesh_surface_inds( void *m_, int *out ){
+	std::vector<int> s; ((mcl::TetMesh*)m_)->surface_inds( s );
+	if( out ){ for( size_t i=0; i<s.size(); ++i ){ out[i] = s[i]; } }
+	return s.size();
 }
 
 int ref_omp_threads(){ return omp_get_max_threads(); }

@@ -160,6 +160,35 @@ def single_tet():
     np.savez_compressed(os.path.join(HERE, "single_tet.npz"), iters=np.array(its), x=np.array(xs))
 
 
+def bunny_steps():
+    """A REAL irregular mesh from the reference's sample data (samples/data/bunny_2250: 9 752 tets), read by the package's
+    own .ele/.node loader (checked against the reference's MeshIO in tests/test_meshes_cpu.py):
+      * StVK, dropped on a Floor handled inside the multi-colour Gauss-Seidel (BASELINE config 3 style, the reference's own
+        colour lists are stored), 5 steps x 8 ADMM iterations;
+      * Neo-Hookean, the topmost vertices pinned, LDLT, 3 steps x 8 ADMM iterations."""
+    prefix = "/root/reference/samples/data/bunny_2250"
+    verts, tets = pkg.meshes.load_elenode(prefix)
+    masses = pkg.meshes.lumped_masses_tets(verts, tets, 1522.0).astype(np.float64)
+    v64 = verts.astype(np.float64)
+    pins = np.nonzero(v64[:, 1] > v64[:, 1].max() - 0.08 * (v64[:, 1].max() - v64[:, 1].min()))[0].astype(np.int32)
+    floor_y = float(v64[:, 1].min() - 0.01)
+    out = {"verts": v64, "tets": tets, "masses": masses, "pins": pins, "floor_y": np.array([floor_y])}
+    scene = (v64, tets, masses, pins)
+    s = scenes.build_tet_scene(CpuSolver("ref"), scene, 2, linsolver=1, iters=8, floor=floor_y, pin=False)
+    colors = s.get_colors()
+    out["floor_color_off"] = np.cumsum([0] + [len(c) for c in colors]).astype(np.int32)
+    out["floor_color_nodes"] = np.concatenate(colors).astype(np.int32)
+    for _ in range(5):   # it bounces: in contact after steps 1, 3 and 5
+        s.step()
+    out["floor_x5"] = s.get_x()
+    assert (np.abs(out["floor_x5"].reshape(-1, 3)[:, 1] - floor_y) < 1e-12).any()
+    s = scenes.build_tet_scene(CpuSolver("ref"), scene, 1, linsolver=0, iters=8)
+    for _ in range(3):
+        s.step()
+    out["ldlt_x3"] = s.get_x()
+    np.savez_compressed(os.path.join(HERE, "bunny_steps.npz"), **out)
+
+
 if __name__ == "__main__":
     assert checkers.have_ref(), "build oracle/_ref first (make -C oracle ref)"
     prox_vectors()
@@ -168,4 +197,5 @@ if __name__ == "__main__":
     single_tet()
     uzawa_floor()
     unstructured_steps()
+    bunny_steps()
     print("golden fixtures written to", HERE)

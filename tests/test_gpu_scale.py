@@ -217,3 +217,35 @@ def test_unstructured_mesh_golden(pkg, linsolver, precision):
     err = float(np.abs(s.get_x() - g["ls%d_x3" % linsolver]).max())
     record("unstructured_golden", linsolver=linsolver, precision=precision, err=err, err_over_bbox=err / bbox)
     assert err < (2e-6 if precision else GATE * bbox), err
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_bunny_golden(pkg, precision):
+    """A real irregular mesh through the device path: the reference's samples/data/bunny_2250 (9 752 tets, read by
+    meshes.load_elenode) -- StVK dropped on a Floor handled inside the Gauss-Seidel sweep with the reference's own colour
+    lists (BASELINE config 3 style), and Neo-Hookean with pins + LDLT -- against the compiled reference's positions
+    (tests/golden/bunny_steps.npz)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bunny_steps.npz"))
+    scene = (g["verts"], g["tets"], g["masses"], g["pins"])
+    bbox = float(np.linalg.norm(g["verts"].max(0) - g["verts"].min(0)))
+    floor_y = float(g["floor_y"][0])
+    off, nodes = g["floor_color_off"], g["floor_color_nodes"]
+    s = pkg.Solver()
+    s.set_options(precision=precision, coloring=pkg.COLOR_USER)
+    s.set_colors([nodes[off[i]:off[i + 1]] for i in range(len(off) - 1)])
+    scenes.build_tet_scene(s, scene, 2, linsolver=1, iters=8, floor=floor_y, pin=False)
+    for _ in range(5):
+        s.step()
+    x = s.get_x()
+    err = float(np.abs(x - g["floor_x5"]).max())
+    record("bunny_floor_golden", precision=precision, err=err, err_over_bbox=err / bbox, info=s.device().info())
+    assert x.reshape(-1, 3)[:, 1].min() >= floor_y - 1e-12 and (np.abs(x.reshape(-1, 3)[:, 1] - floor_y) < 1e-12).any()
+    assert err < (5e-6 if precision else GATE * bbox), err
+    s = pkg.Solver()
+    s.set_options(precision=precision)
+    scenes.build_tet_scene(s, scene, 1, linsolver=0, iters=8)
+    for _ in range(3):
+        s.step()
+    err = float(np.abs(s.get_x() - g["ldlt_x3"]).max())
+    record("bunny_ldlt_golden", precision=precision, err=err, err_over_bbox=err / bbox, info=s.device().info())
+    assert err < (2e-6 if precision else GATE * bbox), err

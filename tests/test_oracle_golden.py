@@ -119,3 +119,18 @@ def test_unstructured_mesh_golden(cpu, linsolver):
     for _ in range(3):
         s.step()
     assert np.abs(s.get_x() - g["ls%d_x3" % linsolver]).max() < 5e-7
+
+
+def test_bunny_golden(cpu):
+    """A real irregular mesh (the reference's samples/data/bunny_2250, 9 752 tets): StVK dropped on a Floor handled inside
+    the Gauss-Seidel sweep with the reference's 16 colour lists, and Neo-Hookean with pins + LDLT."""
+    g = np.load(os.path.join(G, "bunny_steps.npz"))
+    scene = (g["verts"], g["tets"], g["masses"], g["pins"])
+    s = scenes.build_tet_scene(CpuSolver("oracle"), scene, 2, linsolver=1, iters=8, floor=float(g["floor_y"][0]), pin=False, colors=colors_from(g, "floor"))
+    for _ in range(5):
+        s.step()
+    assert np.abs(s.get_x() - g["floor_x5"]).max() < 5e-7
+    s = scenes.build_tet_scene(CpuSolver("oracle"), scene, 1, linsolver=0, iters=8)
+    for _ in range(3):
+        s.step()
+    assert np.abs(s.get_x() - g["ldlt_x3"]).max() < 5e-7
