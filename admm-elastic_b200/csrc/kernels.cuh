@@ -362,16 +362,23 @@ __global__ void __launch_bounds__(256) assemble_kernel(int n, const int *__restr
 	const int r0 = __ldg(&inc_off[w]), r1 = __ldg(&inc_off[w + 1]);
 	double sx = 0, sy = 0, sz = 0;
 	const int *sl = inc_slot + (size_t)r0 * 32 + lane;
-#pragma unroll 4
-	for (int r = 0; r < r1 - r0; ++r) {
-		const int s = __ldg(sl + (size_t)r * 32);
-		if (s == ADMMB200_NO_SLOT) continue;
-		if (s >= 0) {
-			typename Vec4<E>::type v = f[s];
-			sx += double(v.x); sy += double(v.y); sz += double(v.z);
-		} else {
-			double4 v = fpin[s & 0x7fffffff];
-			sx += v.x; sy += v.y; sz += v.z;
+	const int nr = r1 - r0;
+	// batches of 8 rows: the 8 slot indices first (coalesced, independent), then the 8 scattered 16-byte share loads
+	// together -- the kernel is bound by the latency of those gathers, so what counts is how many are in flight
+	for (int r = 0; r < nr; r += 8) {
+		int sidx[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) sidx[j] = (r + j < nr) ? __ldg(sl + (size_t)(r + j) * 32) : ADMMB200_NO_SLOT;
+		typename Vec4<E>::type v[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			v[j].x = 0; v[j].y = 0; v[j].z = 0; v[j].w = 0;
+			if (sidx[j] >= 0 && sidx[j] != ADMMB200_NO_SLOT) v[j] = f[sidx[j]];
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			sx += double(v[j].x); sy += double(v[j].y); sz += double(v[j].z);
+			if (sidx[j] < 0) { const double4 p = fpin[sidx[j] & 0x7fffffff]; sx += p.x; sy += p.y; sz += p.z; } // fp64 pin share (rare)
 		}
 	}
 	if (i >= n) return;
