@@ -541,8 +541,9 @@ def run_b200(args):
     dominant = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * (n_solves / float(n_launch) if k == "ldlt_solve_kernel" else 1.0))
     tr = load_traffic()
     for k in kernels:
-        if k in tr and args.workload == "beam_1m" and world == 1:
-            kernels[k]["traffic"] = tr[k]
+        key = k if k != "ldlt_solve_kernel" else "%s@%s" % (k, args.workload)
+        if key in tr and world == 1 and (args.workload in ("beam_1m", "cloth_512") or k == "ldlt_solve_kernel"):
+            kernels[k]["traffic"] = tr[key]   # dram bytes per launch from the committed ncu --set full capture of this workload
     roofline = dict(kernels[dominant], kernel=dominant)
 
     cfg = common_config(args, scene)
