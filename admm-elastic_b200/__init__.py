@@ -470,11 +470,11 @@ def ldlt_solve_host(rowptr, cols, vals, pos, b):
 
 def ldlt_blocks_solve_host(rowptr, cols, vals, pos, b):
     """Host check of the device's block (supernodal) solve plan (no device): factor with nested dissection, then walk
-    the block plan.  Returns (x, stats) with stats = {blocks, largest, levels_f, levels_b, nnz_out, nnz_inv}."""
+    the block plan.  Returns (x, stats) with stats = {blocks, largest, levels_f, levels_b, nnz_out, nnz_inv, cut, segments}."""
     rowptr, cols, vals, pos, b = _i32(rowptr), _i32(cols), _f64(vals), _f64(pos).ravel(), _f64(b)
     x = np.zeros_like(b)
-    stats = (ctypes.c_longlong * 6)()
+    stats = (ctypes.c_longlong * 8)()
     rc = _host.admmhost_ldlt_blocks_check(rowptr.size - 1, _ip(rowptr), _ip(cols), _dp(vals), _dp(pos), _dp(b), _dp(x), stats)
     if rc:
         raise AdmmError("ldlt block plan failed")
-    return x, dict(zip(("blocks", "largest", "levels_f", "levels_b", "nnz_out", "nnz_inv"), [int(v) for v in stats]))
+    return x, dict(zip(("blocks", "largest", "levels_f", "levels_b", "nnz_out", "nnz_inv", "cut", "segments"), [int(v) for v in stats]))

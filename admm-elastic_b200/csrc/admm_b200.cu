@@ -201,8 +201,8 @@ struct admm_b200_solver {
 	int ld_levels_fwd = 0, ld_levels_bwd = 0, ld_grid = 0, ld_lanes = 4;
 	// block (supernodal) solve, sptrsv_blocks.cuh -- the default; the level-scheduled kernel above stays as ADMM_B200_LDLT_KERNEL=levels
 	bool ld_blocks = false;
-	int lb_levels_f = 0, lb_levels_b = 0;
-	DevBuf<int> lb_blk_of, lb_blk_c0, lb_f_lev_ptr, lb_f_rows, lb_f_rowptr, lb_f_cols, lb_f_lanes, lb_b_lev_ptr, lb_b_cols, lb_b_colptr, lb_b_rows, lb_b_lanes;
+	int lb_levels = 0, lb_cut = 0;
+	DevBuf<int> lb_blk_of, lb_blk_c0, lb_lev_ptr, lb_rows, lb_lanes, lb_f_rowptr, lb_f_cols, lb_b_colptr, lb_b_rows, lb_seg_ptr, lb_seg_begin, lb_seg_end, lb_seg_level;
 	DevBuf<long long> lb_inv_off;
 	DevBuf<double> lb_inv, lb_invT, lb_f_vals, lb_b_vals;
 	DevBuf<double4> lb_t;
@@ -504,6 +504,17 @@ template <int T> void ldlt_launch_T(S *s, LdltParams &P)
 	CK(cudaLaunchCooperativeKernel((void *)ldlt_solve_kernel<T>, dim3(s->ld_grid), dim3(512), args, 0, s->stream));
 }
 
+void fill_ldlt_blocks(S *s, LdltBlkParams &B)
+{
+	B.n = s->ld_n; B.n_levels = s->lb_levels; B.cut = s->lb_cut;
+	B.perm = s->d_ld_perm.p; B.blk_of = s->lb_blk_of.p; B.blk_c0 = s->lb_blk_c0.p; B.inv_off = s->lb_inv_off.p; B.inv = s->lb_inv.p; B.invT = s->lb_invT.p;
+	B.lev_ptr = s->lb_lev_ptr.p; B.rows = s->lb_rows.p; B.lanes = s->lb_lanes.p;
+	B.f_rowptr = s->lb_f_rowptr.p; B.f_cols = s->lb_f_cols.p; B.f_vals = s->lb_f_vals.p;
+	B.b_colptr = s->lb_b_colptr.p; B.b_rows = s->lb_b_rows.p; B.b_vals = s->lb_b_vals.p;
+	B.seg_ptr = s->lb_seg_ptr.p; B.seg_begin = s->lb_seg_begin.p; B.seg_end = s->lb_seg_end.p; B.seg_level = s->lb_seg_level.p;
+	B.D = s->d_ld_D.p; B.t = s->lb_t.p; B.y = s->d_ld_y.p; B.b = nullptr; B.x = nullptr; B.barrier = s->barrier.p; B.active = nullptr;
+}
+
 void launch_ldlt(S *s, const double4 *rhs = nullptr, double4 *out = nullptr, const int *active = nullptr)
 {
 	LdltParams P;
@@ -515,11 +526,8 @@ void launch_ldlt(S *s, const double4 *rhs = nullptr, double4 *out = nullptr, con
 	CK(cudaMemsetAsync(s->barrier.p, 0, sizeof(unsigned int), s->stream));
 	if (s->ld_blocks) {
 		LdltBlkParams B;
-		B.n = s->ld_n; B.n_levels_f = s->lb_levels_f; B.n_levels_b = s->lb_levels_b;
-		B.perm = s->d_ld_perm.p; B.blk_of = s->lb_blk_of.p; B.blk_c0 = s->lb_blk_c0.p; B.inv_off = s->lb_inv_off.p; B.inv = s->lb_inv.p; B.invT = s->lb_invT.p;
-		B.f_lev_ptr = s->lb_f_lev_ptr.p; B.f_rows = s->lb_f_rows.p; B.f_rowptr = s->lb_f_rowptr.p; B.f_cols = s->lb_f_cols.p; B.f_lanes = s->lb_f_lanes.p; B.f_vals = s->lb_f_vals.p;
-		B.b_lev_ptr = s->lb_b_lev_ptr.p; B.b_cols = s->lb_b_cols.p; B.b_colptr = s->lb_b_colptr.p; B.b_rows = s->lb_b_rows.p; B.b_lanes = s->lb_b_lanes.p; B.b_vals = s->lb_b_vals.p;
-		B.D = s->d_ld_D.p; B.t = s->lb_t.p; B.y = s->d_ld_y.p; B.b = P.b; B.x = P.x; B.barrier = s->barrier.p; B.active = active;
+		fill_ldlt_blocks(s, B);
+		B.b = P.b; B.x = P.x; B.active = active;
 		void *args[] = {&B};
 		fine_begin(s, 2);
 		CK(cudaLaunchCooperativeKernel((void *)ldlt_blocks_kernel, dim3(s->ld_grid), dim3(1024), args, 0, s->stream));
@@ -575,12 +583,7 @@ void launch_uzawa(S *s)
 	if (s->ld_blocks) {
 		// one persistent cooperative launch: detection, the conjugate-gradient loop and every A^-1 inside (uzawa_blocks.cuh)
 		UzBlkParams Z;
-		LdltBlkParams &B = Z.L;
-		B.n = s->ld_n; B.n_levels_f = s->lb_levels_f; B.n_levels_b = s->lb_levels_b;
-		B.perm = s->d_ld_perm.p; B.blk_of = s->lb_blk_of.p; B.blk_c0 = s->lb_blk_c0.p; B.inv_off = s->lb_inv_off.p; B.inv = s->lb_inv.p; B.invT = s->lb_invT.p;
-		B.f_lev_ptr = s->lb_f_lev_ptr.p; B.f_rows = s->lb_f_rows.p; B.f_rowptr = s->lb_f_rowptr.p; B.f_cols = s->lb_f_cols.p; B.f_lanes = s->lb_f_lanes.p; B.f_vals = s->lb_f_vals.p;
-		B.b_lev_ptr = s->lb_b_lev_ptr.p; B.b_cols = s->lb_b_cols.p; B.b_colptr = s->lb_b_colptr.p; B.b_rows = s->lb_b_rows.p; B.b_lanes = s->lb_b_lanes.p; B.b_vals = s->lb_b_vals.p;
-		B.D = s->d_ld_D.p; B.t = s->lb_t.p; B.y = s->d_ld_y.p; B.b = nullptr; B.x = nullptr; B.barrier = s->barrier.p; B.active = nullptr;
+		fill_ldlt_blocks(s, Z.L);
 		Z.U = U;
 		Z.cand = s->surface_inds.empty() ? nullptr : s->uz_cand.p; Z.n_cand = (int)s->surface_inds.size();
 		Z.ck = std::sqrt(std::max(0.0, s->constraint_w)); Z.max_iters = s->uz_max_iters;
@@ -1017,18 +1020,18 @@ void build_ldlt(S *s)
 		s->ld_blocks = !(ek && std::string(ek) == "levels");
 	}
 	if (s->ld_blocks) {
-		LdltBlockPlan B = plan_ldlt_blocks(n, Lp.data(), Li.data(), Lx.data());
-		s->lb_levels_f = B.n_levels_f; s->lb_levels_b = B.n_levels_b;
+		LdltBlockPlan B = plan_ldlt_blocks(n, Lp.data(), Li.data(), Lx.data(), s->n_sms, 1024);
+		s->lb_levels = B.n_levels_f; s->lb_cut = B.cut;
 		s->d_ld_perm.upload(s->ld_perm, s->stream);
 		s->lb_blk_of.upload(B.blk_of, s->stream); s->lb_blk_c0.upload(B.blk_c0, s->stream); s->lb_inv_off.upload(B.inv_off, s->stream);
 		s->lb_inv.upload(B.inv, s->stream); s->lb_invT.upload(B.invT, s->stream);
 		auto nonempty_i = [](std::vector<int> &v) { if (v.empty()) v.push_back(0); };
 		auto nonempty_d = [](std::vector<double> &v) { if (v.empty()) v.push_back(0.0); };
 		nonempty_i(B.f_cols); nonempty_d(B.f_vals); nonempty_i(B.b_rows); nonempty_d(B.b_vals);
-		s->lb_f_lev_ptr.upload(B.f_lev_ptr, s->stream); s->lb_f_rows.upload(B.f_rows, s->stream); s->lb_f_rowptr.upload(B.f_rowptr, s->stream);
-		s->lb_f_cols.upload(B.f_cols, s->stream); s->lb_f_vals.upload(B.f_vals, s->stream); s->lb_f_lanes.upload(B.f_lanes, s->stream);
-		s->lb_b_lev_ptr.upload(B.b_lev_ptr, s->stream); s->lb_b_cols.upload(B.b_cols, s->stream); s->lb_b_colptr.upload(B.b_colptr, s->stream);
-		s->lb_b_rows.upload(B.b_rows, s->stream); s->lb_b_vals.upload(B.b_vals, s->stream); s->lb_b_lanes.upload(B.b_lanes, s->stream);
+		s->lb_lev_ptr.upload(B.f_lev_ptr, s->stream); s->lb_rows.upload(B.f_rows, s->stream); s->lb_lanes.upload(B.lanes, s->stream);
+		s->lb_f_rowptr.upload(B.f_rowptr, s->stream); s->lb_f_cols.upload(B.f_cols, s->stream); s->lb_f_vals.upload(B.f_vals, s->stream);
+		s->lb_b_colptr.upload(B.b_colptr, s->stream); s->lb_b_rows.upload(B.b_rows, s->stream); s->lb_b_vals.upload(B.b_vals, s->stream);
+		s->lb_seg_ptr.upload(B.seg_ptr, s->stream); s->lb_seg_begin.upload(B.seg_begin, s->stream); s->lb_seg_end.upload(B.seg_end, s->stream); s->lb_seg_level.upload(B.seg_level, s->stream);
 		s->d_ld_D.upload(s->ld_D, s->stream);
 		s->d_ld_y.alloc(n); s->lb_t.alloc(n);
 		CK(cudaStreamSynchronize(s->stream));
@@ -1037,8 +1040,8 @@ void build_ldlt(S *s)
 		require(occ >= 1, "ldlt block kernel does not fit on an SM");
 		s->ld_grid = s->n_sms;
 		char buf[320];
-		snprintf(buf, sizeof(buf), "ldlt blocks: n %d, nnz(L) %lld, %d blocks (largest %d), %lld entries outside + %lld in the inverted diagonal blocks, %d + %d levels, %d CTAs x 1024", n, (long long)Lp[n],
-			B.n_blocks, B.max_block, B.nnz_out, B.nnz_inv, B.n_levels_f, B.n_levels_b, s->ld_grid);
+		snprintf(buf, sizeof(buf), "ldlt blocks: n %d, nnz(L) %lld, %d blocks (largest %d), %lld entries outside + %lld in the inverted diagonal blocks, %d levels of which %d in the CTA-local bottom forest (%d segments), %d CTAs x 1024", n, (long long)Lp[n],
+			B.n_blocks, B.max_block, B.nnz_out, B.nnz_inv, B.n_levels_f, B.cut, (int)B.seg_ptr.back(), s->ld_grid);
 		s->gs_info = buf;
 	} else {
 	// CSR of strictly lower L (row gather for the forward solve)
@@ -2035,14 +2038,14 @@ int admm_b200_plan_bank_stats(int n, const int *rowptr, const int *cols, const d
 }
 
 // Host-only: plans the block solve for a factor (ldlt_blocks.hpp) and applies it on the host to one right-hand side
-// (n values), exactly as the device kernel walks it.  stats[6] = {blocks, largest block, forward levels, backward levels,
-// entries outside the diagonal blocks, entries of the inverted diagonal blocks}.
+// (n values), exactly as the device kernel walks it.  stats[8] = {blocks, largest block, forward levels, backward levels,
+// entries outside the diagonal blocks, entries of the inverted diagonal blocks, cut level of the bottom forest, segments}.
 int admm_b200_ldlt_blocks_check(int n, const int *perm, const int *Lp, const int *Li, const double *Lx, const double *D, const double *b, double *x, long long *stats)
 {
 	try {
 		LdltBlockPlan B = plan_ldlt_blocks(n, Lp, Li, Lx);
 		ldlt_blocks_solve_host(B, perm, D, b, x);
-		if (stats) { stats[0] = B.n_blocks; stats[1] = B.max_block; stats[2] = B.n_levels_f; stats[3] = B.n_levels_b; stats[4] = B.nnz_out; stats[5] = B.nnz_inv; }
+		if (stats) { stats[0] = B.n_blocks; stats[1] = B.max_block; stats[2] = B.n_levels_f; stats[3] = B.n_levels_b; stats[4] = B.nnz_out; stats[5] = B.nnz_inv; stats[6] = B.cut; stats[7] = (long long)B.seg_ptr.back(); }
 		return 0;
 	} catch (std::exception &e) {
 		g_create_error = e.what();

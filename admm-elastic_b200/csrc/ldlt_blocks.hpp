@@ -38,6 +38,15 @@ struct LdltBlockPlan {
 	std::vector<int> b_lanes;
 	long long nnz_out = 0, nnz_inv = 0;
 	int max_block = 0;
+	// The bottom forest: blocks below level `cut` form independent subtrees of the block tree; every CTA of the solve
+	// kernel owns some of them and walks them level by level with CTA barriers only.  A segment = the rows of one level of
+	// one subtree, f_rows[begin, end), executed in this order forward and in reverse order backward; only levels >= cut
+	// need grid barriers.  lanes[4 * level + {0, 1, 2, 3}] = threads per row in the forward gather / forward dense /
+	// backward gather / backward dense phase.
+	int cut = 0, n_ctas = 0;
+	std::vector<int> seg_ptr;         // [n_ctas + 1] into the segment arrays
+	std::vector<int> seg_begin, seg_end, seg_level;
+	std::vector<int> lanes;           // [4 * n_levels_f]
 };
 
 // Threads per row of a phase: about 8 entries per thread (4 loads in flight, twice), but never fewer rows in flight than the
@@ -53,7 +62,7 @@ inline int ldlt_pow2_lanes(double avg_len, int n_rows = 1 << 30, int grid_thread
 
 // Lp/Li/Lx: strictly lower unit L in CSC with ascending row indices per column (what sparse::factor_ldlt and Eigen's
 // SimplicialLDLT produce).
-inline LdltBlockPlan plan_ldlt_blocks(int n, const int *Lp, const int *Li, const double *Lx, int merge_up_to = 32, int max_block = 4096)
+inline LdltBlockPlan plan_ldlt_blocks(int n, const int *Lp, const int *Li, const double *Lx, int n_ctas = 148, int cta_threads = 1024, int merge_up_to = 32, int max_block = 4096)
 {
 	LdltBlockPlan P;
 	P.n = n;
@@ -187,6 +196,114 @@ inline LdltBlockPlan plan_ldlt_blocks(int n, const int *Lp, const int *Li, const
 	};
 	bucket(flev, P.n_levels_f, P.f_lev_ptr, P.f_rows, P.f_rowptr, P.f_lanes);
 	bucket(blev, P.n_levels_b, P.b_lev_ptr, P.b_cols, P.b_colptr, P.b_lanes);
+
+	// ---- the bottom forest ----
+	// parent block = the block of the elimination-tree parent of a block's last column; a block only reads blocks of its
+	// own subtree, so subtrees whose roots sit below the cut are independent of each other
+	std::vector<int> bparent(P.n_blocks, -1);
+	for (int b = 0; b < P.n_blocks; ++b) {
+		const int last = start[b + 1] - 1;
+		if (Lp[last + 1] > Lp[last]) bparent[b] = P.blk_of[Li[Lp[last]]];
+	}
+	// every block a row reads must be a descendant of the row's block: pre-order intervals of the block tree (children have
+	// smaller indices than their parent, so one backward sweep sizes the subtrees and one forward... parents first) decide
+	bool is_tree = true;
+	for (int b = 0; b < P.n_blocks && is_tree; ++b) if (bparent[b] >= 0 && (bparent[b] <= b || flev[bparent[b]] <= flev[b])) is_tree = false;
+	if (is_tree) {
+		std::vector<int> size(P.n_blocks, 1), tin(P.n_blocks, 0), next_child(P.n_blocks, 0);
+		for (int b = 0; b < P.n_blocks; ++b) if (bparent[b] >= 0) size[bparent[b]] += size[b];
+		// pre-order number: roots in index order; a child's interval starts inside its parent's
+		int counter = 0;
+		for (int b = P.n_blocks - 1; b >= 0; --b) {
+			if (bparent[b] < 0) { tin[b] = counter; counter += size[b]; next_child[b] = tin[b] + 1; }
+			else { tin[b] = next_child[bparent[b]]; next_child[bparent[b]] += size[b]; next_child[b] = tin[b] + 1; }
+		}
+		for (int i = 0; i < n && is_tree; ++i) {
+			const int target = P.blk_of[i];
+			for (int q = P.f_rowptr[i]; q < P.f_rowptr[i + 1]; ++q) {
+				const int a = P.blk_of[P.f_cols[q]];
+				if (tin[a] < tin[target] || tin[a] >= tin[target] + size[target]) { is_tree = false; break; }
+			}
+		}
+	}
+	P.n_ctas = n_ctas;
+	P.cut = 0;
+	if (is_tree) {
+		// the highest cut that still leaves at least one subtree per CTA
+		for (int cut = P.n_levels_f; cut >= 1; --cut) {
+			int roots = 0;
+			for (int b = 0; b < P.n_blocks; ++b) if (flev[b] < cut && (bparent[b] < 0 || flev[bparent[b]] >= cut)) ++roots;
+			if (roots >= n_ctas || cut == 1) { P.cut = roots >= n_ctas ? cut : 0; break; }
+		}
+	}
+	// row range of (level, block) inside f_rows: blocks were bucketed in ascending order within a level
+	std::vector<int> blk_pos(P.n_blocks, 0);
+	{
+		std::vector<int> fill(P.f_lev_ptr.begin(), P.f_lev_ptr.end() - 1);
+		for (int b = 0; b < P.n_blocks; ++b) { blk_pos[b] = fill[flev[b]]; fill[flev[b]] += start[b + 1] - start[b]; }
+	}
+	P.seg_ptr.assign(n_ctas + 1, 0);
+	if (P.cut > 0) {
+		// subtree root of every bottom block, work per subtree, longest-processing-time assignment to the CTAs
+		std::vector<int> root(P.n_blocks, -1);
+		for (int b = P.n_blocks - 1; b >= 0; --b) {
+			if (flev[b] >= P.cut) continue;
+			root[b] = (bparent[b] >= 0 && flev[bparent[b]] < P.cut) ? root[bparent[b]] : b; // parents have larger indices: already set
+		}
+		std::vector<double> work(P.n_blocks, 0.0);
+		for (int b = 0; b < P.n_blocks; ++b) {
+			if (root[b] < 0) continue;
+			const double s_ = start[b + 1] - start[b];
+			double w = 0.5 * s_ * (s_ - 1) + 8.0 * s_;
+			for (int i = start[b]; i < start[b + 1]; ++i) w += P.f_rowptr[i + 1] - P.f_rowptr[i];
+			work[root[b]] += w;
+		}
+		std::vector<int> roots;
+		for (int b = 0; b < P.n_blocks; ++b) if (root[b] == b) roots.push_back(b);
+		std::sort(roots.begin(), roots.end(), [&](int a, int b) { return work[a] != work[b] ? work[a] > work[b] : a < b; });
+		std::vector<double> load(n_ctas, 0.0);
+		std::vector<int> cta_of(P.n_blocks, -1);
+		for (int r : roots) {
+			int best = 0;
+			for (int c = 1; c < n_ctas; ++c) if (load[c] < load[best]) best = c;
+			cta_of[r] = best; load[best] += work[r];
+		}
+		// segments: per CTA its subtrees one after the other, inside a subtree level by level; consecutive blocks of one
+		// level and one subtree that are adjacent in f_rows merge into one segment
+		std::vector<std::vector<int>> blocks_of_cta(n_ctas);
+		for (int b = 0; b < P.n_blocks; ++b) if (root[b] >= 0) blocks_of_cta[cta_of[root[b]]].push_back(b);
+		for (int c = 0; c < n_ctas; ++c) {
+			std::vector<int> &bl = blocks_of_cta[c];
+			std::sort(bl.begin(), bl.end(), [&](int a, int b) {
+				if (root[a] != root[b]) return root[a] < root[b];
+				if (flev[a] != flev[b]) return flev[a] < flev[b];
+				return a < b;
+			});
+			for (size_t k = 0; k < bl.size(); ++k) {
+				const int b = bl[k], len = start[b + 1] - start[b];
+				const bool extend = !P.seg_begin.empty() && (int)P.seg_begin.size() > P.seg_ptr[c] && k > 0 && root[bl[k - 1]] == root[b] && flev[bl[k - 1]] == flev[b] && P.seg_end.back() == blk_pos[b];
+				if (extend) P.seg_end.back() += len;
+				else { P.seg_begin.push_back(blk_pos[b]); P.seg_end.push_back(blk_pos[b] + len); P.seg_level.push_back(flev[b]); }
+			}
+			P.seg_ptr[c + 1] = (int)P.seg_begin.size();
+		}
+	}
+	if (P.seg_begin.empty()) { P.seg_begin.push_back(0); P.seg_end.push_back(0); P.seg_level.push_back(0); }
+	// threads per row: inside the forest a row is shared by the threads of ONE CTA, above it by the whole grid
+	P.lanes.assign(4 * (size_t)P.n_levels_f, 1);
+	for (int l = 0; l < P.n_levels_f; ++l) {
+		double fo = 0, bo = 0, dn = 0;
+		const int cnt = P.f_lev_ptr[l + 1] - P.f_lev_ptr[l];
+		for (int k = P.f_lev_ptr[l]; k < P.f_lev_ptr[l + 1]; ++k) {
+			const int i = P.f_rows[k], b = P.blk_of[i], s_ = start[b + 1] - start[b];
+			fo += P.f_rowptr[i + 1] - P.f_rowptr[i]; bo += P.b_colptr[i + 1] - P.b_colptr[i]; dn += 0.5 * (s_ - 1);
+		}
+		const bool bottom = l < P.cut;
+		const int threads = bottom ? cta_threads : n_ctas * cta_threads, rows = bottom ? std::max(1, cnt / std::max(1, 2 * n_ctas)) : cnt;
+		int t[4] = {ldlt_pow2_lanes(cnt ? fo / cnt : 0.0, rows, threads), ldlt_pow2_lanes(cnt ? dn / cnt : 0.0, rows, threads),
+			ldlt_pow2_lanes(cnt ? bo / cnt : 0.0, rows, threads), ldlt_pow2_lanes(cnt ? dn / cnt : 0.0, rows, threads)};
+		for (int k = 0; k < 4; ++k) P.lanes[4 * l + k] = bottom ? std::min(t[k], 32) : t[k];
+	}
 	return P;
 }
 
@@ -195,6 +312,46 @@ inline void ldlt_blocks_solve_host(const LdltBlockPlan &P, const int *perm, cons
 {
 	const int n = P.n;
 	std::vector<double> t(n), y(n);
+	// the device's order: the bottom forest CTA by CTA, segment by segment, then the levels above the cut; backward in
+	// reverse, with the SAME (forward) levels -- an ancestor always sits on a higher level than its descendants
+	auto fwd = [&](int k0, int k1) {
+		for (int k = k0; k < k1; ++k) {
+			const int i = P.f_rows[k];
+			double s = 0;
+			for (int q = P.f_rowptr[i]; q < P.f_rowptr[i + 1]; ++q) s += P.f_vals[q] * y[P.f_cols[q]];
+			t[i] = b[perm[i]] - s;
+		}
+		for (int k = k0; k < k1; ++k) {
+			const int i = P.f_rows[k], bl = P.blk_of[i], c0 = P.blk_c0[bl], r = i - c0;
+			const double *inv = &P.inv[(size_t)P.inv_off[bl] + (size_t)r * (r - 1) / 2];
+			double s = t[i];
+			for (int c = 0; c < r; ++c) s += inv[c] * t[c0 + c];
+			y[i] = s;
+		}
+	};
+	auto bwd = [&](int k0, int k1) {
+		for (int k = k0; k < k1; ++k) {
+			const int j = P.f_rows[k];
+			double s = 0;
+			for (int q = P.b_colptr[j]; q < P.b_colptr[j + 1]; ++q) s += P.b_vals[q] * y[P.b_rows[q]];
+			t[j] = y[j] / D[j] - s;
+		}
+		for (int k = k0; k < k1; ++k) {
+			const int j = P.f_rows[k], bl = P.blk_of[j], c0 = P.blk_c0[bl], s_ = P.blk_c0[bl + 1] - c0, r = j - c0;
+			const double *invT = &P.invT[(size_t)P.inv_off[bl] + (size_t)r * (s_ - 1) - (size_t)r * (r - 1) / 2];
+			double s = t[j];
+			for (int c = r + 1; c < s_; ++c) s += invT[c - r - 1] * t[c0 + c];
+			y[j] = s;
+		}
+	};
+	if (P.n_ctas > 0 && !P.seg_ptr.empty()) {
+		for (int c = 0; c < P.n_ctas; ++c) for (int sg = P.seg_ptr[c]; sg < P.seg_ptr[c + 1]; ++sg) fwd(P.seg_begin[sg], P.seg_end[sg]);
+		for (int l = P.cut; l < P.n_levels_f; ++l) fwd(P.f_lev_ptr[l], P.f_lev_ptr[l + 1]);
+		for (int l = P.n_levels_f - 1; l >= P.cut; --l) bwd(P.f_lev_ptr[l], P.f_lev_ptr[l + 1]);
+		for (int c = 0; c < P.n_ctas; ++c) for (int sg = P.seg_ptr[c + 1] - 1; sg >= P.seg_ptr[c]; --sg) bwd(P.seg_begin[sg], P.seg_end[sg]);
+		for (int k = 0; k < n; ++k) x[perm[k]] = y[k];
+		return;
+	}
 	for (int l = 0; l < P.n_levels_f; ++l) {
 		for (int k = P.f_lev_ptr[l]; k < P.f_lev_ptr[l + 1]; ++k) {
 			const int i = P.f_rows[k];

@@ -13,15 +13,18 @@
 namespace admmb200 {
 
 struct LdltBlkParams {
-	int n, n_levels_f, n_levels_b;
+	int n, n_levels, cut;            // block levels; levels below `cut` belong to the bottom forest (CTA-local, no grid barrier)
 	const int *perm;                 // [n] perm[new] = old
 	const int *blk_of, *blk_c0;      // [n], [n_blocks + 1]
 	const long long *inv_off;        // [n_blocks]
 	const double *inv, *invT;        // packed strictly-lower inverse rows / transposed rows
-	const int *f_lev_ptr, *f_rows, *f_rowptr, *f_cols, *f_lanes;
+	const int *lev_ptr, *rows;       // rows (= columns) ordered by the level of their block
+	const int *lanes;                // [4 * n_levels] threads per row: forward gather, forward dense, backward gather, backward dense
+	const int *f_rowptr, *f_cols;    // entries of a row LEFT of its block (CSR)
 	const double *f_vals;
-	const int *b_lev_ptr, *b_cols, *b_colptr, *b_rows, *b_lanes;
+	const int *b_colptr, *b_rows;    // entries of a column BELOW its block (CSC)
 	const double *b_vals;
+	const int *seg_ptr, *seg_begin, *seg_end, *seg_level; // the forest: per CTA its segments (ranges of `rows`) in forward order
 	const double *D;
 	double4 *t, *y;                  // work, permuted numbering
 	const double4 *b;                // node order
@@ -74,95 +77,88 @@ __device__ __forceinline__ void blk_row_dot(const double *__restrict__ vals, con
 	}
 }
 
+// One phase over the rows rows[k0, k1), shared by `n_thr` threads of which this one is number `t`:
+//   PHASE 0  forward gather   t_i = b_i - sum_{j left of the block} L_ij y_j
+//   PHASE 1  forward dense    y_i = t_i + sum_{k < i in the block} Linv_ik t_k
+//   PHASE 2  backward gather  t_j = y_j / D_j - sum_{i below the block} L_ij x_i
+//   PHASE 3  backward dense   x_j = t_j + sum_{k > j in the block} Linv_kj t_k
+// Every thread of the CTA runs the same trip count (blk_reduce may hold CTA barriers).
+template <int PHASE>
+__device__ __forceinline__ void blk_phase(const LdltBlkParams &P, const double4 *b, double4 *x, int k0, int k1, int T, int t, int n_thr, double *s_part)
+{
+	const int sub = t & (T - 1), group = t / T, n_groups = n_thr / T;
+	for (int kb = k0; kb < k1; kb += n_groups) {
+		const int k = kb + group;
+		const bool act = k < k1;
+		const int i = act ? __ldg(&P.rows[k]) : 0;
+		double sx = 0, sy = 0, sz = 0;
+		if (act) {
+			if (PHASE == 0) blk_row_dot<true>(P.f_vals, P.f_cols, P.y, __ldg(&P.f_rowptr[i]), __ldg(&P.f_rowptr[i + 1]), sub, T, sx, sy, sz);
+			else if (PHASE == 2) blk_row_dot<true>(P.b_vals, P.b_rows, P.y, __ldg(&P.b_colptr[i]), __ldg(&P.b_colptr[i + 1]), sub, T, sx, sy, sz); // rows below the block: already final
+			else {
+				const int bl = __ldg(&P.blk_of[i]), c0 = __ldg(&P.blk_c0[bl]), r = i - c0;
+				if (PHASE == 1) blk_row_dot<false>(P.inv + __ldg(&P.inv_off[bl]) + (long long)r * (r - 1) / 2, nullptr, P.t + c0, 0, r, sub, T, sx, sy, sz);
+				else {
+					const int s = __ldg(&P.blk_c0[bl + 1]) - c0;
+					blk_row_dot<false>(P.invT + __ldg(&P.inv_off[bl]) + (long long)r * (s - 1) - (long long)r * (r - 1) / 2, nullptr, P.t + c0 + r + 1, 0, s - r - 1, sub, T, sx, sy, sz);
+				}
+			}
+		}
+		blk_reduce(sx, sy, sz, T, s_part);
+		if (act && sub == 0) {
+			if (PHASE == 0) { const double4 bi = ld_node_cg(&b[__ldg(&P.perm[i])]); st_node(&P.t[i], bi.x - sx, bi.y - sy, bi.z - sz); }
+			else if (PHASE == 1) { const double4 ti = ld_node_cg(&P.t[i]); st_node(&P.y[i], ti.x + sx, ti.y + sy, ti.z + sz); }
+			else if (PHASE == 2) { const double4 yj = ld_node_cg(&P.y[i]); const double d = __ldg(&P.D[i]); st_node(&P.t[i], yj.x / d - sx, yj.y / d - sy, yj.z / d - sz); }
+			else {
+				const double4 tj = ld_node_cg(&P.t[i]);
+				const double rx = tj.x + sx, ry = tj.y + sy, rz = tj.z + sz;
+				st_node(&P.y[i], rx, ry, rz);
+				st_node(&x[__ldg(&P.perm[i])], rx, ry, rz);
+			}
+		}
+	}
+}
+
 // The whole solve x = P^T L^-T D^-1 L^-1 P b as a device function: the standalone kernel below and the persistent UzawaCG
-// kernel (uzawa.cuh) call it.  Every thread of the (cooperative) grid must call it; it ends with a grid barrier.
+// kernel (uzawa_blocks.cuh) call it.  Every thread of the (cooperative) grid must call it; it ends with a grid barrier.
+// The bottom forest (levels < cut) is walked CTA by CTA with CTA barriers only -- its subtrees are independent of each
+// other -- so only the 2 x (n_levels - cut) phases above the cut cost a grid barrier per direction.
 __device__ __forceinline__ void ldlt_blocks_solve(const LdltBlkParams &P, const double4 *b, double4 *x, unsigned int &bar_target, double *s_part)
 {
-	const int tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
-
+	const int ltid = threadIdx.x, lthr = blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x, gthr = gridDim.x * blockDim.x;
+	const int sg0 = __ldg(&P.seg_ptr[blockIdx.x]), sg1 = __ldg(&P.seg_ptr[blockIdx.x + 1]);
 	// ---------------- forward: y = L^-1 P b ----------------
-	for (int lv = 0; lv < P.n_levels_f; ++lv) {
-		const int k0 = P.f_lev_ptr[lv], k1 = P.f_lev_ptr[lv + 1];
-		{
-			const int T = P.f_lanes[2 * lv], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
-			for (int kb = k0; kb < k1; kb += n_groups) {
-				const int k = kb + group;
-				const bool act = k < k1;
-				const int i = act ? __ldg(&P.f_rows[k]) : 0;
-				double sx = 0, sy = 0, sz = 0;
-				if (act) blk_row_dot<true>(P.f_vals, P.f_cols, P.y, __ldg(&P.f_rowptr[i]), __ldg(&P.f_rowptr[i + 1]), sub, T, sx, sy, sz);
-				blk_reduce(sx, sy, sz, T, s_part);
-				if (act && sub == 0) {
-					const double4 bi = ld_node_cg(&b[__ldg(&P.perm[i])]);
-					st_node(&P.t[i], bi.x - sx, bi.y - sy, bi.z - sz);
-				}
-			}
-		}
+	for (int sg = sg0; sg < sg1; ++sg) {
+		const int k0 = __ldg(&P.seg_begin[sg]), k1 = __ldg(&P.seg_end[sg]), lv = __ldg(&P.seg_level[sg]);
+		blk_phase<0>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv]), ltid, lthr, s_part);
+		__syncthreads();
+		blk_phase<1>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 1]), ltid, lthr, s_part);
+		__syncthreads();
+	}
+	if (P.cut > 0) grid_barrier(P.barrier, bar_target, gridDim.x);
+	for (int lv = P.cut; lv < P.n_levels; ++lv) {
+		const int k0 = __ldg(&P.lev_ptr[lv]), k1 = __ldg(&P.lev_ptr[lv + 1]);
+		blk_phase<0>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
-		{
-			const int T = P.f_lanes[2 * lv + 1], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
-			for (int kb = k0; kb < k1; kb += n_groups) {
-				const int k = kb + group;
-				const bool act = k < k1;
-				const int i = act ? __ldg(&P.f_rows[k]) : 0;
-				double sx = 0, sy = 0, sz = 0;
-				if (act) {
-					const int bl = __ldg(&P.blk_of[i]), c0 = __ldg(&P.blk_c0[bl]), r = i - c0;
-					const double *inv = P.inv + __ldg(&P.inv_off[bl]) + (long long)r * (r - 1) / 2;
-					blk_row_dot<false>(inv, nullptr, P.t + c0, 0, r, sub, T, sx, sy, sz);
-				}
-				blk_reduce(sx, sy, sz, T, s_part);
-				if (act && sub == 0) {
-					const double4 ti = ld_node_cg(&P.t[i]);
-					st_node(&P.y[i], ti.x + sx, ti.y + sy, ti.z + sz);
-				}
-			}
-		}
+		blk_phase<1>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 1]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
 	}
-	// ---------------- backward: x = P^T L^-T D^-1 y ----------------
-	for (int lv = 0; lv < P.n_levels_b; ++lv) {
-		const int k0 = P.b_lev_ptr[lv], k1 = P.b_lev_ptr[lv + 1];
-		{
-			const int T = P.b_lanes[2 * lv], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
-			for (int kb = k0; kb < k1; kb += n_groups) {
-				const int k = kb + group;
-				const bool act = k < k1;
-				const int j = act ? __ldg(&P.b_cols[k]) : 0;
-				double sx = 0, sy = 0, sz = 0;
-				if (act) blk_row_dot<true>(P.b_vals, P.b_rows, P.y, __ldg(&P.b_colptr[j]), __ldg(&P.b_colptr[j + 1]), sub, T, sx, sy, sz); // rows below the block: already final
-				blk_reduce(sx, sy, sz, T, s_part);
-				if (act && sub == 0) {
-					const double4 yj = ld_node_cg(&P.y[j]);
-					const double d = __ldg(&P.D[j]);
-					st_node(&P.t[j], yj.x / d - sx, yj.y / d - sy, yj.z / d - sz);
-				}
-			}
-		}
+	// ---------------- backward: x = P^T L^-T D^-1 y, the same levels in reverse (an ancestor sits on a higher level) ----------------
+	for (int lv = P.n_levels - 1; lv >= P.cut; --lv) {
+		const int k0 = __ldg(&P.lev_ptr[lv]), k1 = __ldg(&P.lev_ptr[lv + 1]);
+		blk_phase<2>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 2]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
-		{
-			const int T = P.b_lanes[2 * lv + 1], sub = tid & (T - 1), group = tid / T, n_groups = n_threads / T;
-			for (int kb = k0; kb < k1; kb += n_groups) {
-				const int k = kb + group;
-				const bool act = k < k1;
-				const int j = act ? __ldg(&P.b_cols[k]) : 0;
-				double sx = 0, sy = 0, sz = 0;
-				if (act) {
-					const int bl = __ldg(&P.blk_of[j]), c0 = __ldg(&P.blk_c0[bl]), s = __ldg(&P.blk_c0[bl + 1]) - c0, r = j - c0;
-					const double *invT = P.invT + __ldg(&P.inv_off[bl]) + (long long)r * (s - 1) - (long long)r * (r - 1) / 2;
-					blk_row_dot<false>(invT, nullptr, P.t + c0 + r + 1, 0, s - r - 1, sub, T, sx, sy, sz);
-				}
-				blk_reduce(sx, sy, sz, T, s_part);
-				if (act && sub == 0) {
-					const double4 tj = ld_node_cg(&P.t[j]);
-					const double rx = tj.x + sx, ry = tj.y + sy, rz = tj.z + sz;
-					st_node(&P.y[j], rx, ry, rz);
-					st_node(&x[__ldg(&P.perm[j])], rx, ry, rz);
-				}
-			}
-		}
+		blk_phase<3>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 3]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
 	}
+	for (int sg = sg1 - 1; sg >= sg0; --sg) {
+		const int k0 = __ldg(&P.seg_begin[sg]), k1 = __ldg(&P.seg_end[sg]), lv = __ldg(&P.seg_level[sg]);
+		blk_phase<2>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 2]), ltid, lthr, s_part);
+		__syncthreads();
+		blk_phase<3>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 3]), ltid, lthr, s_part);
+		__syncthreads();
+	}
+	if (P.cut > 0) grid_barrier(P.barrier, bar_target, gridDim.x); // callers read x right away
 }
 
 __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)

@@ -261,7 +261,8 @@ int admm_b200_plan_bank_stats( int n, const int *rowptr, const int *cols, const 
 
 /* Host-only: the block (supernodal) plan of the L D L^T solve (csrc/ldlt_blocks.hpp) for the factor of admm_b200_set_ldlt's
  * form, applied on the host to one right-hand side b (n values) exactly as the device kernel walks it.
- * stats[6] = {blocks, largest block, forward levels, backward levels, entries outside / inside the inverted diagonal blocks}. */
+ * stats[8] = {blocks, largest block, forward levels, backward levels, entries outside / inside the inverted diagonal blocks,
+ * cut level of the bottom forest (levels below it need no grid barrier), forest segments}. */
 int admm_b200_ldlt_blocks_check( int n, const int *perm, const int *Lp, const int *Li, const double *Lx, const double *D, const double *b, double *x, long long *stats );
 
 /* One line describing which global-solve kernel finalize chose and why (diagnostics). */
