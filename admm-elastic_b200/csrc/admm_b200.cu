@@ -206,6 +206,8 @@ struct admm_b200_solver {
 	DevBuf<long long> lb_inv_off;
 	DevBuf<double> lb_inv, lb_invT, lb_f_vals, lb_b_vals;
 	DevBuf<double4> lb_t;
+	DevBuf<int4> lb_desc_fg, lb_desc_bg, lb_desc_d; DevBuf<long long> lb_desc_off;
+	DevBuf<unsigned long long> lb_prof; // ADMM_B200_LDLT_PROF=1: phase stamps of the last block solve (debug_get "ldlt_prof")
 
 	// settings
 	bool finalized = false;
@@ -513,6 +515,8 @@ void fill_ldlt_blocks(S *s, LdltBlkParams &B)
 	B.b_colptr = s->lb_b_colptr.p; B.b_rows = s->lb_b_rows.p; B.b_vals = s->lb_b_vals.p;
 	B.seg_ptr = s->lb_seg_ptr.p; B.seg_begin = s->lb_seg_begin.p; B.seg_end = s->lb_seg_end.p; B.seg_level = s->lb_seg_level.p;
 	B.D = s->d_ld_D.p; B.t = s->lb_t.p; B.y = s->d_ld_y.p; B.b = nullptr; B.x = nullptr; B.barrier = s->barrier.p; B.active = nullptr;
+	B.prof = s->lb_prof.p;
+	B.desc_fg = s->lb_desc_fg.p; B.desc_bg = s->lb_desc_bg.p; B.desc_d = s->lb_desc_d.p; B.desc_off = s->lb_desc_off.p;
 }
 
 void launch_ldlt(S *s, const double4 *rhs = nullptr, double4 *out = nullptr, const int *active = nullptr)
@@ -1022,6 +1026,10 @@ void build_ldlt(S *s)
 	if (s->ld_blocks) {
 		LdltBlockPlan B = plan_ldlt_blocks(n, Lp.data(), Li.data(), Lx.data(), s->n_sms, 1024);
 		s->lb_levels = B.n_levels_f; s->lb_cut = B.cut;
+		B.build_descriptors(s->ld_perm.data());
+		auto up4 = [&](DevBuf<int4> &dst, const std::vector<int> &src) { dst.alloc(src.size() / 4); CK(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream)); };
+		up4(s->lb_desc_fg, B.desc_fg); up4(s->lb_desc_bg, B.desc_bg); up4(s->lb_desc_d, B.desc_d);
+		s->lb_desc_off.upload(B.desc_off, s->stream);
 		s->d_ld_perm.upload(s->ld_perm, s->stream);
 		s->lb_blk_of.upload(B.blk_of, s->stream); s->lb_blk_c0.upload(B.blk_c0, s->stream); s->lb_inv_off.upload(B.inv_off, s->stream);
 		s->lb_inv.upload(B.inv, s->stream); s->lb_invT.upload(B.invT, s->stream);
@@ -1034,6 +1042,7 @@ void build_ldlt(S *s)
 		s->lb_seg_ptr.upload(B.seg_ptr, s->stream); s->lb_seg_begin.upload(B.seg_begin, s->stream); s->lb_seg_end.upload(B.seg_end, s->stream); s->lb_seg_level.upload(B.seg_level, s->stream);
 		s->d_ld_D.upload(s->ld_D, s->stream);
 		s->d_ld_y.alloc(n); s->lb_t.alloc(n);
+		if (getenv("ADMM_B200_LDLT_PROF")) { s->lb_prof.alloc(4 * (size_t)B.n_levels_f + 8); s->lb_prof.zero(s->stream); }
 		CK(cudaStreamSynchronize(s->stream));
 		int occ = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ldlt_blocks_kernel, 1024, 0));
@@ -1860,6 +1869,15 @@ int admm_b200_debug_get(admm_b200_solver *s, const char *name, double *out, long
 		if (nm == "z" || nm == "u") {
 			require(s->finalized, "debug_get before finalize");
 			if (s->precision == ADMM_B200_FP64) gather_rows<double>(s, nm == "z", out, n_out); else gather_rows<float>(s, nm == "z", out, n_out);
+			return;
+		}
+		if (nm == "ldlt_prof") {
+			require(s->lb_prof.p != nullptr, "debug_get ldlt_prof: set ADMM_B200_LDLT_PROF=1 before finalize");
+			require(n_out >= (long long)s->lb_prof.n, "debug_get: output too small");
+			std::vector<unsigned long long> tmp(s->lb_prof.n);
+			CK(cudaMemcpy(tmp.data(), s->lb_prof.p, tmp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+			const unsigned long long t0 = tmp[0];
+			for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i] ? (double)(tmp[i] - t0) : -1.0; // ns since the start of the solve
 			return;
 		}
 		if (nm == "gs_prof") {

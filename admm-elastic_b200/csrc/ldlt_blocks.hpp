@@ -47,6 +47,23 @@ struct LdltBlockPlan {
 	std::vector<int> seg_ptr;         // [n_ctas + 1] into the segment arrays
 	std::vector<int> seg_begin, seg_end, seg_level;
 	std::vector<int> lanes;           // [4 * n_levels_f]
+	// Everything a phase needs to know about its k-th row in ONE 16-byte load (the phases are chains of dependent L2 / DRAM
+	// round trips; rows -> rowptr -> entries costs two more than this): by position k in f_rows
+	std::vector<int> desc_fg;         // [4 n] {row i, first, one past the last entry in f_cols / f_vals, perm[i]}
+	std::vector<int> desc_bg;         // [4 n] {column j, first, one past the last entry in b_rows / b_vals, perm[j]}
+	std::vector<int> desc_d;          // [4 n] {first column c0 of the block, r = i - c0, block size s, row i}
+	std::vector<long long> desc_off;  // [n] offset of the block's packed inverse
+	void build_descriptors(const int *perm) {
+		desc_fg.resize(4 * (size_t)n); desc_bg.resize(4 * (size_t)n); desc_d.resize(4 * (size_t)n); desc_off.resize((size_t)n);
+		for (int k = 0; k < n; ++k) {
+			const int i = f_rows[k], b = blk_of[i], c0 = blk_c0[b];
+			int *g = &desc_fg[4 * (size_t)k], *h = &desc_bg[4 * (size_t)k], *d = &desc_d[4 * (size_t)k];
+			g[0] = i; g[1] = f_rowptr[i]; g[2] = f_rowptr[i + 1]; g[3] = perm[i];
+			h[0] = i; h[1] = b_colptr[i]; h[2] = b_colptr[i + 1]; h[3] = perm[i];
+			d[0] = c0; d[1] = i - c0; d[2] = blk_c0[b + 1] - c0; d[3] = i;
+			desc_off[k] = inv_off[b];
+		}
+	}
 };
 
 // Threads per row of a phase: about 8 entries per thread (4 loads in flight, twice), but never fewer rows in flight than the

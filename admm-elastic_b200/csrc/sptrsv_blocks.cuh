@@ -25,13 +25,19 @@ struct LdltBlkParams {
 	const int *b_colptr, *b_rows;    // entries of a column BELOW its block (CSC)
 	const double *b_vals;
 	const int *seg_ptr, *seg_begin, *seg_end, *seg_level; // the forest: per CTA its segments (ranges of `rows`) in forward order
+	const int4 *desc_fg, *desc_bg, *desc_d;   // per position k of `rows`: see LdltBlockPlan::build_descriptors
+	const long long *desc_off;
 	const double *D;
 	double4 *t, *y;                  // work, permuted numbering
 	const double4 *b;                // node order
 	double4 *x;                      // node order, out
 	unsigned int *barrier;
 	const int *active;               // NULL, or a device flag: 0 = skip this solve (uzawa.cuh: the CG loop has already ended)
+	unsigned long long *prof;        // NULL, or [4 * n_levels + 8] nanosecond stamps of CTA 0 (ADMM_B200_LDLT_PROF=1, tools/ldlt_prof.py)
 };
+__device__ __forceinline__ void blk_stamp(const LdltBlkParams &P, int slot) {
+	if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); P.prof[slot] = t; }
+}
 
 // Sum over the T threads of a group (T a power of two, 1..1024; groups are aligned, so one never straddles a CTA).
 // T <= 32: shuffles.  T > 32: every warp reduces, lane 0 leaves its partial sum in shared memory, the group's first warp
@@ -90,30 +96,31 @@ __device__ __forceinline__ void blk_phase(const LdltBlkParams &P, const double4 
 	for (int kb = k0; kb < k1; kb += n_groups) {
 		const int k = kb + group;
 		const bool act = k < k1;
-		const int i = act ? __ldg(&P.rows[k]) : 0;
 		double sx = 0, sy = 0, sz = 0;
+		int4 ds = make_int4(0, 0, 0, 0);
+		double dj = 1.0;
 		if (act) {
-			if (PHASE == 0) blk_row_dot<true>(P.f_vals, P.f_cols, P.y, __ldg(&P.f_rowptr[i]), __ldg(&P.f_rowptr[i + 1]), sub, T, sx, sy, sz);
-			else if (PHASE == 2) blk_row_dot<true>(P.b_vals, P.b_rows, P.y, __ldg(&P.b_colptr[i]), __ldg(&P.b_colptr[i + 1]), sub, T, sx, sy, sz); // rows below the block: already final
+			// one 16-byte descriptor instead of the chain rows[k] -> rowptr / block tables -> entries
+			ds = __ldg(PHASE == 0 ? &P.desc_fg[k] : (PHASE == 2 ? &P.desc_bg[k] : &P.desc_d[k]));
+			if (PHASE == 0) blk_row_dot<true>(P.f_vals, P.f_cols, P.y, ds.y, ds.z, sub, T, sx, sy, sz);
+			else if (PHASE == 2) { if (sub == 0) dj = __ldg(&P.D[ds.x]); blk_row_dot<true>(P.b_vals, P.b_rows, P.y, ds.y, ds.z, sub, T, sx, sy, sz); } // rows below the block: already final
 			else {
-				const int bl = __ldg(&P.blk_of[i]), c0 = __ldg(&P.blk_c0[bl]), r = i - c0;
-				if (PHASE == 1) blk_row_dot<false>(P.inv + __ldg(&P.inv_off[bl]) + (long long)r * (r - 1) / 2, nullptr, P.t + c0, 0, r, sub, T, sx, sy, sz);
-				else {
-					const int s = __ldg(&P.blk_c0[bl + 1]) - c0;
-					blk_row_dot<false>(P.invT + __ldg(&P.inv_off[bl]) + (long long)r * (s - 1) - (long long)r * (r - 1) / 2, nullptr, P.t + c0 + r + 1, 0, s - r - 1, sub, T, sx, sy, sz);
-				}
+				const long long off = __ldg(&P.desc_off[k]);
+				const int c0 = ds.x, r = ds.y, s = ds.z;
+				if (PHASE == 1) blk_row_dot<false>(P.inv + off + (long long)r * (r - 1) / 2, nullptr, P.t + c0, 0, r, sub, T, sx, sy, sz);
+				else blk_row_dot<false>(P.invT + off + (long long)r * (s - 1) - (long long)r * (r - 1) / 2, nullptr, P.t + c0 + r + 1, 0, s - r - 1, sub, T, sx, sy, sz);
 			}
 		}
 		blk_reduce(sx, sy, sz, T, s_part);
 		if (act && sub == 0) {
-			if (PHASE == 0) { const double4 bi = ld_node_cg(&b[__ldg(&P.perm[i])]); st_node(&P.t[i], bi.x - sx, bi.y - sy, bi.z - sz); }
-			else if (PHASE == 1) { const double4 ti = ld_node_cg(&P.t[i]); st_node(&P.y[i], ti.x + sx, ti.y + sy, ti.z + sz); }
-			else if (PHASE == 2) { const double4 yj = ld_node_cg(&P.y[i]); const double d = __ldg(&P.D[i]); st_node(&P.t[i], yj.x / d - sx, yj.y / d - sy, yj.z / d - sz); }
+			if (PHASE == 0) { const double4 bi = ld_node_cg(&b[ds.w]); st_node(&P.t[ds.x], bi.x - sx, bi.y - sy, bi.z - sz); }
+			else if (PHASE == 1) { const double4 ti = ld_node_cg(&P.t[ds.w]); st_node(&P.y[ds.w], ti.x + sx, ti.y + sy, ti.z + sz); }
+			else if (PHASE == 2) { const double4 yj = ld_node_cg(&P.y[ds.x]); st_node(&P.t[ds.x], yj.x / dj - sx, yj.y / dj - sy, yj.z / dj - sz); }
 			else {
-				const double4 tj = ld_node_cg(&P.t[i]);
+				const double4 tj = ld_node_cg(&P.t[ds.w]);
 				const double rx = tj.x + sx, ry = tj.y + sy, rz = tj.z + sz;
-				st_node(&P.y[i], rx, ry, rz);
-				st_node(&x[__ldg(&P.perm[i])], rx, ry, rz);
+				st_node(&P.y[ds.w], rx, ry, rz);
+				st_node(&x[__ldg(&P.perm[ds.w])], rx, ry, rz);
 			}
 		}
 	}
@@ -127,6 +134,7 @@ __device__ __forceinline__ void ldlt_blocks_solve(const LdltBlkParams &P, const 
 {
 	const int ltid = threadIdx.x, lthr = blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x, gthr = gridDim.x * blockDim.x;
 	const int sg0 = __ldg(&P.seg_ptr[blockIdx.x]), sg1 = __ldg(&P.seg_ptr[blockIdx.x + 1]);
+	blk_stamp(P, 0);
 	// ---------------- forward: y = L^-1 P b ----------------
 	for (int sg = sg0; sg < sg1; ++sg) {
 		const int k0 = __ldg(&P.seg_begin[sg]), k1 = __ldg(&P.seg_end[sg]), lv = __ldg(&P.seg_level[sg]);
@@ -135,22 +143,29 @@ __device__ __forceinline__ void ldlt_blocks_solve(const LdltBlkParams &P, const 
 		blk_phase<1>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 1]), ltid, lthr, s_part);
 		__syncthreads();
 	}
+	blk_stamp(P, 1); // own forest done
 	if (P.cut > 0) grid_barrier(P.barrier, bar_target, gridDim.x);
+	blk_stamp(P, 2); // everybody's forest done
 	for (int lv = P.cut; lv < P.n_levels; ++lv) {
 		const int k0 = __ldg(&P.lev_ptr[lv]), k1 = __ldg(&P.lev_ptr[lv + 1]);
 		blk_phase<0>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
+		blk_stamp(P, 8 + 4 * lv);
 		blk_phase<1>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 1]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
+		blk_stamp(P, 8 + 4 * lv + 1);
 	}
 	// ---------------- backward: x = P^T L^-T D^-1 y, the same levels in reverse (an ancestor sits on a higher level) ----------------
 	for (int lv = P.n_levels - 1; lv >= P.cut; --lv) {
 		const int k0 = __ldg(&P.lev_ptr[lv]), k1 = __ldg(&P.lev_ptr[lv + 1]);
 		blk_phase<2>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 2]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
+		blk_stamp(P, 8 + 4 * lv + 2);
 		blk_phase<3>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 3]), gtid, gthr, s_part);
 		grid_barrier(P.barrier, bar_target, gridDim.x);
+		blk_stamp(P, 8 + 4 * lv + 3);
 	}
+	blk_stamp(P, 3); // top done
 	for (int sg = sg1 - 1; sg >= sg0; --sg) {
 		const int k0 = __ldg(&P.seg_begin[sg]), k1 = __ldg(&P.seg_end[sg]), lv = __ldg(&P.seg_level[sg]);
 		blk_phase<2>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 2]), ltid, lthr, s_part);
@@ -158,7 +173,9 @@ __device__ __forceinline__ void ldlt_blocks_solve(const LdltBlkParams &P, const 
 		blk_phase<3>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 3]), ltid, lthr, s_part);
 		__syncthreads();
 	}
+	blk_stamp(P, 4); // own forest done (backward)
 	if (P.cut > 0) grid_barrier(P.barrier, bar_target, gridDim.x); // callers read x right away
+	blk_stamp(P, 5);
 }
 
 __global__ void __launch_bounds__(1024, 1) ldlt_blocks_kernel(LdltBlkParams P)
