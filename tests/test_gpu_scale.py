@@ -29,6 +29,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MU, LAM = scenes.lame(*scenes.LAME_SOFT)
 GATE = 1e-4          # x bbox diagonal
+TIGHT = 5e-6         # x bbox diagonal: what the tests assert (measured: <= 1.6e-7 on the beams, profiles/parity_r02i_gpu.jsonl)
 DENSITY = 1522.0
 
 
@@ -124,7 +125,7 @@ def test_100k_beam_production_kernel_vs_reference(pkg, cpu, model):
     assert "static-ownership kernel, 512 threads" in info, info
     assert inner == 2 * 5 * 30
     assert moved > 10 * GATE       # the beam really moved: the comparison is not vacuous
-    assert err < GATE, err
+    assert err < TIGHT, err
 
 
 @pytest.mark.parametrize("gs_parts", [20, 24])
@@ -139,7 +140,7 @@ def test_100k_beam_reference_colouring(pkg, cpu, gs_parts):
     assert nc >= 8, nc
     assert info.startswith("resident"), info
     assert inner == 2 * 5 * 30
-    assert err < GATE, err
+    assert err < TIGHT, err
 
 
 @pytest.mark.parametrize("variant", ["tiled", "768", "0", "stream"])
@@ -158,7 +159,7 @@ def test_100k_beam_other_solve_kernels(pkg, cpu, variant, monkeypatch):
     record("scale_100k_variant_" + variant, err_over_bbox=err, n_colors=nc, info=info)
     want = {"tiled": "tiled kernel", "768": "static-ownership kernel, 768 threads", "0": "table-walking kernel", "stream": "stream"}[variant]
     assert want in info, info
-    assert err < GATE, err
+    assert err < TIGHT, err
 
 
 def test_100k_beam_reference_colouring_148_parts(pkg, cpu):
@@ -168,7 +169,7 @@ def test_100k_beam_reference_colouring_148_parts(pkg, cpu):
     err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 1, iters=5, steps=1, whose_colors="ref", gs_parts=0)
     record("scale_100k_refcolors_148", err_over_bbox=err, n_colors=nc, info=info, ref_seconds=t_ref)
     assert info.startswith("resident"), info
-    assert err < GATE, err
+    assert err < TIGHT, err
 
 
 def test_100k_beam_floor_inside_the_sweep(pkg, cpu):
@@ -180,7 +181,7 @@ def test_100k_beam_floor_inside_the_sweep(pkg, cpu):
     err, info, nc, inner, moved, t_ref = run_pair(pkg, scene, x0, 2, iters=5, steps=2, whose_colors="gpu", gs_parts=16, floor=floor_y)
     record("scale_100k_floor", err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref)
     assert "static-ownership kernel" in info, info
-    assert err < GATE, err
+    assert err < TIGHT, err
 
 
 @pytest.mark.slow
@@ -193,7 +194,7 @@ def test_1m_bench_scene_one_step_vs_reference(pkg, cpu):
     record("scale_1m_bench_scene", err_over_bbox=err, moved_over_bbox=moved, n_colors=nc, info=info, ref_seconds=t_ref, total_seconds=time.time() - t0)
     assert "static-ownership kernel, 512 threads" in info, info
     assert inner == 5 * 30
-    assert err < GATE, err
+    assert err < TIGHT, err
 
 
 @pytest.mark.parametrize("linsolver", [0, 1])
@@ -216,7 +217,7 @@ def test_unstructured_mesh_golden(pkg, linsolver, precision):
     bbox = float(np.linalg.norm(g["verts"].max(0) - g["verts"].min(0)))
     err = float(np.abs(s.get_x() - g["ls%d_x3" % linsolver]).max())
     record("unstructured_golden", linsolver=linsolver, precision=precision, err=err, err_over_bbox=err / bbox)
-    assert err < (2e-6 if precision else GATE * bbox), err
+    assert err < (2e-6 if precision else 4 * TIGHT * bbox), err
 
 
 @pytest.mark.parametrize("precision", [0, 1])
@@ -240,7 +241,7 @@ def test_bunny_golden(pkg, precision):
     err = float(np.abs(x - g["floor_x5"]).max())
     record("bunny_floor_golden", precision=precision, err=err, err_over_bbox=err / bbox, info=s.device().info())
     assert x.reshape(-1, 3)[:, 1].min() >= floor_y - 1e-12 and (np.abs(x.reshape(-1, 3)[:, 1] - floor_y) < 1e-12).any()
-    assert err < (5e-6 if precision else GATE * bbox), err
+    assert err < (5e-6 if precision else 4 * TIGHT * bbox), err
     s = pkg.Solver()
     s.set_options(precision=precision)
     scenes.build_tet_scene(s, scene, 1, linsolver=0, iters=8)
@@ -248,4 +249,4 @@ def test_bunny_golden(pkg, precision):
         s.step()
     err = float(np.abs(s.get_x() - g["ldlt_x3"]).max())
     record("bunny_ldlt_golden", precision=precision, err=err, err_over_bbox=err / bbox, info=s.device().info())
-    assert err < (2e-6 if precision else GATE * bbox), err
+    assert err < (2e-6 if precision else 4 * TIGHT * bbox), err
