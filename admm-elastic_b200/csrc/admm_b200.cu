@@ -900,7 +900,7 @@ void build_mcgs_resident(S *s)
 	}
 	// static-ownership kernel (mcgs_owned_f32.cuh): fp32 sweeps, one lane per node, every part's slices fit the warps' registers
 	s->gs_owned_threads = 0;
-	if (!s->gs_tiled && val_bytes == 4 && lanes == 1 && s->n_colors <= ADMMB200_OWNED_MAX_COLORS) {
+	if (!s->gs_tiled && val_bytes == 4 && lanes == 1 && s->n_colors <= ADMMB200_OWNED_MAX_COLORS && (long long)s->gs_iters * s->n_colors <= 510) { // 9-bit pass tags in its mailbox words
 		const char *eo = getenv("ADMM_B200_GS_OWNED"); // 0: keep the table-walking kernel; 512 / 768: force that variant
 		const int want_threads = eo ? atoi(eo) : -1;
 		int pick = 0;

@@ -18,9 +18,10 @@
 //     "not converged".  Only a CTA in which no node can prove it takes the slow path of the old kernel.
 //   * MAILBOXES instead of a node-indexed exchange array: every part has one slot per halo node in its own
 //     halo order (partition.hpp, plan_mailboxes), a boundary node is stored into the slot of every part
-//     that reads it (first two slot ids in registers), so the reader's polls are coalesced.  The words are
-//     the {value, tag} words of mcgs_resident_f32.cuh (no fence, no flag), double-buffered by sweep parity;
-//     a slot on another GPU is written through the peer mapping (st.relaxed.sys), never read.
+//     that reads it (first two slot ids in registers), so the reader's polls are coalesced.  A word is 16 bytes:
+//     x, y, z and the pass tag of a node in ONE store and ONE polling load (mb_store / mb_load below; "flag in data"
+//     as in mcgs_resident_f32.cuh: no fence, no flag), double-buffered by sweep parity; a slot on another GPU is
+//     written through the peer mapping (st.relaxed.sys), never read.
 //   * x_ref of the part's nodes is staged in the (not yet needed) matrix-value region of shared memory
 //     while r0 = b - A x_ref is formed with the exact fp64 matrix values streamed once; the fp32 values
 //     arrive by TMA bulk copy afterwards.
@@ -66,6 +67,30 @@ __device__ __forceinline__ void owned_gather(const float *__restrict__ s_val, co
 			sx = fmaf(a[j], dv.x, sx); sy = fmaf(a[j], dv.y, sy); sz = fmaf(a[j], dv.z, sz);
 		}
 	}
+}
+
+// One mailbox word of this kernel: the three increments of a node and the pass tag in 16 bytes, written and polled with ONE
+// 128-bit access.  tools/micro/store_bench.cu (profiles/r02t_store_bench.txt): a publishing warp pays ~25 cycles per store
+// instruction plus 4-6 per 128-byte line it touches, and four warps publishing at once share that rate, so three tagged
+// 8-byte words in three arrays per node and reader (round 1) cost three times the instructions and lines of one 16-byte
+// word; the polls shrink from three loads per slot to one.  Measured: 0.380 -> 0.357 ms per solve on the 1M-tet beam,
+// 0.281 -> 0.269 on the 100k-tet beam (same build otherwise).  PTX only promises single-copy atomicity per 64-bit element of the vector, so each half
+// carries its own 16-bit tag and is valid on its own: {x, y_hi16 | tag} and {z, y_lo16 | tag}.  tag = solve sequence
+// (7 bits) << 9 | pass + 1 (< 512): a slot is rewritten every sweep of every solve, so a stale word can never carry the
+// tag a reader is waiting for.
+__device__ __forceinline__ void mb_store(ulonglong2 *p, float x, float y, float z, unsigned int tag16, bool peer) {
+	const unsigned int yb = __float_as_uint(y);
+	const unsigned long long a = (unsigned long long)__float_as_uint(x) | ((unsigned long long)((yb & 0xffff0000u) | tag16) << 32);
+	const unsigned long long b = (unsigned long long)__float_as_uint(z) | ((unsigned long long)((yb << 16) | tag16) << 32);
+	if (peer) asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+	else asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ bool mb_load(const ulonglong2 *p, unsigned int tag16, float4 &out) {
+	unsigned long long a, b;
+	asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+	const unsigned int ah = (unsigned int)(a >> 32), bh = (unsigned int)(b >> 32);
+	out = make_float4(__uint_as_float((unsigned int)a), __uint_as_float((ah & 0xffff0000u) | (bh >> 16)), __uint_as_float((unsigned int)b), 0.f);
+	return (ah & 0xffffu) == tag16 && (bh & 0xffffu) == tag16;
 }
 
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
@@ -237,19 +262,20 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 		__syncthreads();
 	}
 	const double thresh = check ? 4.0 * P.tol2 * __ldcg(&P.resid[0]) : 0.0;
-	const size_t TS = (size_t)R.total_slots, buf_stride = 3 * TS; // dglob: [sweep parity][x | y | z][slot]
+	const size_t buf_stride = (size_t)R.total_slots; // mailboxes: [sweep parity][slot] of 16-byte words
+	const unsigned int tag_seq = ((R.tag_base >> 12) & 0x7fu) << 9;
+	ulonglong2 *const mbox = (ulonglong2 *)R.dglob;
 	long long pw = 0, pc = 0, pb = 0, po = 0, t_prev_end = 0, ps1 = 0, ps2 = 0, n_retry = 0, n_spin = 0, hop_nbr = 0, hop_own = 0, hop_first = 0, hop_n = 0;
 
 	// Pulls the halo values of colour `cp` published with tag `tag` in buffer `buf` into shared memory
 	// (thread t0 of nt takes every nt-th node).
-	auto refresh = [&](int cp, const uint2 *buf, unsigned int tag, int t0, int nt) {
+	auto refresh = [&](int cp, const ulonglong2 *buf, unsigned int tag, int t0, int nt) {
 		const int end = s_hcol[cp + 1];
 		for (int h = s_hcol[cp] + t0; h < end; h += nt) {
-			const uint2 *w = buf + (size_t)d.slot_off + h; // consecutive lanes, consecutive slots: coalesced polls
-			uint2 a, b, c;
-			a = ll_load(w); b = ll_load(w + TS); c = ll_load(w + 2 * TS);
-			while (a.y != tag || b.y != tag || c.y != tag) { if (PROF) ++n_spin; a = ll_load(w); b = ll_load(w + TS); c = ll_load(w + 2 * TS); }
-			s_d[d.n_own + h] = make_float4(__uint_as_float(a.x), __uint_as_float(b.x), __uint_as_float(c.x), 0.f);
+			const ulonglong2 *w = buf + (size_t)d.slot_off + h; // consecutive lanes, consecutive slots: coalesced polls
+			float4 v;
+			while (!mb_load(w, tag, v)) { if (PROF) ++n_spin; }
+			s_d[d.n_own + h] = v;
 		}
 	};
 
@@ -264,7 +290,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 		const size_t pub_off = (size_t)(it & 1) * buf_stride;
 		for (int color = 0; color < C; ++color) {
 			const bool last = check && (color == C - 1);
-			const unsigned int pass_tag = R.tag_base | (pass + 1);
+			const unsigned int pass_tag = tag_seq | (pass + 1);
 			const int role = s_role[color * NW + warp];
 			long long t0 = 0, t1 = 0;
 			if (PROF) { t0 = clk_ordered(); if (t_prev_end) po += t0 - t_prev_end; TR(0); }
@@ -288,11 +314,11 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 					// what the neighbours changed in the previous pass: the halo nodes of that pass's colour
 					const int cp = (color + C - 1) % C;
 					const int it_prev = color > 0 ? it : it - 1;
-					refresh(cp, R.dglob + (size_t)(it_prev & 1) * buf_stride, R.tag_base | pass, 32 * role + lane, n_poll);
+					refresh(cp, mbox + (size_t)(it_prev & 1) * buf_stride, tag_seq | pass, 32 * role + lane, n_poll);
 				}
 				if (PROF) TR(1);
 				named_sync(1, n_poll);
-				if (PROF && pass > 0 && role == 0 && lane == 0) {
+				if (PROF && (R.dbg & 128) && pass > 0 && role == 0 && lane == 0) {
 					// when did the neighbours publish what has just arrived?  (global timer; single GPU only)
 					const unsigned long long now = gtime_ns();
 					volatile unsigned long long *pubt = (volatile unsigned long long *)(R.prof + 16 * gridDim.x + 1024);
@@ -312,6 +338,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				if (PROF && (R.dbg & 4) && !(S[k].meta & 0x100)) continue; // timing experiment: no interior work
 				float sx, sy, sz;
 				owned_gather(s_val, s_col, s_d, S[k].r0, (PROF && (R.dbg & 32)) ? S[k].r0 : S[k].r1, lane, sx, sy, sz);
+				if (PROF) TR(5);
 				const int l = S[k].l;
 				if (l < 0) continue;
 				const float4 dold = s_d[l];
@@ -338,13 +365,14 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 					}
 				}
 				s_d[l] = dn;
+				if (PROF) TR(6);
 				if ((S[k].meta & 0x100) && !(PROF && (R.dbg & 16))) {
 					const int cnt = (S[k].meta >> 10) & 63;
 					auto put = [&](unsigned int ent) {
 						const unsigned int q = ent >> 27;
 						const size_t at = pub_off + (size_t)(ent & 0x7ffffffu);
-						if ((int)q == R.rank) { uint2 *w = R.dglob + at; ll_store(w, dn.x, pass_tag); ll_store(w + TS, dn.y, pass_tag); ll_store(w + 2 * TS, dn.z, pass_tag); }
-						else { uint2 *w = R.peer_dglob[q] + at; ll_store_sys(w, dn.x, pass_tag); ll_store_sys(w + TS, dn.y, pass_tag); ll_store_sys(w + 2 * TS, dn.z, pass_tag); }
+						if ((int)q == R.rank) mb_store(mbox + at, dn.x, dn.y, dn.z, pass_tag, false);
+						else mb_store((ulonglong2 *)R.peer_dglob[q] + at, dn.x, dn.y, dn.z, pass_tag, true);
 					};
 					if (cnt > 0) put(S[k].dst0);
 					if (cnt > 1) put(S[k].dst1);
@@ -356,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 						for (int e = e0 + 4; e < e0 + cnt; ++e) put(__ldg(&R.dest_slot[e]));
 					}
 					if (PROF && (R.dbg & 64)) __threadfence(); // timing experiment: does a fence get the published words out sooner?
-					if (PROF && lane == 0 && R.world == 1) atomicMax(R.prof + 16 * gridDim.x + 1024 + (size_t)(R.part0 + blockIdx.x) * 128 + (pass & 127), gtime_ns());
+					if (PROF && (R.dbg & 128) && lane == 0 && R.world == 1) atomicMax(R.prof + 16 * gridDim.x + 1024 + (size_t)(R.part0 + blockIdx.x) * 128 + (pass & 127), gtime_ns());
 				}
 			}
 			long long t2 = 0;
@@ -403,7 +431,7 @@ __global__ void __launch_bounds__(NT, 1) mcgs_owned_f32_kernel(McgsRes32Params R
 				const double b2 = __ldcg(&P.resid[0]);
 				// exact residual b - A x = r0 - A d (src/NodalMultiColorGS.hpp:136-139).  Every part takes this
 				// branch; the last colour's halo values are the only ones not pulled in yet.
-				refresh(C - 1, R.dglob + pub_off, R.tag_base | pass, tid, NT);
+				refresh(C - 1, mbox + pub_off, tag_seq | pass, tid, NT);
 				__syncthreads();
 				double acc = 0;
 #pragma unroll

@@ -5,7 +5,8 @@ import numpy as np, bench, argparse
 import __graft_entry__ as g
 pkg=g.load_package()
 args=argparse.Namespace(workload='beam_1m',model=1,admm_iters=20,linsolver=1,precision=0)
-scene=bench.make_scene(pkg,'beam_1m'); mu,lam=pkg.meshes.lame(*bench.LAME)
+WL=sys.argv[1] if len(sys.argv)>1 else 'beam_1m'
+scene=bench.make_scene(pkg,WL); mu,lam=pkg.meshes.lame(*bench.LAME)
 sol=pkg.Solver(); sol.set_options(precision=0,timers=True)
 sol.add_nodes(scene['verts'],scene['masses']); sol.add_tets(scene['verts'],scene['elems'],1,mu,lam); sol.set_pins(scene['pins'])
 assert sol.initialize(dt=1/24,admm_iters=20,gravity=-9.8,linsolver=1)
@@ -26,11 +27,11 @@ print('dbg',os.environ.get('ADMM_B200_GS_DBG','0'),sol.device().info())
 print('bwarps info: n_own/halo etc. in info above; solve us:', sol.device().time_kernels(10))
 
 # timeline of passes 40..43 of part (dbg >> 8): per warp, cycles relative to warp 0's pass-40 start
-# events: 0 pass start, 1 poll done, 2 after halo barrier, 3 slice done + published, 4 after end-of-pass barrier
+# events: 0 pass start, 1 poll done, 2 after halo barrier, 3 slice done + published, 4 after end-of-pass barrier, 5 gather done, 6 update done (before publishing)
 t00=tr[0,0,0]
 if t00>0:
     for ps in range(4):
         print('pass',40+ps)
         for w in range(16):
             e=tr[w,ps]
-            print('  warp %2d: '%w+' '.join('%6s'%(int(v-t00) if v>0 else '-') for v in e[:5]))
+            print('  warp %2d: '%w+' '.join('%6s'%(int(v-t00) if v>0 else '-') for v in e[:7]))
