@@ -289,6 +289,16 @@ class Solver(object):
         c = _f64(center)
         self._ck(_host.admmhost_add_sphere(self.h, _dp(c), ctypes.c_double(radius)))
 
+    def add_wind(self, tris, direction):
+        """Solver::ext_forces.push_back(WindForce(tris)) with WindForce::direction (src/ExplicitForce.hpp:40-48); returns the
+        index to pass to set_wind_direction.  Call before initialize."""
+        tris, d = _i32(tris).ravel(), _f64(direction).ravel()
+        return int(_host.admmhost_add_wind(self.h, _ip(tris), tris.size // 3, _dp(d)))
+
+    def set_wind_direction(self, index, direction):
+        d = _f64(direction).ravel()
+        self._ck(_host.admmhost_set_wind_direction(self.h, int(index), _dp(d)))
+
     def set_surface_inds(self, inds):
         """Solver::surface_inds: the vertices UzawaCG's collision detection tests, in that order (empty: all nodes)."""
         inds = _i32(inds).ravel()
@@ -478,3 +488,11 @@ def ldlt_blocks_solve_host(rowptr, cols, vals, pos, b):
     if rc:
         raise AdmmError("ldlt block plan failed")
     return x, dict(zip(("blocks", "largest", "levels_f", "levels_b", "nnz_out", "nnz_inv", "cut", "segments"), [int(v) for v in stats]))
+
+
+def wind_project(tris, direction, dt, x, v):
+    """WindForce::project alone (host form of the device kernels): returns the new velocities."""
+    tris, d, x = _i32(tris).ravel(), _f64(direction).ravel(), _f64(x).ravel()
+    v = _f64(v).ravel().copy()
+    _host.admmhost_wind_project(_ip(tris), tris.size // 3, _dp(d), ctypes.c_double(dt), x.size // 3, _dp(x), _dp(v))
+    return v

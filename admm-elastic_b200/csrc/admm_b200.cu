@@ -19,6 +19,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <memory>
 
 using namespace admmb200;
 
@@ -129,6 +130,12 @@ struct admm_b200_solver {
 	DevBuf<int> d_pin_slot;
 	DevBuf<double> d_pin_pos;
 	std::vector<Obstacle> obstacles;
+	// Solver::ext_forces (src/Solver.hpp:71): wind forces, applied in order at the top of every step
+	struct Wind {
+		std::vector<int> tris; double dir[3]; bool uploaded = false; int n_touched = 0;
+		DevBuf<int> d_tris, d_nodes, d_inc_ptr, d_inc_tri; DevBuf<double4> d_kick;
+	};
+	std::vector<std::unique_ptr<Wind>> winds;
 	DevBuf<Obstacle> d_obstacles;
 
 	// mcgs device
@@ -1196,6 +1203,30 @@ void do_step(S *s, int admm_iters, double gravity, admm_b200_runtime *rt)
 	}
 	const int n = s->n_nodes;
 	const int nb = (n + 255) / 256;
+	for (auto &wp : s->winds) {
+		S::Wind &w = *wp;
+		const int nt = (int)(w.tris.size() / 3);
+		if (nt == 0) continue;
+		if (!w.uploaded) {
+			// node -> its triangles, in triangle order (the order the kicks are added in)
+			std::vector<int> cnt((size_t)n, 0), nodes, ptr(1, 0), inc;
+			for (int t = 0; t < 3 * nt; ++t) { require(w.tris[t] >= 0 && w.tris[t] < n, "wind force: vertex index out of range"); cnt[w.tris[t]]++; }
+			std::vector<int> slot((size_t)n, -1);
+			for (int i = 0; i < n; ++i) if (cnt[i]) { slot[i] = (int)nodes.size(); nodes.push_back(i); ptr.push_back(ptr.back() + cnt[i]); }
+			inc.resize((size_t)ptr.back());
+			std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+			for (int t = 0; t < nt; ++t) for (int c = 0; c < 3; ++c) inc[(size_t)fill[slot[w.tris[3 * t + c]]]++] = t;
+			w.n_touched = (int)nodes.size();
+			w.d_tris.upload(w.tris, s->stream); w.d_nodes.upload(nodes, s->stream); w.d_inc_ptr.upload(ptr, s->stream); w.d_inc_tri.upload(inc, s->stream);
+			w.d_kick.alloc((size_t)nt);
+			CK(cudaStreamSynchronize(s->stream)); // the host vectors above go out of scope
+			w.uploaded = true;
+		}
+		wind_tri_kernel<<<(nt + 255) / 256, 256, 0, s->stream>>>(nt, w.d_tris.p, w.dir[0], w.dir[1], w.dir[2], s->dt, s->x.p, s->v.p, w.d_kick.p);
+		wind_node_kernel<<<(w.n_touched + 255) / 256, 256, 0, s->stream>>>(w.n_touched, w.d_nodes.p, w.d_inc_ptr.p, w.d_inc_tri.p, w.d_kick.p, s->v.p);
+		CK(cudaGetLastError());
+		s->launches += 2;
+	}
 	step_begin_kernel<<<nb, 256, 0, s->stream>>>(n, s->dt, gravity, s->x.p, s->v.p, s->m.p, s->mxbar.p, s->cx.p);
 	CK(cudaGetLastError());
 	s->launches++;
@@ -1593,6 +1624,27 @@ int admm_b200_add_obstacle(admm_b200_solver *s, int kind, const double *params)
 		Obstacle o; o.kind = kind;
 		for (int i = 0; i < 4; ++i) o.p[i] = (kind == ADMM_B200_FLOOR && i > 0) ? 0.0 : params[i];
 		s->obstacles.push_back(o);
+	});
+}
+
+int admm_b200_add_wind(admm_b200_solver *s, const int *tris, int n_tris, const double *direction, int *id)
+{
+	return guard(s, [&]() {
+		require(n_tris >= 0 && (tris || n_tris == 0) && direction, "add_wind: bad arguments");
+		require(s->world == 1, "add_wind: explicit forces are single-GPU");
+		std::unique_ptr<S::Wind> w(new S::Wind());
+		w->tris.assign(tris, tris + 3 * (size_t)n_tris);
+		for (int a = 0; a < 3; ++a) w->dir[a] = direction[a];
+		s->winds.push_back(std::move(w));
+		if (id) *id = (int)s->winds.size() - 1;
+	});
+}
+
+int admm_b200_set_wind_direction(admm_b200_solver *s, int id, const double *direction)
+{
+	return guard(s, [&]() {
+		require(id >= 0 && id < (int)s->winds.size() && direction, "set_wind_direction: no such wind force");
+		for (int a = 0; a < 3; ++a) s->winds[id]->dir[a] = direction[a];
 	});
 }
 

@@ -61,6 +61,39 @@ __global__ void step_begin_kernel(int n, double dt, double gravity, const double
 	st_node(&mxbar[i], mi.x * bx, mi.y * by, mi.z * bz);
 }
 
+// WindForce::project (src/ExplicitForce.cpp:47-104): a velocity kick per triangle, -alpha_n area v_n |v_n| n x 0.33 dt added to
+// its three nodes, before gravity and x_bar (src/Solver.cpp:53-54).  The reference forms the kicks in an `omp parallel for`
+// while other threads are already adding theirs to the same velocities: its result depends on the thread count.  Here every
+// kick is formed from the velocities BEFORE the call (wind_tri_kernel), then each node adds the kicks of its triangles in a
+// fixed order (wind_node_kernel): order independent and bit-reproducible.  oracle/admm_oracle.c: oracle_wind_project states
+// both readings; they agree when the explicit drag is not stiff (alpha_n area |v| dt << 1).
+__global__ void wind_tri_kernel(int n_tris, const int *__restrict__ tris, double dx, double dy, double dz, double dt,
+	const double4 *__restrict__ x, const double4 *__restrict__ v, double4 *__restrict__ kick)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tris) return;
+	const int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+	const double4 p0 = x[i0], p1 = x[i1], p2 = x[i2], v0 = v[i0], v1 = v[i1], v2 = v[i2];
+	const double rx = (v0.x + v1.x + v2.x) / 3.0 - dx, ry = (v0.y + v1.y + v2.y) / 3.0 - dy, rz = (v0.z + v1.z + v2.z) / 3.0 - dz;
+	const double ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z, bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+	double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+	const double len = sqrt(nx * nx + ny * ny + nz * nz), area = 0.5 * len;
+	if (len > 0) { nx /= len; ny /= len; nz /= len; }
+	const double vn = nx * rx + ny * ry + nz * rz;
+	const double c = -1000.0 * area * vn * fabs(vn);
+	st_node(&kick[t], c * nx * 0.33 * dt, c * ny * 0.33 * dt, c * nz * 0.33 * dt);
+}
+__global__ void wind_node_kernel(int n_touched, const int *__restrict__ nodes, const int *__restrict__ inc_ptr, const int *__restrict__ inc_tri,
+	const double4 *__restrict__ kick, double4 *__restrict__ v)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_touched) return;
+	const int i = nodes[k];
+	double4 vi = v[i];
+	for (int q = inc_ptr[k]; q < inc_ptr[k + 1]; ++q) { const double4 f = kick[inc_tri[q]]; vi.x += f.x; vi.y += f.y; vi.z += f.z; }
+	st_node(&v[i], vi.x, vi.y, vi.z);
+}
+
 __global__ void step_end_kernel(int n, double dt, double4 *__restrict__ x, double4 *__restrict__ v, const double4 *__restrict__ cx)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -290,6 +290,41 @@ class Floor : public PassiveCollision { public: double m_y; Floor(double y) : m_
 class Sphere : public PassiveCollision { public: Vec3 center; double rad; Sphere(const Vec3 &c, double r) : center(c), rad(r) {} int kind() const { return ADMM_B200_SPHERE; } void params(double *p) const { p[0] = center[0]; p[1] = center[1]; p[2] = center[2]; p[3] = rad; } };
 
 //
+//	Explicit forces (src/ExplicitForce.hpp:31-48): applied at the top of step(), before gravity (src/Solver.cpp:53-57).
+//	WindForce runs on the device (csrc/kernels.cuh: wind_tri_kernel / wind_node_kernel).  Any other subclass is a host
+//	callback on m_x / m_v: step() calls it before the state goes up; step_device() refuses (the state is not on the host).
+//
+class ExplicitForce {
+public:
+	typedef std::vector<double> VecX;
+	virtual ~ExplicitForce() {}
+	virtual void project(double dt, VecX &x, VecX &v, VecX &m) const = 0;
+};
+class WindForce : public ExplicitForce { // src/ExplicitForce.hpp:40-48
+public:
+	WindForce(const std::vector<int> &tris_) : tris(tris_) { direction = Vec3(0, 0, 0); }
+	// Host form of the device kernels (every kick from the velocities before the call, added node by node in triangle
+	// order); Solver::step() does not call it -- the device applies the force -- it is here for callers that do.
+	void project(double dt, VecX &x, VecX &v, VecX &m) const {
+		(void)m;
+		const VecX v0(v);
+		const size_t nt = tris.size() / 3;
+		for (size_t t = 0; t < nt; ++t) {
+			const int id[3] = {3 * tris[3 * t], 3 * tris[3 * t + 1], 3 * tris[3 * t + 2]};
+			double r[3], a[3], b[3];
+			for (int c = 0; c < 3; ++c) { r[c] = (v0[id[0] + c] + v0[id[1] + c] + v0[id[2] + c]) / 3.0 - direction[c]; a[c] = x[id[1] + c] - x[id[0] + c]; b[c] = x[id[2] + c] - x[id[0] + c]; }
+			double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+			const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), area = 0.5 * len;
+			if (len > 0) for (int c = 0; c < 3; ++c) n[c] /= len;
+			const double vn = n[0] * r[0] + n[1] * r[1] + n[2] * r[2], k = -1000.0 * area * vn * std::fabs(vn);
+			for (int j = 0; j < 3; ++j) for (int c = 0; c < 3; ++c) v[id[j] + c] += k * n[c] * 0.33 * dt;
+		}
+	}
+	std::vector<int> tris;
+	Vec3 direction;
+};
+
+//
 //	The main solver (src/Solver.hpp:33-141)
 //
 class Solver {
@@ -334,6 +369,7 @@ public:
 	VecX m_x, m_v, m_masses; // per-node x3, as in the reference
 	std::vector<int> surface_inds;
 	std::vector<std::shared_ptr<EnergyTerm>> energyterms;
+	std::vector<std::shared_ptr<ExplicitForce>> ext_forces; // src/Solver.hpp:71; fixed at initialize(), WindForce::direction may change
 	std::vector<std::vector<int>> user_colors; // device_options.coloring == 2
 
 	template <typename T> int add_nodes(T *x, T *m, int n_verts) { // src/Solver.hpp:127-141
@@ -382,6 +418,8 @@ protected:
 	int n_D_rows = 0;
 	bool state_on_device_newer = false;
 	std::vector<int> m_node_owner;
+	std::vector<int> m_wind_id; // per ext_forces entry: device id of a WindForce, -1 for a host force
+	void apply_ext_forces(bool host_state);
 
 	bool host_pinned = false;
 	void release_device() {
@@ -588,6 +626,16 @@ inline bool Solver::initialize(const Settings &settings_) { // src/Solver.cpp:16
 	if (!p_idx.empty()) check(admm_b200_add_pins(handle, (int)p_idx.size(), p_idx.data(), p_pos.data(), p_w.data(), p_row.data()), "add_pins");
 
 	for (auto &o : passive_objs) { double p[4]; o->params(p); check(admm_b200_add_obstacle(handle, o->kind(), p), "add_obstacle"); }
+	m_wind_id.assign(ext_forces.size(), -1);
+	for (size_t i = 0; i < ext_forces.size(); ++i) {
+		// the reference applies ext_forces in order; device and host forces cannot be interleaved, so a host force may not
+		// come after a WindForce
+		if (const WindForce *w = dynamic_cast<const WindForce *>(ext_forces[i].get())) {
+			const double d[3] = {w->direction[0], w->direction[1], w->direction[2]};
+			check(admm_b200_add_wind(handle, w->tris.data(), (int)(w->tris.size() / 3), d, &m_wind_id[i]), "add_wind");
+		} else
+			for (size_t j = 0; j < i; ++j) if (m_wind_id[j] >= 0) throw std::runtime_error("**admm_b200::Solver Error: a host ExplicitForce after a WindForce (put host forces first)");
+	}
 	if (m_settings.linsolver == 2) {
 		// what UzawaCG's collision rows depend on: the candidate vertices and their order (src/Solver.cpp:93), and
 		// constraint_w = 1 unless -ck overrides it (src/Solver.cpp:239,245)
@@ -636,13 +684,29 @@ inline void Solver::step() { // src/Solver.cpp:35-110
 	m_runtime = RuntimeData();
 	admm_b200_runtime rt;
 	if (state_on_device_newer) sync_state();
+	apply_ext_forces(true);
 	check(admm_b200_step_host(handle, m_settings.admm_iters, m_settings.gravity, m_x.data(), m_v.data(), device_options.timers ? &rt : nullptr), "step");
 	if (device_options.timers) { m_runtime.global_ms = rt.global_ms; m_runtime.local_ms = rt.local_ms; m_runtime.collision_ms = rt.collision_ms; m_runtime.inner_iters = rt.inner_iters; m_runtime.assemble_ms = rt.assemble_ms; m_runtime.step_ms = rt.step_ms; }
 	if (m_settings.verbose > 0) m_runtime.print(m_settings);
 }
 
+inline void Solver::apply_ext_forces(bool host_state) { // src/Solver.cpp:53-54
+	if (ext_forces.size() != m_wind_id.size()) throw std::runtime_error("**admm_b200::Solver Error: ext_forces changed after initialize");
+	for (size_t i = 0; i < ext_forces.size(); ++i) {
+		if (m_wind_id[i] >= 0) {
+			const WindForce *w = static_cast<const WindForce *>(ext_forces[i].get());
+			const double d[3] = {w->direction[0], w->direction[1], w->direction[2]};
+			check(admm_b200_set_wind_direction(handle, m_wind_id[i], d), "set_wind_direction");
+		} else {
+			if (!host_state) throw std::runtime_error("**admm_b200::Solver Error: step_device() with a host ExplicitForce");
+			ext_forces[i]->project(m_settings.timestep_s, m_x, m_v, m_masses);
+		}
+	}
+}
+
 inline void Solver::step_device() {
 	if (!initialized) throw std::runtime_error("**Solver::step Error: not initialized");
+	apply_ext_forces(false);
 	m_runtime = RuntimeData();
 	admm_b200_runtime rt;
 	check(admm_b200_step(handle, m_settings.admm_iters, m_settings.gravity, device_options.timers ? &rt : nullptr), "step");

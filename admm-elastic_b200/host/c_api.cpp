@@ -100,6 +100,30 @@ int admmhost_set_options(void *h_, int device, int precision, int gs_max_iters, 
 }
 
 int admmhost_set_surface_inds(void *h_, const int *idx, int n) { ((Host *)h_)->solver.surface_inds.assign(idx, idx + n); return 0; }
+// Solver::ext_forces.push_back(std::make_shared<WindForce>(tris)); returns its index in ext_forces
+int admmhost_add_wind(void *h_, const int *tris, int n_tris, const double *dir) {
+	Host *h = (Host *)h_;
+	std::shared_ptr<admm_b200::WindForce> w = std::make_shared<admm_b200::WindForce>(std::vector<int>(tris, tris + 3 * (size_t)n_tris));
+	w->direction = admm_b200::Vec3(dir[0], dir[1], dir[2]);
+	h->solver.ext_forces.emplace_back(w);
+	return (int)h->solver.ext_forces.size() - 1;
+}
+int admmhost_set_wind_direction(void *h_, int index, const double *dir) {
+	Host *h = (Host *)h_;
+	if (index < 0 || index >= (int)h->solver.ext_forces.size()) return 1;
+	admm_b200::WindForce *w = dynamic_cast<admm_b200::WindForce *>(h->solver.ext_forces[index].get());
+	if (!w) return 1;
+	w->direction = admm_b200::Vec3(dir[0], dir[1], dir[2]);
+	return 0;
+}
+// WindForce::project alone (host form of the device kernels)
+void admmhost_wind_project(const int *tris, int n_tris, const double *dir, double dt, int n_nodes, const double *x, double *v) {
+	admm_b200::WindForce w(std::vector<int>(tris, tris + 3 * (size_t)n_tris));
+	w.direction = admm_b200::Vec3(dir[0], dir[1], dir[2]);
+	std::vector<double> xx(x, x + 3 * (size_t)n_nodes), vv(v, v + 3 * (size_t)n_nodes), mm(3 * (size_t)n_nodes, 1.0);
+	w.project(dt, xx, vv, mm);
+	for (size_t i = 0; i < vv.size(); ++i) v[i] = vv[i];
+}
 int admmhost_set_gs_parts(void *h_, int n_parts) { ((Host *)h_)->solver.device_options.gs_parts = n_parts; return 0; }
 
 int admmhost_set_rank(void *h_, int rank, int world) {

@@ -122,6 +122,14 @@ int admm_b200_set_gs_pins( admm_b200_solver *s, int n, const int *idx, const dou
  * (src/Collider.hpp:137-150); order of calls = order of passive_objs. */
 int admm_b200_add_obstacle( admm_b200_solver *s, int kind, const double *params );
 
+/* Solver::ext_forces.push_back( WindForce(tris) ) (src/Solver.hpp:71, src/ExplicitForce.hpp:40-48): a wind force over a list
+ * of triangles (3 vertex indices each), applied to the velocities at the top of every step, before gravity
+ * (src/Solver.cpp:53-57; WindForce::project, src/ExplicitForce.cpp:47-104), in the order of the calls.  `direction` is
+ * WindForce::direction and may be changed between steps.  Every kick is formed from the velocities before the call
+ * (the reference's result depends on its thread count, see csrc/kernels.cuh: wind_tri_kernel).  Single-GPU. */
+int admm_b200_add_wind( admm_b200_solver *s, const int *tris, int n_tris, const double *direction, int *id );
+int admm_b200_set_wind_direction( admm_b200_solver *s, int id, const double *direction );
+
 /* UzawaCG only.  The vertices Collider::detect tests for passive hits, in that order: Solver::surface_inds
  * (src/Solver.hpp:69, src/Solver.cpp:93, src/Collider.hpp:152-212; filled by binding::add_tetmesh,
  * samples/utils/AddMeshes.hpp:130-136).  n = 0 (the default): every node, in node order.  The order fixes the row order of

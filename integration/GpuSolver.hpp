@@ -177,7 +177,6 @@ inline bool GpuSolver::initialize( const Settings &settings_ ){
 		if( it != energyterms.end() ){ energyterms.erase(it); }
 	}
 	m_pin_energies.clear();
-	if( ext_forces.size() > 0 ){ throw std::runtime_error("**GpuSolver Error: explicit forces are not on the GPU path"); }
 	if( m_constraints->collider->dynamic_objs.size() > 0 ){ throw std::runtime_error("**GpuSolver Error: self collision is not on the GPU path"); }
 
 	// The reference's own initialize: validates, appends SpringPins, builds D, W, A and the CPU linear solver
@@ -285,6 +284,11 @@ inline void GpuSolver::step(){
 	if( !initialized || !h ){ throw std::runtime_error("**GpuSolver::step Error: not initialized"); }
 	m_runtime = RuntimeData();
 	admm_b200_runtime rt;
+	// Explicit forces (src/Solver.cpp:53-54): the reference's own ExplicitForce::project on the host arrays, which are about
+	// to travel to the device anyway -- any subclass works and WindForce keeps the reference's exact (thread-order
+	// dependent) arithmetic.  admm_b200_add_wind is the device form for callers that keep the state resident.
+	const int n_ext_forces = ext_forces.size();
+	for( int i=0; i<n_ext_forces; ++i ){ ext_forces[i]->project( m_settings.timestep_s, m_x, m_v, m_masses ); }
 	ck( admm_b200_step_host( h, m_settings.admm_iters, m_settings.gravity, m_x.data(), m_v.data(), &rt ), "step" );
 	m_runtime.global_ms = rt.global_ms; m_runtime.local_ms = rt.local_ms; m_runtime.collision_ms = rt.collision_ms; m_runtime.inner_iters = rt.inner_iters;
 	if( m_settings.verbose > 0 ){ m_runtime.print(m_settings); }

@@ -388,6 +388,8 @@ typedef struct oracle_solver {
 	int *surf; int n_surf;   /* Solver::surface_inds (src/Solver.hpp:69): the vertices Collider::detect tests, in order; none = all */
 	double uz_ck;            /* sqrt(max(0, constraint_w)), ConstraintSet::make_matrix (src/ConstraintSet.hpp:66) */
 	double global_ms, local_ms; int inner_iters;
+	/* Solver::ext_forces (src/Solver.hpp:71): WindForce objects, applied in order at the top of step() (src/Solver.cpp:53-54) */
+	struct { int *tris; int n_tris; double dir[3]; } wind[4]; int n_wind, wind_sequential;
 	int initialized;
 	char err[256];
 } oracle_solver;
@@ -680,6 +682,7 @@ void oracle_destroy(oracle_solver *s)
 {
 	if (!s) return;
 	free(s->x); free(s->v); free(s->m); free(s->terms); free(s->pin_idx); free(s->pin_pos); free(s->color_off); free(s->color_nodes);
+	{ int w; for (w = 0; w < s->n_wind; ++w) free(s->wind[w].tris); }
 	csr_free(&s->A); free(s->Lp); free(s->Li); free(s->Lx); free(s->Dg); free(s->uz_y); free(s);
 }
 const char *oracle_last_error(const oracle_solver *s) { return s->err; }
@@ -837,6 +840,51 @@ int oracle_initialize(oracle_solver *s, double dt, int admm_iters, double gravit
 	return 0;
 }
 
+/* WindForce::project (src/ExplicitForce.cpp:47-104), Wejchert & Haumann: per triangle the mean node velocity relative to
+   the wind, its component along the unit normal, force = -alpha_n area v_n |v_n| n, a 0.33 share times dt added to the
+   VELOCITY of each of the three nodes (no division by mass in the reference).
+   The reference loops over the triangles with `omp parallel for` and adds the shares under an `omp critical` while other
+   threads are reading the same velocities (:62-66 against :96-100): with one thread every triangle sees the velocities
+   already changed by the triangles before it; with several threads the outcome depends on the interleaving.
+   sequential = 1 restates the one-thread order (pinned against the compiled reference run with one thread,
+   tests/test_oracle_vs_ref.py); sequential = 0 forms every force from the velocities BEFORE the call, the only
+   order-independent reading and the one the device implements (csrc/kernels.cuh: wind_*_kernel). */
+void oracle_wind_project(int n_tris, const int *tris, const double *dir, double dt, int n_nodes, const double *x, double *v, int sequential)
+{
+	int i, j, a;
+	double *v0 = v;
+	if (!sequential) {
+		v0 = (double *)malloc((size_t)3 * n_nodes * sizeof(double));
+		memcpy(v0, v, (size_t)3 * n_nodes * sizeof(double));
+	}
+	for (i = 0; i < n_tris; ++i) {
+		const int id[3] = {3 * tris[3 * i], 3 * tris[3 * i + 1], 3 * tris[3 * i + 2]};
+		double vr[3], e1[3], e2[3], n[3], len, area, vn, f[3];
+		for (a = 0; a < 3; ++a) vr[a] = (v0[id[0] + a] + v0[id[1] + a] + v0[id[2] + a]) / 3.0 - dir[a];
+		for (a = 0; a < 3; ++a) { e1[a] = x[id[1] + a] - x[id[0] + a]; e2[a] = x[id[2] + a] - x[id[0] + a]; }
+		cross3(e1, e2, n);
+		len = norm3(n);
+		area = 0.5 * len;
+		if (len > 0) for (a = 0; a < 3; ++a) n[a] /= len; /* Eigen's normalized() leaves a zero vector as it is */
+		vn = dot3(n, vr);
+		for (a = 0; a < 3; ++a) { f[a] = -1000.0 * area * vn * fabs(vn) * n[a]; f[a] *= 0.33; f[a] *= dt; }
+		for (j = 0; j < 3; ++j) for (a = 0; a < 3; ++a) v[id[j] + a] += f[a];
+	}
+	if (!sequential) free(v0);
+}
+
+void oracle_wind_mode(oracle_solver *s, int sequential) { s->wind_sequential = sequential; }
+int oracle_add_wind(oracle_solver *s, const int *tris, int n_tris, const double *dir)
+{
+	if (s->n_wind >= 4) { snprintf(s->err, sizeof(s->err), "oracle: at most 4 wind forces"); return 1; }
+	s->wind[s->n_wind].tris = (int *)malloc((size_t)3 * (n_tris > 0 ? n_tris : 1) * sizeof(int));
+	memcpy(s->wind[s->n_wind].tris, tris, (size_t)3 * n_tris * sizeof(int));
+	s->wind[s->n_wind].n_tris = n_tris;
+	memcpy(s->wind[s->n_wind].dir, dir, 3 * sizeof(double));
+	s->n_wind++;
+	return 0;
+}
+
 /* Solver::step (src/Solver.cpp:35-110); optional traces hold z,u (n_rows each) and b,x (dof each) per ADMM iteration */
 int oracle_step_traced(oracle_solver *s, double *zt, double *ut, double *bt, double *xt)
 {
@@ -845,6 +893,7 @@ int oracle_step_traced(oracle_solver *s, double *zt, double *ut, double *bt, dou
 	double *x_bar = (double *)malloc(dof * sizeof(double)), *M_xbar = (double *)malloc(dof * sizeof(double)), *cx = (double *)malloc(dof * sizeof(double));
 	double *z = (double *)calloc(R > 0 ? R : 1, sizeof(double)), *u = (double *)calloc(R > 0 ? R : 1, sizeof(double)), *b = (double *)malloc(dof * sizeof(double));
 	s->global_ms = s->local_ms = 0; s->inner_iters = 0;
+	for (i = 0; i < s->n_wind; ++i) oracle_wind_project(s->wind[i].n_tris, s->wind[i].tris, s->wind[i].dir, dt, s->n_nodes, s->x, s->v, s->wind_sequential);
 	if (fabs(s->gravity) > 0) for (i = 0; i < s->n_nodes; ++i) s->v[3 * i + 1] += dt * s->gravity;
 	for (i = 0; i < dof; ++i) { x_bar[i] = s->x[i] + dt * s->v[i]; M_xbar[i] = s->m[i] * x_bar[i]; cx[i] = x_bar[i]; }
 	for (it = 0; it < s->admm_iters; ++it) {

@@ -108,6 +108,16 @@ int gpub_add_sphere( void *h_, const double *c, double r ){
 	return guarded( h, [&](){ h->solver.add_obstacle( std::make_shared<admm::Sphere>( Eigen::Vector3d(c[0],c[1],c[2]), r ) ); } );
 }
 
+int gpub_add_wind( void *h_, const int *tris, int n_tris, const double *dir ){
+	Handle *h = (Handle*)h_;
+	return guarded( h, [&](){
+		std::vector<int> t( tris, tris+3*n_tris );
+		std::shared_ptr<admm::WindForce> w = std::make_shared<admm::WindForce>( t );
+		w->direction = Eigen::Vector3d( dir[0], dir[1], dir[2] );
+		h->solver.ext_forces.emplace_back( w );
+	} );
+}
+
 // 0 ok, 1 exception, 2 initialize() == false
 int gpub_initialize( void *h_, double dt, int admm_iters, double gravity, int linsolver ){
 	Handle *h = (Handle*)h_;

@@ -208,6 +208,26 @@ int ref_set_pins( void *h_, const int *inds, const double *points, int n ){
 // Solver::surface_inds (src/Solver.hpp:69): the vertices Collider::detect tests (src/Solver.cpp:93)
 void ref_set_surface_inds( void *h_, const int *inds, int n ){ ((Handle*)h_)->solver.surface_inds.assign( inds, inds+n ); }
 
+// Solver::ext_forces (src/Solver.hpp:71) with the reference's own WindForce (src/ExplicitForce.hpp:40-48)
+int ref_add_wind( void *h_, const int *tris, int n_tris, const double *dir ){
+	Handle *h = (Handle*)h_;
+	return guarded( h, [&](){
+		std::vector<int> t( tris, tris+3*n_tris );
+		std::shared_ptr<admm::WindForce> w = std::make_shared<admm::WindForce>( t );
+		w->direction = Eigen::Vector3d( dir[0], dir[1], dir[2] );
+		h->solver.ext_forces.emplace_back( w );
+	} );
+}
+// WindForce::project alone on caller-owned arrays (src/ExplicitForce.cpp:47-104)
+void ref_wind_project( const int *tris, int n_tris, const double *dir, double dt, int n_nodes, const double *x, double *v ){
+	std::vector<int> t( tris, tris+3*n_tris );
+	admm::WindForce w( t );
+	w.direction = Eigen::Vector3d( dir[0], dir[1], dir[2] );
+	Eigen::VectorXd xx = Eigen::Map<const Eigen::VectorXd>( x, 3*n_nodes ), vv = Eigen::Map<const Eigen::VectorXd>( v, 3*n_nodes ), mm = Eigen::VectorXd::Ones( 3*n_nodes );
+	w.project( dt, xx, vv, mm );
+	Eigen::Map<Eigen::VectorXd>( v, 3*n_nodes ) = vv;
+}
+
 int ref_add_floor( void *h_, double y ){
 	Handle *h = (Handle*)h_;
 	return guarded( h, [&](){ h->solver.add_obstacle( std::make_shared<admm::Floor>( y ) ); } );

@@ -52,7 +52,7 @@ def oracle_lib():
                    "oracle_set_colors", "oracle_gs_params", "oracle_initialize", "oracle_step", "oracle_step_traced", "oracle_dof",
                    "oracle_n_rows", "oracle_n_terms", "oracle_get_x", "oracle_get_v", "oracle_set_x", "oracle_set_v", "oracle_set_admm_iters",
                    "oracle_runtime", "oracle_get_row_offsets", "oracle_get_weights", "oracle_A_shape", "oracle_A_get", "oracle_linsolve",
-                   "oracle_apply_D", "oracle_term_energy", "oracle_set_uzawa", "oracle_add_spline_tets", "oracle_prox_tets_k"):
+                   "oracle_apply_D", "oracle_term_energy", "oracle_set_uzawa", "oracle_add_spline_tets", "oracle_prox_tets_k", "oracle_add_wind", "oracle_wind_mode", "oracle_wind_project"):
             getattr(L, fn).argtypes = None
         _oracle = L
     return _oracle
@@ -149,6 +149,10 @@ class GpuBinding(object):
 
     def add_floor(self, y):
         self._ck(self.L.gpub_add_floor(self.h, D(y)))
+
+    def add_wind(self, tris, direction):
+        tris, d = i32(tris).ravel(), f64(direction).ravel()
+        self._ck(self.L.gpub_add_wind(self.h, ip(tris), tris.size // 3, dp(d)))
 
     def add_sphere(self, c, r):
         cc = f64(c)
@@ -301,6 +305,16 @@ class CpuSolver(object):
             cc = f64(c)
             self._ck(self.L.ref_add_sphere(self.h, dp(cc), D(r)))
 
+    def add_wind(self, tris, direction, sequential=False):
+        """Solver::ext_forces.push_back(WindForce(tris)) with WindForce::direction.  The oracle forms every force from the
+        velocities before the call unless sequential=True (the reference's one-thread order, see oracle_wind_project)."""
+        tris, d = i32(tris).ravel(), f64(direction).ravel()
+        if self.kind == "oracle":
+            self.L.oracle_wind_mode(self.h, int(bool(sequential)))
+            self._ck(self.L.oracle_add_wind(self.h, ip(tris), tris.size // 3, dp(d)))
+        else:
+            self._ck(self.L.ref_add_wind(self.h, ip(tris), tris.size // 3, dp(d)))
+
     def set_surface_inds(self, inds, constraint_w=-1.0):
         """Solver::surface_inds (+ Settings::constraint_w for the oracle, which takes both through one call; the reference
         gets constraint_w through initialize).  Call before initialize."""
@@ -448,3 +462,14 @@ def random_F(n, sigma, seed=1234, rotate=True):
         Q[:, :, 2] *= det[:, None]
         F = Q @ F
     return np.ascontiguousarray(F.transpose(0, 2, 1).reshape(n, 9))
+
+
+def wind_project(kind, tris, direction, dt, x, v, sequential=False):
+    """WindForce::project (src/ExplicitForce.cpp:47-104) alone: returns the new velocities.  kind = "oracle" | "ref"."""
+    tris, d, x = i32(tris).ravel(), f64(direction).ravel(), f64(x).ravel()
+    v = f64(v).ravel().copy()
+    if kind == "oracle":
+        oracle_lib().oracle_wind_project(tris.size // 3, ip(tris), dp(d), D(dt), x.size // 3, dp(x), dp(v), int(bool(sequential)))
+    else:
+        ref_lib().ref_wind_project(ip(tris), tris.size // 3, dp(d), D(dt), x.size // 3, dp(x), dp(v))
+    return v
