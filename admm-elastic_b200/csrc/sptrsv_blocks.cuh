@@ -89,8 +89,18 @@ __device__ __forceinline__ void blk_row_dot(const double *__restrict__ vals, con
 //   PHASE 2  backward gather  t_j = y_j / D_j - sum_{i below the block} L_ij x_i
 //   PHASE 3  backward dense   x_j = t_j + sum_{k > j in the block} Linv_kj t_k
 // Every thread of the CTA runs the same trip count (blk_reduce may hold CTA barriers).
+// The descriptor of this thread's FIRST row of a phase.  It does not depend on anything the solve computes, so the caller
+// asks for it before the barrier that precedes the phase: one L2 round trip less on the chain after the barrier.
 template <int PHASE>
-__device__ __forceinline__ void blk_phase(const LdltBlkParams &P, const double4 *b, double4 *x, int k0, int k1, int T, int t, int n_thr, double *s_part)
+__device__ __forceinline__ int4 blk_prefetch(const LdltBlkParams &P, int k0, int k1, int T, int t)
+{
+	const int k = k0 + t / T;
+	if (k >= k1) return make_int4(0, 0, 0, 0);
+	return __ldg(PHASE == 0 ? &P.desc_fg[k] : (PHASE == 2 ? &P.desc_bg[k] : &P.desc_d[k]));
+}
+
+template <int PHASE>
+__device__ __forceinline__ void blk_phase(const LdltBlkParams &P, const double4 *b, double4 *x, int k0, int k1, int T, int t, int n_thr, double *s_part, int4 pref)
 {
 	const int sub = t & (T - 1), group = t / T, n_groups = n_thr / T;
 	for (int kb = k0; kb < k1; kb += n_groups) {
@@ -99,9 +109,11 @@ __device__ __forceinline__ void blk_phase(const LdltBlkParams &P, const double4 
 		double sx = 0, sy = 0, sz = 0;
 		int4 ds = make_int4(0, 0, 0, 0);
 		double dj = 1.0;
+		double4 own = make_double4(0, 0, 0, 0); // the row's own right-hand side / intermediate value: asked for before the dot product
 		if (act) {
 			// one 16-byte descriptor instead of the chain rows[k] -> rowptr / block tables -> entries
-			ds = __ldg(PHASE == 0 ? &P.desc_fg[k] : (PHASE == 2 ? &P.desc_bg[k] : &P.desc_d[k]));
+			ds = kb == k0 ? pref : __ldg(PHASE == 0 ? &P.desc_fg[k] : (PHASE == 2 ? &P.desc_bg[k] : &P.desc_d[k]));
+			if (sub == 0) own = PHASE == 0 ? ld_node_cg(&b[ds.w]) : (PHASE == 2 ? ld_node_cg(&P.y[ds.x]) : ld_node_cg(&P.t[ds.w]));
 			if (PHASE == 0) blk_row_dot<true>(P.f_vals, P.f_cols, P.y, ds.y, ds.z, sub, T, sx, sy, sz);
 			else if (PHASE == 2) { if (sub == 0) dj = __ldg(&P.D[ds.x]); blk_row_dot<true>(P.b_vals, P.b_rows, P.y, ds.y, ds.z, sub, T, sx, sy, sz); } // rows below the block: already final
 			else {
@@ -113,12 +125,11 @@ __device__ __forceinline__ void blk_phase(const LdltBlkParams &P, const double4 
 		}
 		blk_reduce(sx, sy, sz, T, s_part);
 		if (act && sub == 0) {
-			if (PHASE == 0) { const double4 bi = ld_node_cg(&b[ds.w]); st_node(&P.t[ds.x], bi.x - sx, bi.y - sy, bi.z - sz); }
-			else if (PHASE == 1) { const double4 ti = ld_node_cg(&P.t[ds.w]); st_node(&P.y[ds.w], ti.x + sx, ti.y + sy, ti.z + sz); }
-			else if (PHASE == 2) { const double4 yj = ld_node_cg(&P.y[ds.x]); st_node(&P.t[ds.x], yj.x / dj - sx, yj.y / dj - sy, yj.z / dj - sz); }
+			if (PHASE == 0) st_node(&P.t[ds.x], own.x - sx, own.y - sy, own.z - sz);
+			else if (PHASE == 1) st_node(&P.y[ds.w], own.x + sx, own.y + sy, own.z + sz);
+			else if (PHASE == 2) st_node(&P.t[ds.x], own.x / dj - sx, own.y / dj - sy, own.z / dj - sz);
 			else {
-				const double4 tj = ld_node_cg(&P.t[ds.w]);
-				const double rx = tj.x + sx, ry = tj.y + sy, rz = tj.z + sz;
+				const double rx = own.x + sx, ry = own.y + sy, rz = own.z + sz;
 				st_node(&P.y[ds.w], rx, ry, rz);
 				st_node(&x[__ldg(&P.perm[ds.w])], rx, ry, rz);
 			}
@@ -134,44 +145,69 @@ __device__ __forceinline__ void ldlt_blocks_solve(const LdltBlkParams &P, const 
 {
 	const int ltid = threadIdx.x, lthr = blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x, gthr = gridDim.x * blockDim.x;
 	const int sg0 = __ldg(&P.seg_ptr[blockIdx.x]), sg1 = __ldg(&P.seg_ptr[blockIdx.x + 1]);
+	const int4 none = make_int4(0, 0, 0, 0);
+	// a phase's first descriptor is always asked for BEFORE the barrier in front of the phase (blk_prefetch)
+	struct Seg { int k0, k1, lv; };
+	auto seg = [&](int sg) { Seg g; g.k0 = __ldg(&P.seg_begin[sg]); g.k1 = __ldg(&P.seg_end[sg]); g.lv = __ldg(&P.seg_level[sg]); return g; };
+	auto lev = [&](int lv) { Seg g; g.k0 = __ldg(&P.lev_ptr[lv]); g.k1 = __ldg(&P.lev_ptr[lv + 1]); g.lv = lv; return g; };
+	const bool top = P.cut < P.n_levels;
 	blk_stamp(P, 0);
 	// ---------------- forward: y = L^-1 P b ----------------
-	for (int sg = sg0; sg < sg1; ++sg) {
-		const int k0 = __ldg(&P.seg_begin[sg]), k1 = __ldg(&P.seg_end[sg]), lv = __ldg(&P.seg_level[sg]);
-		blk_phase<0>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv]), ltid, lthr, s_part);
-		__syncthreads();
-		blk_phase<1>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 1]), ltid, lthr, s_part);
-		__syncthreads();
+	{
+		Seg g = sg0 < sg1 ? seg(sg0) : Seg{0, 0, 0};
+		int4 pf = sg0 < sg1 ? blk_prefetch<0>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv]), ltid) : none;
+		for (int sg = sg0; sg < sg1; ++sg) {
+			const int T1 = __ldg(&P.lanes[4 * g.lv + 1]);
+			blk_phase<0>(P, b, x, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv]), ltid, lthr, s_part, pf);
+			pf = blk_prefetch<1>(P, g.k0, g.k1, T1, ltid);
+			__syncthreads();
+			blk_phase<1>(P, b, x, g.k0, g.k1, T1, ltid, lthr, s_part, pf);
+			if (sg + 1 < sg1) { g = seg(sg + 1); pf = blk_prefetch<0>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv]), ltid); }
+			__syncthreads();
+		}
 	}
 	blk_stamp(P, 1); // own forest done
-	if (P.cut > 0) grid_barrier(P.barrier, bar_target, gridDim.x);
-	blk_stamp(P, 2); // everybody's forest done
-	for (int lv = P.cut; lv < P.n_levels; ++lv) {
-		const int k0 = __ldg(&P.lev_ptr[lv]), k1 = __ldg(&P.lev_ptr[lv + 1]);
-		blk_phase<0>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv]), gtid, gthr, s_part);
-		grid_barrier(P.barrier, bar_target, gridDim.x);
-		blk_stamp(P, 8 + 4 * lv);
-		blk_phase<1>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 1]), gtid, gthr, s_part);
-		grid_barrier(P.barrier, bar_target, gridDim.x);
-		blk_stamp(P, 8 + 4 * lv + 1);
-	}
-	// ---------------- backward: x = P^T L^-T D^-1 y, the same levels in reverse (an ancestor sits on a higher level) ----------------
-	for (int lv = P.n_levels - 1; lv >= P.cut; --lv) {
-		const int k0 = __ldg(&P.lev_ptr[lv]), k1 = __ldg(&P.lev_ptr[lv + 1]);
-		blk_phase<2>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 2]), gtid, gthr, s_part);
-		grid_barrier(P.barrier, bar_target, gridDim.x);
-		blk_stamp(P, 8 + 4 * lv + 2);
-		blk_phase<3>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 3]), gtid, gthr, s_part);
-		grid_barrier(P.barrier, bar_target, gridDim.x);
-		blk_stamp(P, 8 + 4 * lv + 3);
-	}
-	blk_stamp(P, 3); // top done
-	for (int sg = sg1 - 1; sg >= sg0; --sg) {
-		const int k0 = __ldg(&P.seg_begin[sg]), k1 = __ldg(&P.seg_end[sg]), lv = __ldg(&P.seg_level[sg]);
-		blk_phase<2>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 2]), ltid, lthr, s_part);
-		__syncthreads();
-		blk_phase<3>(P, b, x, k0, k1, __ldg(&P.lanes[4 * lv + 3]), ltid, lthr, s_part);
-		__syncthreads();
+	{
+		Seg g = top ? lev(P.cut) : Seg{0, 0, 0};
+		int4 pf = top ? blk_prefetch<0>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv]), gtid) : none;
+		if (P.cut > 0) grid_barrier(P.barrier, bar_target, gridDim.x);
+		blk_stamp(P, 2); // everybody's forest done
+		for (int lv = P.cut; lv < P.n_levels; ++lv) {
+			const int T1 = __ldg(&P.lanes[4 * lv + 1]);
+			blk_phase<0>(P, b, x, g.k0, g.k1, __ldg(&P.lanes[4 * lv]), gtid, gthr, s_part, pf);
+			pf = blk_prefetch<1>(P, g.k0, g.k1, T1, gtid);
+			grid_barrier(P.barrier, bar_target, gridDim.x);
+			blk_stamp(P, 8 + 4 * lv);
+			blk_phase<1>(P, b, x, g.k0, g.k1, T1, gtid, gthr, s_part, pf);
+			if (lv + 1 < P.n_levels) { g = lev(lv + 1); pf = blk_prefetch<0>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv]), gtid); }
+			else pf = blk_prefetch<2>(P, g.k0, g.k1, __ldg(&P.lanes[4 * lv + 2]), gtid); // the backward sweep starts on this level
+			grid_barrier(P.barrier, bar_target, gridDim.x);
+			blk_stamp(P, 8 + 4 * lv + 1);
+		}
+		// ---------------- backward: x = P^T L^-T D^-1 y, the same levels in reverse (an ancestor sits on a higher level) ----------------
+		for (int lv = P.n_levels - 1; lv >= P.cut; --lv) {
+			const int T3 = __ldg(&P.lanes[4 * lv + 3]);
+			blk_phase<2>(P, b, x, g.k0, g.k1, __ldg(&P.lanes[4 * lv + 2]), gtid, gthr, s_part, pf);
+			pf = blk_prefetch<3>(P, g.k0, g.k1, T3, gtid);
+			grid_barrier(P.barrier, bar_target, gridDim.x);
+			blk_stamp(P, 8 + 4 * lv + 2);
+			blk_phase<3>(P, b, x, g.k0, g.k1, T3, gtid, gthr, s_part, pf);
+			if (lv > P.cut) { g = lev(lv - 1); pf = blk_prefetch<2>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv + 2]), gtid); }
+			else if (sg0 < sg1) { g = seg(sg1 - 1); pf = blk_prefetch<2>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv + 2]), ltid); } // own forest next
+			grid_barrier(P.barrier, bar_target, gridDim.x);
+			blk_stamp(P, 8 + 4 * lv + 3);
+		}
+		blk_stamp(P, 3); // top done
+		if (!top && sg0 < sg1) { g = seg(sg1 - 1); pf = blk_prefetch<2>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv + 2]), ltid); }
+		for (int sg = sg1 - 1; sg >= sg0; --sg) {
+			const int T3 = __ldg(&P.lanes[4 * g.lv + 3]);
+			blk_phase<2>(P, b, x, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv + 2]), ltid, lthr, s_part, pf);
+			pf = blk_prefetch<3>(P, g.k0, g.k1, T3, ltid);
+			__syncthreads();
+			blk_phase<3>(P, b, x, g.k0, g.k1, T3, ltid, lthr, s_part, pf);
+			if (sg > sg0) { g = seg(sg - 1); pf = blk_prefetch<2>(P, g.k0, g.k1, __ldg(&P.lanes[4 * g.lv + 2]), ltid); }
+			__syncthreads();
+		}
 	}
 	blk_stamp(P, 4); // own forest done (backward)
 	if (P.cut > 0) grid_barrier(P.barrier, bar_target, gridDim.x); // callers read x right away

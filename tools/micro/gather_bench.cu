@@ -99,6 +99,95 @@ __device__ __forceinline__ void gather_v3(const float *__restrict__ s_val, const
 	}
 }
 
+// v4: the columns are stored as BYTE offsets into s_d (col * 16 < 65536 for any part that fits): no multiply between the
+// index load and the gather
+__device__ __forceinline__ void gather_v4(const float *__restrict__ s_val, const uint16_t *__restrict__ s_off, const float4 *__restrict__ s_d,
+	int r0, int r1, int lane, float &sx, float &sy, float &sz)
+{
+	sx = 0.f; sy = 0.f; sz = 0.f;
+	const float *v = s_val + r0 * 32 + lane;
+	const uint16_t *c = s_off + r0 * 32 + lane;
+	const unsigned char *base = (const unsigned char *)s_d;
+	const int n = r1 - r0;
+	for (int r = 0; r < n; r += 8) {
+		unsigned int cc[8]; float a[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const int rr = min(r + j, n - 1);
+			cc[j] = c[rr * 32];
+			a[j] = (r + j < n) ? v[rr * 32] : 0.f;
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const float4 dv = *(const float4 *)(base + cc[j]);
+			sx = fmaf(a[j], dv.x, sx); sy = fmaf(a[j], dv.y, sy); sz = fmaf(a[j], dv.z, sz);
+		}
+	}
+}
+// v6: two row-steps per index / value load: byte offsets packed in pairs (one LDS.32 = 2 columns), values as float2;
+// rows padded to an even length by the caller
+__device__ __forceinline__ void gather_v6(const float *__restrict__ s_val, const uint16_t *__restrict__ s_off, const float4 *__restrict__ s_d,
+	int r0, int r1, int lane, float &sx, float &sy, float &sz)
+{
+	sx = 0.f; sy = 0.f; sz = 0.f;
+	// pair p of the slice lives at rows (2p, 2p + 1) of the ordinary layout, re-read here as [pair][lane] of 32 / 64 bits
+	const float2 *v = (const float2 *)(s_val + r0 * 32) + lane;
+	const unsigned int *c = (const unsigned int *)(s_off + r0 * 32) + lane;
+	const unsigned char *base = (const unsigned char *)s_d;
+	const int np = (r1 - r0) >> 1;
+	for (int p = 0; p < np; p += 4) {
+		unsigned int cc[4]; float2 a[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int pp = min(p + j, np - 1);
+			cc[j] = c[pp * 32];
+			a[j] = v[pp * 32];
+			if (p + j >= np) a[j] = make_float2(0.f, 0.f);
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const float4 d0 = *(const float4 *)(base + (cc[j] & 0xffffu)), d1 = *(const float4 *)(base + (cc[j] >> 16));
+			sx = fmaf(a[j].x, d0.x, sx); sy = fmaf(a[j].x, d0.y, sy); sz = fmaf(a[j].x, d0.z, sz);
+			sx = fmaf(a[j].y, d1.x, sx); sy = fmaf(a[j].y, d1.y, sy); sz = fmaf(a[j].y, d1.z, sz);
+		}
+	}
+}
+
+// v7: the order of the loads is FORCED (volatile asm): all 8 index loads, all 8 value loads, all 8 gathers, then the
+// multiply-adds on two independent accumulator sets.  ptxas schedules v0's batch as 2 + 6 (two dependent rounds).
+__device__ __forceinline__ unsigned int lds_u16(const void *p) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"((unsigned int)__cvta_generic_to_shared(p))); return v; }
+__device__ __forceinline__ float lds_f32(const void *p) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned int)__cvta_generic_to_shared(p))); return v; }
+__device__ __forceinline__ float4 lds_f4(unsigned int addr) { float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v; }
+__device__ __forceinline__ void gather_v7(const float *__restrict__ s_val, const uint16_t *__restrict__ s_col, const float4 *__restrict__ s_d,
+	int r0, int r1, int lane, float &sx, float &sy, float &sz)
+{
+	float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+	const float *v = s_val + r0 * 32 + lane;
+	const uint16_t *c = s_col + r0 * 32 + lane;
+	const unsigned int base = (unsigned int)__cvta_generic_to_shared(s_d);
+	const int n = r1 - r0;
+	for (int r = 0; r < n; r += 8) {
+		unsigned int cc[8]; float a[8]; float4 dv[8];
+		int rr[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) rr[j] = min(r + j, n - 1) * 32;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) cc[j] = lds_u16(c + rr[j]);
+#pragma unroll
+		for (int j = 0; j < 8; ++j) a[j] = lds_f32(v + rr[j]);
+#pragma unroll
+		for (int j = 0; j < 8; ++j) dv[j] = lds_f4(base + cc[j] * 16);
+#pragma unroll
+		for (int j = 0; j < 8; ++j) if (r + j >= n) a[j] = 0.f;
+#pragma unroll
+		for (int j = 0; j < 8; j += 2) {
+			ax = fmaf(a[j], dv[j].x, ax); ay = fmaf(a[j], dv[j].y, ay); az = fmaf(a[j], dv[j].z, az);
+			bx = fmaf(a[j + 1], dv[j + 1].x, bx); by = fmaf(a[j + 1], dv[j + 1].y, by); bz = fmaf(a[j + 1], dv[j + 1].z, bz);
+		}
+	}
+	sx = ax + bx; sy = ay + by; sz = az + bz;
+}
+
 template <int V>
 __global__ void __launch_bounds__(512, 1) bench_kernel(const float *g_val, const uint16_t *g_col, const int *g_srow, int n_loc, int n_rows, int n_slices,
 	int active_warps, int reps, int sync_mode, long long *out)
@@ -121,7 +210,10 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(const float *g_val, const
 			if (V == 0) gather_v0(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
 			else if (V == 1) gather_v1(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
 			else if (V == 2) gather_v2(s_val, s_col, s_d, r0, r0 + ((r1 - r0) & ~7), lane, sx, sy, sz);
-			else gather_v3(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
+			else if (V == 3) gather_v3(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
+			else if (V == 4) gather_v4(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
+			else if (V == 6) gather_v6(s_val, s_col, s_d, r0, r0 + ((r1 - r0) & ~1), lane, sx, sy, sz);
+			else gather_v7(s_val, s_col, s_d, r0, r1, lane, sx, sy, sz);
 			// the update: write the node's own entry (as the sweep does)
 			const int l = (sl * 32 + lane) % n_loc;
 			float4 dold = s_d[l];
@@ -173,14 +265,21 @@ int main()
 	CK(cudaMemcpy(d_srow, srow.data(), srow.size() * 4, cudaMemcpyHostToDevice));
 	const size_t smem = 16 * (size_t)n_loc + 6 * 32 * (size_t)n_rows;
 	printf("part: %d local nodes, %d rows, %d slices, %zu B shared memory\n", n_loc, n_rows, n_slices, smem);
-	const void *kern[4] = {(const void *)bench_kernel<0>, (const void *)bench_kernel<1>, (const void *)bench_kernel<2>, (const void *)bench_kernel<3>};
-	for (int v = 0; v < 4; ++v) CK(cudaFuncSetAttribute(kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const void *kern[8] = {(const void *)bench_kernel<0>, (const void *)bench_kernel<1>, (const void *)bench_kernel<2>, (const void *)bench_kernel<3>,
+		(const void *)bench_kernel<4>, (const void *)bench_kernel<4>, (const void *)bench_kernel<6>, (const void *)bench_kernel<7>};
+	for (int v = 0; v < 8; ++v) CK(cudaFuncSetAttribute(kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	uint16_t *d_off[6];
+	for (int p = 0; p < 6; ++p) {
+		std::vector<uint16_t> o(pats[p].size());
+		for (size_t i = 0; i < o.size(); ++i) o[i] = (uint16_t)(pats[p][i] * 16);
+		CK(cudaMalloc(&d_off[p], o.size() * 2)); CK(cudaMemcpy(d_off[p], o.data(), o.size() * 2, cudaMemcpyHostToDevice));
+	}
 	const int reps = 200;
-	for (int pat = 0; pat < 6; ++pat)
-		for (int v : {0, 2})
-			for (int sync_mode = 0; sync_mode < (pat < 2 ? 2 : 1); ++sync_mode)
+	for (int pat = 1; pat < 3; ++pat)
+		for (int v : {0, 7})
+			for (int sync_mode = 0; sync_mode < 1; ++sync_mode)
 				for (int aw : {1, 4, 8, 16}) {
-					const uint16_t *dc = d_pat[pat];
+					const uint16_t *dc = (v >= 4 && v != 7) ? d_off[pat] : d_pat[pat];
 					int nl = n_loc, nr = n_rows, ns = n_slices, r = reps, sm = sync_mode;
 					void *args[] = {&d_val, &dc, &d_srow, &nl, &nr, &ns, &aw, &r, &sm, &d_out};
 					for (int w = 0; w < 2; ++w) CK(cudaLaunchKernel(kern[v], dim3(148), dim3(512), args, smem, 0));
