@@ -199,9 +199,10 @@ class DeviceSolver(object):
         self._ck(_cuda.admm_b200_time_kernels(self.h, int(reps), _dp(out)))
         return {"local_ms": out[0], "assemble_ms": out[1], "global_ms": out[2]}
 
-    def set_deferred_timers(self, on=True):
-        """Timed steps without a synchronise per step (admm_b200_set_deferred_timers); read with collect_timers()."""
-        self._ck(_cuda.admm_b200_set_deferred_timers(self.h, int(bool(on))))
+    def set_deferred_timers(self, on=True, stride=1):
+        """Timed steps without a synchronise per step (admm_b200_set_deferred_timers); read with collect_timers().
+        stride = n > 1: only every n-th step records its events (and is counted by collect_timers)."""
+        self._ck(_cuda.admm_b200_set_deferred_timers(self.h, int(max(1, stride)) if on else 0))
 
     def collect_timers(self):
         """Sums over all steps since the last collection: RuntimeData fields + 'steps' (admm_b200_collect_timers)."""

@@ -55,6 +55,7 @@ SOLVER_NAMES = {0: "LDLT", 1: "NodalMultiColorGS 30 sweeps omega=1.9", 2: "Uzawa
 # N ranks vs one GPU after the same steps (same colours; only the summation order of a vertex's element shares and the
 # fp32 rounding inside the sweeps differ): max |dx| / bounding-box diagonal.  fp32 has 6e-8; W + 2K + 2 steps x 20 ADMM
 # iterations amplify it (measured at N = 2 after 25 steps: 4.7e-7); the fp32 gate of SURVEY.md 8d is 1e-4.
+TIMER_STRIDE = 4           # per-phase / per-kernel CUDA events on every 4th step of a timed region (see measure(): timed)
 PARITY_TOL_REL = 2e-6
 
 
@@ -378,11 +379,13 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
 
     def timed(fn, n):
         """n calls of fn bracketed by barrier+sync, CUDA events on the solver's stream, max over ranks.  The per-phase and
-        per-kernel events of every step are recorded inside this region but read only after it (deferred timers,
-        admm_b200_collect_timers): no host synchronise per step, the next step's launches queue behind the running one."""
+        per-kernel events are recorded inside this region -- on every TIMER_STRIDE-th step, an event costs ~3 us of stream
+        time and a fully instrumented step carries 0.64 ms of them (tools/timer_overhead.py) -- and read only after it
+        (deferred timers, admm_b200_collect_timers): no host synchronise per step, the next step's launches queue behind
+        the running one.  acc holds SUMS over the sampled steps, acc["steps"] of them."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sol.set_timers(False)
-        dev.set_deferred_timers(True)
+        dev.set_deferred_timers(True, stride=TIMER_STRIDE)
         barrier()
         with torch.cuda.stream(stream):
             e0.record(stream)
@@ -394,7 +397,7 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
         acc["kernels"] = {k: list(v) for k, v in dev.kernel_times().items()}   # events tightly around each hot kernel launch
         dev.set_deferred_timers(False)
         sol.set_timers(True)
-        assert acc["steps"] == n, acc
+        assert acc["steps"] == (n + TIMER_STRIDE - 1) // TIMER_STRIDE, acc
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -490,7 +493,8 @@ def run_b200(args):
 
     # ---- roofline: algorithmic bytes / CUDA-event durations from the timed region ----
     peak, peak_src = measured_peaks()
-    n_launch = K * iters
+    n_sampled = max(int(acc["steps"]), 1)   # steps of the timed region that carried events
+    n_launch = n_sampled * iters
     # average launch duration of each hot kernel: CUDA events recorded on the solver's stream right before and after
     # every launch inside the timed region (admm_b200_kernel_times).  The step_breakdown phases below also contain
     # the helpers (scratch memset, the queue consumer of degenerate elements) and the gaps between launches.
@@ -560,8 +564,10 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / K, "api": "admm_b200::Solver::step() -> admm_b200_step_host"},
         "gpu_launches": int(m["launches"]),
         "roofline": roofline, "kernels": kernels,
-        "step_breakdown_ms": {"local": acc["local_ms"] / K, "assemble": acc["assemble_ms"] / K, "solve": (acc["global_ms"] - acc["assemble_ms"]) / K,
-                              "device_step": acc["step_ms"] / K},
+        "step_breakdown_ms": {"local": acc["local_ms"] / n_sampled, "assemble": acc["assemble_ms"] / n_sampled, "solve": (acc["global_ms"] - acc["assemble_ms"]) / n_sampled,
+                              "device_step": acc["step_ms"] / n_sampled},
+        "timer_sampling": {"stride": TIMER_STRIDE, "sampled_steps": n_sampled, "of_steps": K,
+                           "note": "step_breakdown_ms, roofline and kernels come from CUDA events recorded inside the timed region on every %d-th step; an event costs ~3 us of stream time, so an instrumented step is ~0.6 ms longer than an uninstrumented one (tools/timer_overhead.py)" % TIMER_STRIDE},
         "clocks": m["clk"], "finite": finite,
     }
     if scene["kind"] == "tet":
