@@ -55,6 +55,7 @@ SOLVER_NAMES = {0: "LDLT", 1: "NodalMultiColorGS 30 sweeps omega=1.9", 2: "Uzawa
 # N ranks vs one GPU after the same steps (same colours; only the summation order of a vertex's element shares and the
 # fp32 rounding inside the sweeps differ): max |dx| / bounding-box diagonal.  fp32 has 6e-8; W + 2K + 2 steps x 20 ADMM
 # iterations amplify it (measured at N = 2 after 25 steps: 4.7e-7); the fp32 gate of SURVEY.md 8d is 1e-4.
+WEAK_TIMEOUT_S = 420       # watchdog of the optional 8M-tet leg at N = 8 (normally ~100 s incl. building the mesh)
 TIMER_STRIDE = 4           # per-phase / per-kernel CUDA events on every 4th step of a timed region (see measure(): timed)
 PARITY_TOL_REL = 2e-6
 
@@ -373,6 +374,12 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
     n_colors = len(sol.colors()) if args.linsolver == 1 else 0
 
     def barrier():
+        # This rank's solver work must be FINISHED before the NCCL kernel of dist.barrier() is launched: the solve kernel is
+        # a cooperative launch that needs every SM (with 1M tets per GPU 214 KB of shared memory each) and waits for its
+        # neighbours on other GPUs; an NCCL kernel that slips in between two queued solver kernels on one rank and
+        # between two others on the next one holds an SM on both, neither rank's next solve kernel can be scheduled, and
+        # the NCCL kernels wait for each other's ranks forever.  (Seen once: the 8M-tet leg at N = 8, round 2.)
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -579,8 +586,22 @@ def run_b200(args):
     if world == 8 and args.workload == "beam_1m" and not args.no_weak:
         wargs = argparse.Namespace(**vars(args))
         wargs.workload = "beam_8m"
+        # Safety net: this extra leg must never cost the main line.  If it has not finished after WEAK_TIMEOUT_S (a cross-GPU
+        # wait that never ends cannot be interrupted from inside the process), rank 0 prints the line without it and every
+        # rank leaves; the driver's clock then still sees a complete run.
+        import threading
+
+        def give_up():
+            if rank == 0:
+                line["weak_8m"] = {"value": None, "error": "the 8M-tet leg did not finish within %d s and was abandoned" % WEAK_TIMEOUT_S}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        watchdog = threading.Timer(WEAK_TIMEOUT_S, give_up)
+        watchdog.daemon = True
+        watchdog.start()
         wscene = make_scene(pkg, "beam_8m")
         wm = measure(pkg, wargs, wscene, torch, dist, stream, rank, world, local_rank, min(K, 5), 3)
+        watchdog.cancel()
         line["weak_8m"] = {"value": iters * min(K, 5) / (wm["ms_res"] * 1e-3), "unit": "ADMM iters/s", "e2e": iters * min(K, 5) / (wm["ms_e2e"] * 1e-3),
                            "workload": workload_name(wargs, wscene), "n_elements_this_rank": wm["n_el_rank"], "steps": min(K, 5),
                            "vs_single_gpu_1m": iters * min(K, 5) / (wm["ms_res"] * 1e-3) / (parity["single_gpu_value"] if parity and parity.get("single_gpu_value") else float("nan")),
