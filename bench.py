@@ -375,10 +375,11 @@ def measure(pkg, args, scene, torch, dist, stream, rank, world, local_rank, K, W
 
     def barrier():
         # This rank's solver work must be FINISHED before the NCCL kernel of dist.barrier() is launched: the solve kernel is
-        # a cooperative launch that needs every SM (with 1M tets per GPU 214 KB of shared memory each) and waits for its
+        # a cooperative launch that needs every SM whole (512 threads x 128 registers per CTA) and waits for its
         # neighbours on other GPUs; an NCCL kernel that slips in between two queued solver kernels on one rank and
         # between two others on the next one holds an SM on both, neither rank's next solve kernel can be scheduled, and
-        # the NCCL kernels wait for each other's ranks forever.  (Seen once: the 8M-tet leg at N = 8, round 2.)
+        # the NCCL kernels wait for each other's ranks forever.  (Seen once, at N = 8 in round 2, when the sampled timers let
+        # the host finish queueing the steps long before the GPU had run them.)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
