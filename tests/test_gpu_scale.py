@@ -29,7 +29,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MU, LAM = scenes.lame(*scenes.LAME_SOFT)
 GATE = 1e-4          # x bbox diagonal
-TIGHT = 5e-6         # x bbox diagonal: what the tests assert (measured: <= 1.6e-7 on the beams, profiles/parity_r02i_gpu.jsonl)
+TIGHT = 5e-6         # x bbox diagonal: what the tests assert (measured: <= 1.6e-7 on the beams, profiles/parity_r03a_gpu.jsonl)
 DENSITY = 1522.0
 
 
