@@ -285,6 +285,7 @@ public:
 //
 //	Passive collision objects handled inside the GS sweep (src/PassiveObject.hpp:32-64)
 //
+class DynamicCollision { public: virtual ~DynamicCollision() {} }; // src/DynamicObject.hpp:31-48, placeholder: see Solver::add_dynamic_collider
 class PassiveCollision { public: virtual ~PassiveCollision() {} virtual int kind() const = 0; virtual void params(double *p4) const = 0; };
 class Floor : public PassiveCollision { public: double m_y; Floor(double y) : m_y(y) {} int kind() const { return ADMM_B200_FLOOR; } void params(double *p) const { p[0] = m_y; p[1] = p[2] = p[3] = 0; } };
 class Sphere : public PassiveCollision { public: Vec3 center; double rad; Sphere(const Vec3 &c, double r) : center(c), rad(r) {} int kind() const { return ADMM_B200_SPHERE; } void params(double *p) const { p[0] = center[0]; p[1] = center[1]; p[2] = center[2]; p[3] = rad; } };
@@ -380,6 +381,9 @@ public:
 	}
 	virtual void set_pins(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
 	virtual void add_obstacle(std::shared_ptr<PassiveCollision> obj) { passive_objs.emplace_back(obj); }
+	// src/Solver.hpp:93: self collision (DynamicCollision, BVH) is not on the GPU path; the signature is
+	// kept so that callers compile, and says so loudly instead of ignoring the collider
+	virtual void add_dynamic_collider(std::shared_ptr<DynamicCollision>) { throw std::runtime_error("**admm_b200::Solver::add_dynamic_collider Error: self collision is not on the GPU path"); }
 	virtual bool initialize(const Settings &settings_ = Settings());
 	virtual void step();
 	virtual const RuntimeData &runtime_data() { return m_runtime; }
